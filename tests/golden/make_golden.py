@@ -1,0 +1,239 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by running the REFERENCE ITSELF (jeffsonyu/VTacO,
+mounted read-only at /root/reference) on CPU in the build container.
+
+The reference is Python and cannot travel to the GPU box, so its outputs are
+frozen here as small fixtures.  Run:  python tests/golden/make_golden.py
+
+What is shimmed (absent third-party packages, no network):
+  torch_scatter  -> oracle.convonet.scatter_mean / scatter_max (published 2.0.9 semantics)
+  pykdtree, pybullet, trimesh, igl, plyfile, tensorboardX, skimage.measure,
+  matplotlib, mpl_toolkits, chumpy-free: only imported, never called on this path.
+  ./data/VTacO_mesh/depth_origin.txt — read at import time by
+  src/conv_onet/{generation,training,inferencing}.py:17-18.
+Nothing from the reference tree is copied; only its numerical outputs are saved.
+"""
+import os
+import sys
+import types
+import tempfile
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get('VTACO_REF', '/root/reference')
+sys.path.insert(0, ROOT)
+
+
+def install_shims():
+    from oracle import convonet as oc
+
+    def mod(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+
+    def _scatter_mean(src, index, dim=-1, out=None, dim_size=None):
+        return oc.scatter_mean(src, index, dim_size=dim_size, out=out)
+
+    def _scatter_max(src, index, dim=-1, out=None, dim_size=None):
+        return oc.scatter_max(src, index, dim_size), None
+
+    mod('torch_scatter', scatter_mean=_scatter_mean, scatter_max=_scatter_max)
+    k = mod('pykdtree')
+    k.kdtree = mod('pykdtree.kdtree', KDTree=object)
+    mod('pybullet')
+    mod('trimesh', Trimesh=object)
+    mod('igl')
+    mod('plyfile', PlyData=object, PlyElement=object)
+    mod('tensorboardX', SummaryWriter=object)
+    sk = mod('skimage')
+    sk.measure = mod('skimage.measure', marching_cubes=None, block_reduce=None)
+    mpl = mod('matplotlib', use=lambda *a, **k: None)
+    mpl.pyplot = mod('matplotlib.pyplot')
+    mt = mod('mpl_toolkits')
+    mt.mplot3d = mod('mpl_toolkits.mplot3d', Axes3D=object)
+    for name in ('chumpy',):
+        if name not in sys.modules:
+            try:
+                __import__(name)
+            except Exception:
+                mod(name)
+
+
+def import_reference():
+    scratch = tempfile.mkdtemp(prefix='vtaco_ref_')
+    os.makedirs(os.path.join(scratch, 'data', 'VTacO_mesh'))
+    np.savetxt(os.path.join(scratch, 'data', 'VTacO_mesh', 'depth_origin.txt'), np.zeros(240 * 320))
+    os.chdir(scratch)
+    install_shims()
+    sys.path.insert(0, REF)
+    from src import common, layers  # noqa
+    from src.encoder import encoder_dict
+    from src.conv_onet import models, generation
+    return common, encoder_dict, models, generation
+
+
+def rs_randn(seed, *shape, scale=1.0):
+    """Stable cross-version generator (numpy legacy RandomState)."""
+    return (np.random.RandomState(seed).randn(*shape) * scale).astype(np.float32)
+
+
+def rs_uniform(seed, lo, hi, *shape):
+    return np.random.RandomState(seed).uniform(lo, hi, size=shape).astype(np.float32)
+
+
+def randomise(module, seed):
+    """Default init, then every parameter re-drawn from a stable stream so the
+    fixture does not depend on torch's RNG; ResnetBlockFC.fc_1.weight (zero-init
+    in src/layers.py:39) becomes N(0, 0.1^2) so the residual branch is exercised."""
+    rs = np.random.RandomState(seed)
+    with torch.no_grad():
+        for name, prm in sorted(module.named_parameters()):
+            fan_in = prm.shape[1] if prm.dim() > 1 else prm.shape[0]
+            bound = 1.0 / np.sqrt(max(fan_in, 1))
+            if name.endswith('fc_1.weight'):
+                val = rs.randn(*prm.shape) * 0.1
+            else:
+                val = rs.uniform(-bound, bound, size=tuple(prm.shape))
+            prm.copy_(torch.from_numpy(val.astype(np.float32)))
+
+
+def sd_np(module, prefix=''):
+    return {prefix + k: v.detach().cpu().numpy() for k, v in module.state_dict().items()}
+
+
+def synthetic_cloud(seed, n_visual, n_tactile_per_tip=128, n_tips=5):
+    """visual points uniform in [-.5,.5]^3 + 5 tactile Gaussian blobs
+    (sigma .01) + N(0,.005^2) noise."""
+    rs = np.random.RandomState(seed)
+    vis = rs.uniform(-0.5, 0.5, size=(n_visual, 3))
+    tips = rs.uniform(-0.35, 0.35, size=(n_tips, 3))
+    tac = (tips[:, None, :] + rs.randn(n_tips, n_tactile_per_tip, 3) * 0.01).reshape(-1, 3)
+    pts = np.concatenate([vis, tac], 0) + rs.randn(n_visual + n_tips * n_tactile_per_tip, 3) * 0.005
+    return pts.astype(np.float32), tips.astype(np.float32)
+
+
+def main():
+    torch.set_num_threads(4)
+    common, encoder_dict, models, generation = import_reference()
+    out = {}
+
+    # ---- G1: coordinate helpers (src/common.py:268-348) ------------------- #
+    pts = rs_uniform(1, -0.62, 0.62, 1, 4096, 3)
+    edge = np.array([[0.55, -0.55, 0.0], [0.5500055, 0.55055, -0.5500055], [0.7, -0.7, 0.55],
+                     [0.549999, -0.549999, 0.275], [1e-8, -1e-8, 0.0], [np.float32(0.55) - 1e-7, 0.3, -0.3]],
+                    dtype=np.float32)
+    pts[0, :edge.shape[0]] = edge
+    g = {'p': pts}
+    tp = torch.from_numpy(pts)
+    for plane in ('xz', 'xy', 'yz'):
+        xy = common.normalize_coordinate(tp.clone(), padding=0.1, plane=plane)
+        g['norm_' + plane] = xy.numpy()
+        for R in (32, 64, 128):
+            g['idx_%s_%d' % (plane, R)] = common.coordinate2index(xy, R).numpy()
+    pn = common.normalize_3d_coordinate(tp.clone(), padding=0.1)
+    g['norm_grid'] = pn.numpy()
+    for R in (32, 64, 128):
+        g['idx_grid_%d' % R] = common.coordinate2index(pn, R, coord_type='3d').numpy()
+    for nx in (8, 32, 128, 256):
+        g['axis_%d' % nx] = (1.1 * common.make_3d_grid((-0.5,) * 3, (0.5,) * 3, (nx, 1, 1)))[:, 0].numpy()
+    g['grid3_4'] = common.make_3d_grid((-0.5,) * 3, (0.5,) * 3, (4, 3, 2)).numpy()
+    np.savez_compressed(os.path.join(HERE, 'coords.npz'), **g)
+
+    # ---- G2: LocalDecoder (decoder.py:9-161), grid + tri-plane + mixed ----- #
+    for leaky, contact, tag in ((False, True, 'relu'), (True, False, 'leaky')):
+        dec = models.decoder_dict['simple_local'](dim=3, c_dim=32, padding=0.1, with_contact=contact,
+                                                  sample_mode='bilinear', hidden_size=32, leaky=leaky)
+        randomise(dec, 11 if not leaky else 12)
+        dec.eval()
+        B, N, Rg, Rp = 2, 1536, 16, 32
+        p = rs_uniform(21, -0.6, 0.6, B, N, 3)
+        p[0, :edge.shape[0]] = edge
+        feats = {'grid': rs_randn(31, B, 32, Rg, Rg, Rg), 'xz': rs_randn(32, B, 32, Rp, Rp),
+                 'xy': rs_randn(33, B, 32, Rp, Rp), 'yz': rs_randn(34, B, 32, Rp, Rp)}
+        c_img = rs_randn(35, B, N, 32)
+        c_img[:, ::3] = 0.0
+        g = {'p': p, 'c_img': c_img, 'feat_seeds': np.array([31, 32, 33, 34]),
+             'feat_shapes': np.array([Rg, Rp])}
+        g.update(sd_np(dec, 'w.'))
+        tp, tci = torch.from_numpy(p), torch.from_numpy(c_img)
+        combos = {'grid': ['grid'], 'tri': ['xz', 'xy', 'yz'], 'all': ['grid', 'xz', 'xy', 'yz'], 'xz': ['xz']}
+        with torch.no_grad():
+            for cname, keys in combos.items():
+                cp = {k: torch.from_numpy(feats[k]) for k in keys}
+                for mode in ('bilinear', 'nearest'):
+                    dec.sample_mode = mode
+                    g['fwd_%s_%s' % (cname, mode)] = dec(tp, cp).numpy()
+                    g['img_%s_%s' % (cname, mode)] = dec.forward_img(tp, cp, tci).numpy()
+                    if contact:
+                        o, oc_ = dec.forward_contact(tp, cp)
+                        g['con_%s_%s' % (cname, mode)] = np.stack([o.numpy(), oc_.numpy()])
+                dec.sample_mode = 'bilinear'
+            g['sample_grid'] = dec.sample_grid_feature(tp, torch.from_numpy(feats['grid'])).numpy()
+            g['sample_xz'] = dec.sample_plane_feature(tp, torch.from_numpy(feats['xz']), plane='xz').numpy()
+            g['sample_yz'] = dec.sample_plane_feature(tp, torch.from_numpy(feats['yz']), plane='yz').numpy()
+        np.savez_compressed(os.path.join(HERE, 'decoder_%s.npz' % tag), **g)
+
+    # ---- G3: LocalPoolPointnet PointNet part (pointnet.py:135-172) --------- #
+    for tag, kw in (('grid', dict(plane_type='grid', grid_resolution=32)),
+                    ('tri', dict(plane_type=['xz', 'xy', 'yz'], plane_resolution=32)),
+                    ('all_mean', dict(plane_type=['xz', 'xy', 'yz', 'grid'], plane_resolution=16,
+                                      grid_resolution=16, scatter_type='mean'))):
+        enc = encoder_dict['pointnet_local_pool'](dim=3, c_dim=32, padding=0.1, hidden_dim=32, **kw)
+        randomise(enc, 41)
+        enc.eval()
+        cloud0, _ = synthetic_cloud(51, 600, 40)
+        cloud1, _ = synthetic_cloud(52, 600, 40)
+        p = np.stack([cloud0, cloud1])
+        p[1, :edge.shape[0]] = edge
+        g = {'p': p}
+        g.update(sd_np(enc, 'w.'))
+        with torch.no_grad():
+            fea = enc(torch.from_numpy(p))
+        for k, v in fea.items():
+            v = v.numpy()
+            flat = v.reshape(v.shape[0], v.shape[1], -1)
+            occ = np.abs(flat).sum(1) != 0
+            b_idx, cell = np.nonzero(occ)
+            g['fea_%s_shape' % k] = np.array(v.shape)
+            g['fea_%s_b' % k] = b_idx.astype(np.int32)
+            g['fea_%s_cell' % k] = cell.astype(np.int32)
+            g['fea_%s_val' % k] = flat[b_idx, :, cell]
+        g['key_order'] = np.array(list(fea.keys()))
+        np.savez_compressed(os.path.join(HERE, 'encoder_%s.npz' % tag), **g)
+
+    # ---- G4: Generator3D.eval_points on the dense lattice (generation.py:338-383)
+    dec = models.decoder_dict['simple_local'](dim=3, c_dim=32, padding=0.1, with_contact=False,
+                                              sample_mode='bilinear', hidden_size=32)
+    randomise(dec, 61)
+    net = models.ConvolutionalOccupancyNetwork(dec, None, None, None, None, device='cpu')
+    nx = 32
+    gen = generation.Generator3D(net, device='cpu', resolution0=nx // 4, with_img=True, padding=0.1,
+                                 input_type='pointcloud', points_batch_size=10000)
+    pointsf = 1.1 * common.make_3d_grid((-0.5,) * 3, (0.5,) * 3, (nx,) * 3)
+    Rg = 16
+    c = {'grid': torch.from_numpy(rs_randn(71, 1, 32, Rg, Rg, Rg))}
+    tips = rs_uniform(72, -0.3, 0.3, 5, 3)
+    tip_feat = rs_randn(73, 5, 32)
+    touch = np.array([1, 0, 1, 1, 0], dtype=bool)
+    from oracle.convonet import fingertip_c_img
+    c_img_all = fingertip_c_img(pointsf, tips, torch.from_numpy(tip_feat), touch, 0.05)
+    vals_img = gen.eval_points(pointsf, c, c_img_all.unsqueeze(0)).numpy()
+    gen.with_img = False
+    vals = gen.eval_points(pointsf, c).numpy()
+    g = {'nx': np.array(nx), 'feat_seed': np.array(71), 'Rg': np.array(Rg), 'tips': tips, 'tip_feat': tip_feat,
+         'touch': touch, 'logits_img': vals_img, 'logits': vals,
+         'c_img_rows': np.nonzero(np.abs(c_img_all.numpy()).sum(1))[0].astype(np.int32)}
+    g.update(sd_np(dec, 'w.'))
+    np.savez_compressed(os.path.join(HERE, 'eval_points.npz'), **g)
+
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith('.npz'):
+            print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, 'KiB')
+
+
+if __name__ == '__main__':
+    main()
