@@ -1,0 +1,165 @@
+/*
+ * vtaco_b200.h — C ABI of the B200-native convolutional-occupancy hot path.
+ *
+ * Drop-in boundary for jeffsonyu/VTacO's conv-occupancy path.  The reference has
+ * no FFI layer of its own (it is pure Python/PyTorch): its "operator API" is the
+ * nn.Module interface of src/encoder/pointnet.py and
+ * src/conv_onet/models/decoder.py, which vtaco_b200/ mirrors in Python.  Below
+ * those modules every arithmetic step goes through the entry points declared
+ * here; each one cites the reference code it replaces.
+ *
+ * Conventions
+ *  - plain pointers + sizes only; every pointer is a DEVICE pointer unless the
+ *    name ends in _host.  No torch types, no allocation, no global state.
+ *  - `stream` is a cudaStream_t passed as void*; all work is enqueued on it and
+ *    the call returns without synchronising.
+ *  - return value: 0 on success, negative vtaco_status on error (never throws).
+ *  - all feature tensors are fp32; "channels-last" (CL) means the channel index
+ *    is the fastest one: grid [B][Rz][Ry][Rx][C], plane [B][R_i1][R_i0][C].
+ */
+#ifndef VTACO_B200_H
+#define VTACO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VTACO_ABI_VERSION 1
+
+typedef enum {
+  VTACO_OK = 0,
+  VTACO_ERR_INVALID_ARG = -1,   /* null pointer, bad size, bad enum */
+  VTACO_ERR_UNSUPPORTED = -2,   /* shape outside what the kernels implement */
+  VTACO_ERR_CUDA = -3,          /* a CUDA runtime call failed (see vtaco_last_cuda_error) */
+  VTACO_ERR_CAPACITY = -4       /* caller-supplied output capacity too small */
+} vtaco_status;
+
+/* plane / volume kinds, in the reference's key vocabulary */
+enum { VTACO_PLANE_XZ = 0, VTACO_PLANE_XY = 1, VTACO_PLANE_YZ = 2, VTACO_GRID = 3 };
+
+/* `tensor / python_scalar`: CUDA ATen multiplies by fp32(1/d), CPU ATen divides */
+enum { VTACO_DIV_RECIPROCAL = 0, VTACO_DIV_TRUE = 1 };
+
+enum { VTACO_SAMPLE_BILINEAR = 0, VTACO_SAMPLE_NEAREST = 1 };
+
+int vtaco_abi_version(void);
+const char* vtaco_status_string(int status);
+/* cudaGetErrorString of the last CUDA error seen by this library on this thread */
+const char* vtaco_last_cuda_error(void);
+
+/* ------------------------------------------------------------------------- *
+ * (1) point -> cell index.
+ * Replaces normalize_coordinate (src/common.py:268-291) or
+ * normalize_3d_coordinate (:293-309) followed by coordinate2index (:333-348).
+ * p: [n_points][3].  kind: VTACO_PLANE_* or VTACO_GRID.  Writes int32 and/or
+ * int64 flat cell indices (either pointer may be NULL) and, if non-NULL, the
+ * normalised coordinates ([n_points][2] for planes, [n_points][3] for the grid).
+ * ------------------------------------------------------------------------- */
+int vtaco_point_to_cell(const float* p, int64_t n_points, double padding, int reso, int kind,
+                        int div_mode, int32_t* idx32, int64_t* idx64, float* coord, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * (2) channels-first -> channels-last relayout of a feature tensor.
+ * src [B][C][S] -> dst [B][S][C]  (S = R*R or R*R*R).  The decoder kernel
+ * gathers from CL so one interpolation tap is one 128-byte line (C = 32).
+ * ------------------------------------------------------------------------- */
+int vtaco_relayout_cl(const float* src, float* dst, int B, int C, int64_t S, void* stream);
+/* inverse: [B][S][C] -> [B][C][S] (API-facing tensors are channels-first) */
+int vtaco_relayout_cf(const float* src, float* dst, int B, int C, int64_t S, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * (3) fused LocalDecoder forward.
+ * Replaces LocalDecoder.forward / forward_img / forward_contact
+ * (src/conv_onet/models/decoder.py:71-161): normalise + clamp, bi/trilinear
+ * grid_sample (border, align_corners=True) of every present feature tensor,
+ * sum, fc_p | fc_p_img, n_blocks x {fc_c[i], ResnetBlockFC}, fc_out
+ * [, fc_out_contact] — one kernel, activations never leave the SM.
+ * In dense mode it also replaces make_3d_grid (src/common.py:178-197) and the
+ * chunk loop of Generator3D.eval_points (src/conv_onet/generation.py:338-383).
+ *
+ * Packed weight buffer (fp32, device), hidden = c_dim = 32, K-major ("[in][out]"):
+ *   off 0      fc_p.weight^T        [3][32]
+ *   off 96     fc_p.bias            [32]
+ *   off 128    fc_p_img.weight[:, :3]^T [3][32]
+ *   off 224    fc_p_img.bias        [32]
+ *   off 256    fc_p_img.weight[:, 3:]^T [32][32]
+ *   off 1280   per block i (stride 3168):
+ *                fc_c[i].weight^T [32][32], fc_c[i].bias [32],
+ *                blocks[i].fc_0.weight^T [32][32], .bias [32],
+ *                blocks[i].fc_1.weight^T [32][32], .bias [32]
+ *   off 1280+3168*n_blocks  fc_out.weight [32], fc_out_contact.weight [32],
+ *                fc_out.bias, fc_out_contact.bias, 2 pad
+ * ------------------------------------------------------------------------- */
+#define VTACO_DEC_HIDDEN 32
+#define VTACO_DEC_OFF_WP 0
+#define VTACO_DEC_OFF_BP 96
+#define VTACO_DEC_OFF_WPI 128
+#define VTACO_DEC_OFF_BPI 224
+#define VTACO_DEC_OFF_WIMG 256
+#define VTACO_DEC_OFF_BLOCKS 1280
+#define VTACO_DEC_BLOCK_STRIDE 3168
+#define VTACO_DEC_TAIL 68
+#define VTACO_DEC_PACKED_FLOATS(n_blocks) (VTACO_DEC_OFF_BLOCKS + VTACO_DEC_BLOCK_STRIDE * (n_blocks) + VTACO_DEC_TAIL)
+#define VTACO_MAX_TIPS 8
+
+typedef struct vtaco_decoder_args {
+  /* ---- queries ---- */
+  const float* p;          /* flat mode: [B][N][3]; NULL selects dense mode            */
+  int32_t B;               /* batch (samples; each has its own feature tensors)          */
+  int64_t N;               /* flat mode: queries per sample                              */
+  /* dense mode: the lattice (1+padding)*make_3d_grid(nx^3); query (ix,iy,iz) has
+   * p = (axis[ix], axis[iy], axis[iz]); rows ix in [x0, x1) are evaluated (slab).  */
+  const float* axis;       /* [nx] exact axis values (host computes them like the reference) */
+  int32_t nx, x0, x1;
+  /* ---- features, channels-last; NULL = key absent.  Order of summation is
+   * grid, xz, xy, yz as in decoder.py:75-82 ---- */
+  const float* grid;       /* [B][Rg][Rg][Rg][32] */
+  const float* plane[3];   /* xz, xy, yz: [B][Rp][Rp][32] */
+  int32_t reso_grid, reso_plane;
+  double padding;          /* python float of the reference (0.1); constants are formed in double */
+  int32_t div_mode;        /* VTACO_DIV_* */
+  int32_t sample_mode;     /* VTACO_SAMPLE_* */
+  /* ---- network ---- */
+  const float* weights;    /* packed, see above */
+  int32_t n_blocks;
+  int32_t leaky;           /* activation before fc_out: 0 ReLU, 1 LeakyReLU(0.2)         */
+  int32_t use_img;         /* 0: net = fc_p(p); 1: net = fc_p_img(cat[p, c_img])         */
+  const float* c_img;      /* use_img, dense tensor: [B][N][32] (dense mode: [nx^3][32]); may be NULL if tips used */
+  /* compact tactile conditioning (dense mode; generation.py:190-200): a query takes
+   * tip_feat[f] iff f = argmin_f |p - tip_f| (float64), that distance < tip_radius and
+   * tip_touch[f] != 0.  Ignored when n_tips == 0. */
+  int32_t n_tips;
+  double tips[VTACO_MAX_TIPS][3];
+  int32_t tip_touch[VTACO_MAX_TIPS];
+  double tip_radius;
+  const float* tip_feat;   /* [n_tips][32] device */
+  /* ---- outputs ---- */
+  float* logits;           /* flat: [B][N]; dense: [nx][nx][nx] (full grid base pointer) */
+  float* contact;          /* optional second head (forward_contact), same shape, or NULL */
+  int32_t* minmax_key;     /* optional [2]: ordered-int keys of min / max logit, updated with
+                              atomicMin/atomicMax (caller initialises to INT32_MAX, INT32_MIN) */
+  int32_t variant;         /* 0 = default inner loop; 1 = packed FFMA2 inner loop (tuning knob) */
+} vtaco_decoder_args;
+
+int vtaco_decoder_forward(const vtaco_decoder_args* args, void* stream);
+/* Interpolation only — LocalDecoder.sample_plane_feature / sample_grid_feature
+ * (decoder.py:55-68).  Uses the feature / padding / div_mode / sample_mode fields of
+ * `args`; p: [B][N][3]; out: [B][32][N] (sum over the present keys). */
+int vtaco_sample_features(const vtaco_decoder_args* args, const float* p, int64_t N, float* out, void* stream);
+/* decode an ordered-int key written by the decoder / encoder kernels back to float (host helper) */
+float vtaco_key_to_float_host(int32_t key);
+
+/* ------------------------------------------------------------------------- *
+ * (4) self-measured FP32 FMA peak (roofline denominator of the decoder).
+ * Runs a register-resident FMA loop on every SM and returns achieved FLOP/s in
+ * *flops_per_s_host.  variant 0: scalar FFMA, 1: packed FFMA2 (fma.rn.f32x2).
+ * Synchronises the stream (measurement helper, not a data-path call).
+ * ------------------------------------------------------------------------- */
+int vtaco_fp32_peak(int variant, int iters, double* flops_per_s_host, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VTACO_B200_H */

@@ -1,0 +1,133 @@
+"""ctypes binding of the C ABI declared in include/vtaco_b200.h.
+
+The shared library (vtaco_b200/lib/libvtaco_b200.so) is built in-tree by
+`python -m vtaco_b200.build`.  There is NO fallback: if the library is missing
+or a call fails, a RuntimeError is raised.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'lib', 'libvtaco_b200.so')
+
+MAX_TIPS = 8
+PLANE_XZ, PLANE_XY, PLANE_YZ, GRID = 0, 1, 2, 3
+KIND = {'xz': PLANE_XZ, 'xy': PLANE_XY, 'yz': PLANE_YZ, 'grid': GRID}
+DIV_RECIPROCAL, DIV_TRUE = 0, 1
+SAMPLE = {'bilinear': 0, 'nearest': 1}
+
+DEC_OFF_WP, DEC_OFF_BP, DEC_OFF_WPI, DEC_OFF_BPI, DEC_OFF_WIMG = 0, 96, 128, 224, 256
+DEC_OFF_BLOCKS, DEC_BLOCK_STRIDE, DEC_TAIL = 1280, 3168, 68
+
+
+def dec_packed_floats(n_blocks):
+    return DEC_OFF_BLOCKS + DEC_BLOCK_STRIDE * n_blocks + DEC_TAIL
+
+
+class DecoderArgs(C.Structure):
+    _fields_ = [
+        ('p', C.c_void_p), ('B', C.c_int32), ('N', C.c_int64),
+        ('axis', C.c_void_p), ('nx', C.c_int32), ('x0', C.c_int32), ('x1', C.c_int32),
+        ('grid', C.c_void_p), ('plane', C.c_void_p * 3),
+        ('reso_grid', C.c_int32), ('reso_plane', C.c_int32),
+        ('padding', C.c_double), ('div_mode', C.c_int32), ('sample_mode', C.c_int32),
+        ('weights', C.c_void_p), ('n_blocks', C.c_int32), ('leaky', C.c_int32), ('use_img', C.c_int32),
+        ('c_img', C.c_void_p),
+        ('n_tips', C.c_int32), ('tips', (C.c_double * 3) * MAX_TIPS), ('tip_touch', C.c_int32 * MAX_TIPS),
+        ('tip_radius', C.c_double), ('tip_feat', C.c_void_p),
+        ('logits', C.c_void_p), ('contact', C.c_void_p), ('minmax_key', C.c_void_p),
+        ('variant', C.c_int32),
+    ]
+
+
+class McArgs(C.Structure):
+    _fields_ = [
+        ('grid', C.c_void_p), ('nx', C.c_int32), ('ny', C.c_int32), ('nz', C.c_int32),
+        ('x0', C.c_int32), ('x1', C.c_int32),
+        ('level', C.c_float), ('level_from_keys', C.c_void_p),
+        ('scratch', C.c_void_p), ('scratch_bytes', C.c_int64),
+        ('vertices', C.c_void_p), ('vertex_capacity', C.c_int64),
+        ('faces', C.c_void_p), ('face_capacity', C.c_int64),
+        ('counts', C.c_void_p),
+        ('vscale', C.c_float), ('voffset', C.c_float),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    """Load the shared library (once).  Fails loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            'vtaco_b200: %s not found. Build it with `python -m vtaco_b200.build` '
+            '(nvcc, sm_100a). There is no CPU / PyTorch fallback.' % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    L.vtaco_abi_version.restype = C.c_int
+    L.vtaco_status_string.restype = C.c_char_p
+    L.vtaco_status_string.argtypes = [C.c_int]
+    L.vtaco_last_cuda_error.restype = C.c_char_p
+    L.vtaco_point_to_cell.argtypes = [C.c_void_p, C.c_int64, C.c_double, C.c_int, C.c_int, C.c_int,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.vtaco_relayout_cl.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p]
+    L.vtaco_relayout_cf.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p]
+    L.vtaco_decoder_forward.argtypes = [C.POINTER(DecoderArgs), C.c_void_p]
+    L.vtaco_sample_features.argtypes = [C.POINTER(DecoderArgs), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    L.vtaco_key_to_float_host.restype = C.c_float
+    L.vtaco_key_to_float_host.argtypes = [C.c_int32]
+    L.vtaco_fp32_peak.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double), C.c_void_p]
+    for name, argtypes in _OPTIONAL.items():
+        if hasattr(L, name):
+            getattr(L, name).argtypes = argtypes
+    if L.vtaco_abi_version() != 1:
+        raise RuntimeError('vtaco_b200: ABI version mismatch')
+    _lib = L
+    return L
+
+
+_OPTIONAL = {
+    'vtaco_scatter_max_gather': [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int,
+                                 C.c_int64, C.c_int, C.c_void_p],
+    'vtaco_scatter_mean': [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int,
+                           C.c_int64, C.c_void_p],
+    'vtaco_encoder_pointnet': [C.c_void_p, C.c_void_p],
+    'vtaco_marching_cubes': [C.POINTER(McArgs), C.c_void_p],
+    'vtaco_mc_scratch_bytes': [C.c_int, C.c_int, C.c_int],
+}
+
+
+def check(status, what):
+    if status != 0:
+        L = lib()
+        msg = L.vtaco_status_string(status).decode()
+        if status == -3:
+            msg += ': ' + L.vtaco_last_cuda_error().decode()
+        raise RuntimeError('vtaco_b200.%s failed: %s' % (what, msg))
+
+
+def stream_ptr(device=None):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def require_cuda(t, name):
+    if not t.is_cuda:
+        raise RuntimeError('vtaco_b200: %s must be a CUDA tensor (CUDA-only build, no CPU fallback)' % name)
+    if t.dtype != torch.float32:
+        raise TypeError('vtaco_b200: %s must be float32, got %s' % (name, t.dtype))
+
+
+def forbid_autograd(*tensors):
+    """The kernels are forward-only (backward is SURVEY §8f 'next')."""
+    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
+        raise NotImplementedError(
+            'vtaco_b200 kernels are forward-only: call under torch.no_grad() '
+            '(backward kernels are not implemented yet)')

@@ -1,0 +1,301 @@
+"""LocalDecoder — drop-in for reference src/conv_onet/models/decoder.py:9-161.
+
+Same constructor arguments, parameter names / shapes (state_dict compatible) and
+method names.  All arithmetic runs in ONE fused CUDA kernel
+(vtaco_decoder_forward, vtaco_b200/csrc/decoder.cu); there is no PyTorch or CPU
+fallback.  Extra, non-reference entry point: `forward_dense` evaluates the
+extraction lattice of Generator3D without materialising the query tensor.
+"""
+import ctypes as C
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ... import _abi
+from ...common import _div_mode, dense_axis
+from ...layers import ResnetBlockFC
+
+_PLANES = ('xz', 'xy', 'yz')
+
+
+def _as_channels_last(t):
+    """Return a contiguous tensor laid out [B][spatial...][C] holding the values of the
+    channels-first tensor `t` (B,C,*spatial); zero-copy when `t` already is in torch's
+    channels_last(_3d) memory format."""
+    nd = t.dim()
+    perm = (0,) + tuple(range(2, nd)) + (1,)
+    v = t.permute(*perm)
+    if v.is_contiguous():
+        return v
+    B, Cc = t.shape[0], t.shape[1]
+    S = t[0, 0].numel()
+    src = t.contiguous()
+    dst = torch.empty(v.shape, dtype=t.dtype, device=t.device)
+    with torch.cuda.device(t.device):
+        st = _abi.lib().vtaco_relayout_cl(_abi.ptr(src), _abi.ptr(dst), B, Cc, S, _abi.stream_ptr(t.device))
+    _abi.check(st, 'relayout_cl')
+    return dst
+
+
+class LocalDecoder(nn.Module):
+    ''' Decoder conditioned on plane / volume local features (reference decoder.py:9-52).
+
+    Args:
+        dim (int): input dimension
+        c_dim (int): dimension of latent conditioned code c
+        hidden_size (int): hidden size of Decoder network
+        n_blocks (int): number of blocks ResNetBlockFC layers
+        leaky (bool): whether to use leaky ReLUs
+        sample_mode (str): sampling feature strategy, bilinear|nearest
+        padding (float): conventional padding paramter of ONet for unit cube
+        with_contact (bool): add the fc_out_contact head
+    '''
+
+    def __init__(self, dim=3, c_dim=128, hidden_size=256, n_blocks=5, leaky=False,
+                 sample_mode='bilinear', padding=0.1, with_contact=False):
+        super().__init__()
+        self.c_dim = c_dim
+        self.n_blocks = n_blocks
+        self.dim = dim
+        self.hidden_size = hidden_size
+        if c_dim != 0:
+            self.fc_c = nn.ModuleList([nn.Linear(c_dim, hidden_size) for _ in range(n_blocks)])
+        self.fc_p = nn.Linear(dim, hidden_size)
+        self.fc_p_img = nn.Linear(dim + c_dim, hidden_size)
+        self.blocks = nn.ModuleList([ResnetBlockFC(hidden_size) for _ in range(n_blocks)])
+        self.fc_out = nn.Linear(hidden_size, 1)
+        if with_contact:
+            self.fc_out_contact = nn.Linear(hidden_size, 1)
+        self.leaky = bool(leaky)
+        self.actvn = F.relu if not leaky else (lambda x: F.leaky_relu(x, 0.2))
+        self.sample_mode = sample_mode
+        self.padding = padding
+        # how `tensor / python_scalar` of normalize_* is evaluated ('cuda' | 'true'), SURVEY §7.2-1
+        self.division = 'cuda'
+        self.kernel_variant = 0
+        self._pack_cache = None
+        self._cl_cache = {}
+
+    # ------------------------------------------------------------------ packing
+    def _check_supported(self):
+        if self.dim != 3 or self.hidden_size != 32 or self.c_dim not in (0, 32):
+            raise NotImplementedError(
+                'vtaco_b200 fused decoder kernel implements dim=3, hidden_size=32, c_dim in {0,32} '
+                '(every shipped VTacO config); got dim=%d hidden_size=%d c_dim=%d'
+                % (self.dim, self.hidden_size, self.c_dim))
+        if self.sample_mode not in _abi.SAMPLE:
+            raise ValueError('sample_mode must be bilinear|nearest, got %r' % (self.sample_mode,))
+
+    def _packed_weights(self):
+        """Flat fp32 buffer in the layout documented in include/vtaco_b200.h."""
+        params = list(self.parameters())
+        key = tuple((p.data_ptr(), p._version) for p in params)
+        if self._pack_cache is not None and self._pack_cache[0] == key:
+            return self._pack_cache[1]
+        dev = self.fc_p.weight.device
+        H, nb = 32, self.n_blocks
+        buf = torch.zeros(_abi.dec_packed_floats(nb), dtype=torch.float32, device=dev)
+        with torch.no_grad():
+            buf[0:96] = self.fc_p.weight.t().reshape(-1)
+            buf[96:128] = self.fc_p.bias
+            wpi = self.fc_p_img.weight
+            buf[128:224] = wpi[:, :3].t().reshape(-1)
+            buf[224:256] = self.fc_p_img.bias
+            if self.c_dim:
+                buf[256:1280] = wpi[:, 3:].t().reshape(-1)
+            for i in range(nb):
+                o = _abi.DEC_OFF_BLOCKS + i * _abi.DEC_BLOCK_STRIDE
+                if self.c_dim:
+                    buf[o:o + 1024] = self.fc_c[i].weight.t().reshape(-1)
+                    buf[o + 1024:o + 1056] = self.fc_c[i].bias
+                blk = self.blocks[i]
+                buf[o + 1056:o + 2080] = blk.fc_0.weight.t().reshape(-1)
+                buf[o + 2080:o + 2112] = blk.fc_0.bias
+                buf[o + 2112:o + 3136] = blk.fc_1.weight.t().reshape(-1)
+                buf[o + 3136:o + 3168] = blk.fc_1.bias
+            o = _abi.DEC_OFF_BLOCKS + nb * _abi.DEC_BLOCK_STRIDE
+            buf[o:o + H] = self.fc_out.weight.reshape(-1)
+            buf[o + 64] = self.fc_out.bias[0]
+            if hasattr(self, 'fc_out_contact'):
+                buf[o + H:o + 2 * H] = self.fc_out_contact.weight.reshape(-1)
+                buf[o + 65] = self.fc_out_contact.bias[0]
+        self._pack_cache = (key, buf)
+        return buf
+
+    def _features_cl(self, c_plane):
+        """Channels-last views/copies of the feature tensors (cached per tensor version)."""
+        out = {}
+        live = set()
+        for k, t in c_plane.items():
+            if k not in ('grid',) + _PLANES:
+                continue
+            _abi.require_cuda(t, "c_plane['%s']" % k)
+            want_dim = 5 if k == 'grid' else 4
+            if t.dim() != want_dim or t.size(1) != 32:
+                raise ValueError("c_plane['%s'] must be (B,32,%s), got %s"
+                                 % (k, 'R,R,R' if k == 'grid' else 'R,R', tuple(t.shape)))
+            if len(set(t.shape[2:])) != 1:
+                raise NotImplementedError('feature tensors must be cubic/square')
+            ck = (k, t.data_ptr(), t._version, tuple(t.shape), tuple(t.stride()))
+            live.add(ck)
+            hit = self._cl_cache.get(ck)
+            if hit is None:
+                hit = _as_channels_last(t)
+                self._cl_cache[ck] = hit
+            out[k] = hit
+        for ck in list(self._cl_cache):
+            if ck not in live:
+                del self._cl_cache[ck]
+        return out
+
+    # ------------------------------------------------------------------ kernel call
+    def _run(self, args, device):
+        with torch.cuda.device(device):
+            st = _abi.lib().vtaco_decoder_forward(C.byref(args), _abi.stream_ptr(device))
+        _abi.check(st, 'decoder_forward')
+
+    def _base_args(self, c_plane, B):
+        self._check_supported()
+        a = _abi.DecoderArgs()
+        cl = self._features_cl(c_plane) if self.c_dim != 0 else {}
+        if self.c_dim != 0 and not cl:
+            raise ValueError('c_plane holds none of grid/xz/xy/yz')
+        for k, t in cl.items():
+            if t.size(0) != B:
+                raise ValueError("c_plane['%s'] batch %d != %d" % (k, t.size(0), B))
+        a.B = B
+        if 'grid' in cl:
+            a.grid = cl['grid'].data_ptr()
+            a.reso_grid = cl['grid'].size(1)
+        rp = None
+        for i, k in enumerate(_PLANES):
+            if k in cl:
+                a.plane[i] = cl[k].data_ptr()
+                if rp is not None and rp != cl[k].size(1):
+                    raise NotImplementedError('all planes must share one resolution')
+                rp = cl[k].size(1)
+        a.reso_plane = rp or 0
+        a.padding = float(self.padding)
+        a.div_mode = _div_mode(self.division)
+        a.sample_mode = _abi.SAMPLE[self.sample_mode]
+        w = self._packed_weights()
+        a.weights = w.data_ptr()
+        a.n_blocks = self.n_blocks
+        a.leaky = int(self.leaky)
+        a.variant = int(self.kernel_variant)
+        return a, (cl, w)
+
+    def _decode(self, p, c_plane, use_img=False, c_img=None, contact=False):
+        _abi.require_cuda(p, 'p')
+        if p.dim() != 3 or p.size(2) != 3:
+            raise ValueError('p must have shape (B, N, 3)')
+        _abi.forbid_autograd(p, c_img, *self.parameters(), *[t for t in c_plane.values() if torch.is_tensor(t)])
+        B, N = p.shape[0], p.shape[1]
+        pc = p.contiguous()
+        out = torch.empty((B, N), dtype=torch.float32, device=p.device)
+        out_c = torch.empty((B, N), dtype=torch.float32, device=p.device) if contact else None
+        if N == 0 or B == 0:
+            return (out, out_c) if contact else out
+        a, keep = self._base_args(c_plane, B)
+        a.p = pc.data_ptr()
+        a.N = N
+        a.use_img = int(use_img)
+        if use_img:
+            if c_img is None:
+                raise ValueError('forward_img needs c_img')
+            _abi.require_cuda(c_img, 'c_img')
+            if tuple(c_img.shape) != (B, N, self.c_dim):
+                raise ValueError('c_img must have shape (B, N, c_dim)')
+            cic = c_img.contiguous()
+            a.c_img = cic.data_ptr() if self.c_dim else None
+        a.logits = out.data_ptr()
+        if contact:
+            if not hasattr(self, 'fc_out_contact'):
+                raise AttributeError("'LocalDecoder' object has no attribute 'fc_out_contact'")
+            a.contact = out_c.data_ptr()
+        self._run(a, p.device)
+        return (out, out_c) if contact else out
+
+    # ------------------------------------------------------------------ reference API
+    def forward(self, p, c_plane, **kwargs):
+        """reference decoder.py:135-161 -> logits (B,N)."""
+        return self._decode(p, c_plane)
+
+    def forward_img(self, p, c_plane, c_img, **kwargs):
+        """reference decoder.py:71-103 -> logits (B,N)."""
+        return self._decode(p, c_plane, use_img=True, c_img=c_img)
+
+    def forward_contact(self, p, c_plane, **kwargs):
+        """reference decoder.py:105-133 -> (logits, contact) each (B,N)."""
+        return self._decode(p, c_plane, contact=True)
+
+    def sample_plane_feature(self, p, c, plane='xz'):
+        """reference decoder.py:55-60 -> (B, c_dim, N)."""
+        return self._sample(p, {plane if plane in ('xz', 'xy') else 'yz': c})
+
+    def sample_grid_feature(self, p, c):
+        """reference decoder.py:62-68 -> (B, c_dim, N)."""
+        return self._sample(p, {'grid': c})
+
+    def _sample(self, p, c_plane):
+        _abi.require_cuda(p, 'p')
+        _abi.forbid_autograd(p, *c_plane.values())
+        B, N = p.shape[0], p.shape[1]
+        a, keep = self._base_args(c_plane, B)
+        pc = p.contiguous()
+        out = torch.empty((B, 32, N), dtype=torch.float32, device=p.device)
+        L = _abi.lib()
+        with torch.cuda.device(p.device):
+            st = L.vtaco_sample_features(C.byref(a), _abi.ptr(pc), N, _abi.ptr(out), _abi.stream_ptr(p.device))
+        _abi.check(st, 'sample_features')
+        return out
+
+    # ------------------------------------------------------------------ dense lattice (Generator3D fast path)
+    def forward_dense(self, c_plane, nx, x0=0, x1=None, use_img=False, c_img=None, tips=None,
+                      out=None, minmax_key=None, axis=None):
+        """Evaluate the extraction lattice (1+padding)*make_3d_grid(nx^3) (reference
+        generation.py:155-157) for rows x in [x0,x1) directly into `out` (nx,nx,nx).
+
+        use_img + c_img (nx^3, 32): dense tactile tensor as in eval_points;
+        use_img + tips=(pos (F,3) float64, feat (F,32) cuda tensor, touch (F,) bool, radius):
+        compact form of generation.py:190-200.  `minmax_key` (int32[2], init
+        [INT32_MAX, INT32_MIN]) receives ordered-int keys of min/max logit."""
+        dev = self.fc_out.weight.device
+        _abi.forbid_autograd(*self.parameters())
+        x1 = nx if x1 is None else x1
+        if out is None:
+            out = torch.empty((nx, nx, nx), dtype=torch.float32, device=dev)
+        if tuple(out.shape) != (nx, nx, nx) or not out.is_contiguous():
+            raise ValueError('out must be a contiguous (nx,nx,nx) tensor')
+        a, keep = self._base_args(c_plane, 1)
+        if axis is None:
+            axis = dense_axis(nx, self.padding, dev)
+        a.axis = axis.data_ptr()
+        a.nx, a.x0, a.x1 = nx, x0, x1
+        a.use_img = int(use_img)
+        if use_img and c_img is not None:
+            _abi.require_cuda(c_img, 'c_img')
+            cic = c_img.reshape(-1, 32).contiguous()
+            if cic.size(0) != nx ** 3:
+                raise ValueError('dense c_img must have nx^3 rows')
+            a.c_img = cic.data_ptr()
+        if use_img and tips is not None:
+            pos, feat, touch, radius = tips
+            F_ = len(pos)
+            if F_ > _abi.MAX_TIPS:
+                raise ValueError('at most %d tips' % _abi.MAX_TIPS)
+            a.n_tips = F_
+            for f in range(F_):
+                for d in range(3):
+                    a.tips[f][d] = float(pos[f][d])
+                a.tip_touch[f] = int(bool(touch[f]))
+            a.tip_radius = float(radius)
+            _abi.require_cuda(feat, 'tip features')
+            featc = feat.contiguous()
+            a.tip_feat = featc.data_ptr()
+        a.logits = out.data_ptr()
+        if minmax_key is not None:
+            a.minmax_key = minmax_key.data_ptr()
+        self._run(a, dev)
+        return out
