@@ -29,12 +29,12 @@ def _divide(x, d, cuda_division):
     """`tensor / python_scalar`.
 
     CPU ATen performs an IEEE fp32 division by fp32(d); CUDA ATen
-    (div_true_kernel_cuda) multiplies by fp32(1/fp32(d)).  The two differ in the
+    (div_true_kernel_cuda) multiplies by fp32(1/d).  The two differ in the
     last bit for ~half of the inputs.
     """
     if not cuda_division:
         return x / d
-    inv = np.float32(1.0) / np.float32(d)
+    inv = np.float32(1.0 / d)  # reciprocal formed in double, then rounded (measured, see common.cuh)
     return x * float(inv)  # fp32 tensor * python scalar -> fp32 multiply by fp32(inv)
 
 

@@ -11,7 +11,9 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-4
 
 
-def make_decoder(W, leaky=False, contact=False, mode='bilinear', division='true'):
+def make_decoder(W, leaky=False, contact=None, mode='bilinear', division='true'):
+    if contact is None:
+        contact = 'fc_out_contact.weight' in W
     from vtaco_b200.conv_onet.models import decoder_dict
     dec = decoder_dict['simple_local'](dim=3, c_dim=32, padding=0.1, with_contact=contact,
                                        sample_mode=mode, hidden_size=32, leaky=leaky)

@@ -31,10 +31,15 @@ struct NormConst {
 
 inline NormConst make_norm_const(double padding, int div_mode) {
   NormConst c;
-  c.d2 = (float)((1.0 + padding) + 10e-6);
-  c.d3 = (float)((1.0 + padding) + 10e-4);
-  c.inv2 = 1.0f / c.d2;  // ATen CUDA div_true_kernel_cuda: a * (1/b) in fp32
-  c.inv3 = 1.0f / c.d3;
+  const double d2 = (1.0 + padding) + 10e-6, d3 = (1.0 + padding) + 10e-4;
+  c.d2 = (float)d2;
+  c.d3 = (float)d3;
+  // ATen CUDA div_true_kernel_cuda multiplies by the reciprocal of the python scalar;
+  // measured on B200 / torch 2.11 (tests/test_coords_gpu.py): the reciprocal is formed
+  // in double from the double scalar and then rounded to fp32 — fp32(1/1.10001) differs
+  // from 1.0f/fp32(1.10001) in the last bit.
+  c.inv2 = (float)(1.0 / d2);
+  c.inv3 = (float)(1.0 / d3);
   c.hi2 = (float)(1.0 - 10e-6);
   c.hi3 = (float)(1.0 - 10e-4);
   c.div_true = (div_mode == VTACO_DIV_TRUE);
