@@ -152,6 +152,64 @@ int vtaco_sample_features(const vtaco_decoder_args* args, const float* p, int64_
 float vtaco_key_to_float_host(int32_t key);
 
 /* ------------------------------------------------------------------------- *
+ * (5) LocalPoolPointnet, PointNet part.
+ * Replaces LocalPoolPointnet.forward up to (not including) the UNet/UNet3D
+ * (src/encoder/pointnet.py:135-172): point->cell per key, fc_pos, n_blocks x
+ * ResnetBlockFC(2H->H) with pool_local (:116-132; torch_scatter scatter_max or
+ * scatter_mean + gather) between blocks, fc_c, and scatter_mean of the per-point
+ * code into zero-filled feature planes / grid (:85-114).
+ *
+ * Keys are listed in the reference's insertion order (xz, xy, yz, grid; only the
+ * enabled ones).  Outputs are CHANNELS-LAST dense tensors [B][cells][32]; the
+ * Python module exposes them as (B,32,R,R[,R]) views in torch's channels_last
+ * memory format, so values/shapes are the reference's and the decoder reads them
+ * without a copy.
+ *
+ * Packed weights (hidden_dim = 32, c_dim = 32), K-major:
+ *   off 0    fc_pos.weight^T [3][64];  off 192  fc_pos.bias [64]
+ *   off 256  per block i (stride 5184): fc_0.weight^T [64][32], fc_0.bias [32],
+ *            fc_1.weight^T [32][32], fc_1.bias [32], shortcut.weight^T [64][32]
+ *   off 256+5184*n_blocks  fc_c.weight^T [32][32], fc_c.bias [32]
+ * ------------------------------------------------------------------------- */
+#define VTACO_ENC_OFF_BLOCKS 256
+#define VTACO_ENC_BLOCK_STRIDE 5184
+#define VTACO_ENC_PACKED_FLOATS(n_blocks) (VTACO_ENC_OFF_BLOCKS + VTACO_ENC_BLOCK_STRIDE * (n_blocks) + 1056)
+
+typedef struct vtaco_encoder_args {
+  const float* p;          /* [B][T][3] */
+  int32_t B;
+  int64_t T;
+  double padding;
+  int32_t div_mode;        /* VTACO_DIV_* */
+  int32_t n_keys;          /* 1..4 */
+  int32_t kind[4];         /* VTACO_PLANE_* / VTACO_GRID per key */
+  int32_t reso[4];
+  int32_t pool_mean;       /* scatter_type: 0 'max' (default), 1 'mean' */
+  int32_t n_blocks;
+  const float* weights;    /* packed, see above */
+  void* workspace;         /* >= vtaco_encoder_workspace_bytes(...) */
+  int64_t workspace_bytes;
+  float* out_cl[4];        /* per key [B][cells][32], zero-filled by the call; NULL skips the key's output */
+  float* c_out;            /* optional [B][T][32]: per-point code c = fc_c(net) */
+  int32_t* index_out[4];   /* optional per key [B*T] int32 cell indices */
+} vtaco_encoder_args;
+
+int64_t vtaco_encoder_workspace_bytes(int32_t B, int64_t T, int32_t n_keys, const int32_t* kind, const int32_t* reso);
+int vtaco_encoder_pointnet(const vtaco_encoder_args* args, void* stream);
+
+/* pool_local stand-alone (src/encoder/pointnet.py:116-132): feat [B][T][32] row-major,
+ * idx32_host_array[k] = device pointer to key k's [B*T] int32 cell indices, cells[k] = R^2 | R^3;
+ * out [B][T][32] = sum over keys of (per-cell max | mean gathered back to the points). */
+int64_t vtaco_pool_workspace_bytes(int32_t B, int64_t T, int32_t n_keys, const int64_t* cells_host);
+int vtaco_pool_local(const float* feat, int32_t B, int64_t T, int32_t n_keys, const int32_t* const* idx32_host_array,
+                     const int64_t* cells_host, int32_t mean, void* workspace, int64_t workspace_bytes, float* out,
+                     void* stream);
+/* scatter_mean stand-alone (pointnet.py:91-93,106-108): c [B][T][32] -> out_cl [B][cells][32] (zero-filled here).
+ * workspace >= vtaco_pool_workspace_bytes(B, T, 1, &cells). */
+int vtaco_scatter_mean(const float* c, const int32_t* idx32, int32_t B, int64_t T, int64_t cells, void* workspace,
+                       int64_t workspace_bytes, float* out_cl, void* stream);
+
+/* ------------------------------------------------------------------------- *
  * (4) self-measured FP32 FMA peak (roofline denominator of the decoder).
  * Runs a register-resident FMA loop on every SM and returns achieved FLOP/s in
  * *flops_per_s_host.  variant 0: scalar FFMA, 1: packed FFMA2 (fma.rn.f32x2).

@@ -230,6 +230,36 @@ def main():
     g.update(sd_np(dec, 'w.'))
     np.savez_compressed(os.path.join(HERE, 'eval_points.npz'), **g)
 
+    # ---- G5: state_dict contract + UNet / UNet3D post-processing (unet.py:117-239, unet3d.py:361-491)
+    import json
+    from src.encoder.unet import UNet
+    from src.encoder.unet3d import UNet3D
+    contract = {}
+    enc_g = encoder_dict['pointnet_local_pool'](dim=3, c_dim=32, padding=0.1, hidden_dim=32, plane_type='grid',
+                                                grid_resolution=64, unet3d=True,
+                                                unet3d_kwargs=dict(num_levels=4, f_maps=32, in_channels=32, out_channels=32))
+    enc_t = encoder_dict['pointnet_local_pool'](dim=3, c_dim=32, padding=0.1, hidden_dim=32,
+                                                plane_type=['xz', 'xy', 'yz'], plane_resolution=32, unet=True,
+                                                unet_kwargs=dict(depth=4, merge_mode='concat', start_filts=32))
+    dec_c = models.decoder_dict['simple_local'](dim=3, c_dim=32, padding=0.1, with_contact=True,
+                                                sample_mode='bilinear', hidden_size=32)
+    for name, m in (('encoder_grid_unet3d', enc_g), ('encoder_tri_unet', enc_t), ('decoder_contact', dec_c)):
+        contract[name] = {k: list(v.shape) for k, v in m.state_dict().items()}
+    with open(os.path.join(HERE, 'state_dict_contract.json'), 'w') as f:
+        json.dump(contract, f, indent=0, sort_keys=True)
+    g = {}
+    u2 = UNet(8, in_channels=8, depth=3, merge_mode='concat', start_filts=8)
+    randomise(u2, 81)
+    u3 = UNet3D(in_channels=8, out_channels=8, num_levels=3, f_maps=8)
+    randomise(u3, 82)
+    x2, x3 = rs_randn(83, 2, 8, 16, 16), rs_randn(84, 1, 8, 8, 8, 8)
+    with torch.no_grad():
+        g['unet_out'] = u2.eval()(torch.from_numpy(x2)).numpy()
+        g['unet3d_out'] = u3.eval()(torch.from_numpy(x3)).numpy()
+    g.update(sd_np(u2, 'u2.'))
+    g.update(sd_np(u3, 'u3.'))
+    np.savez_compressed(os.path.join(HERE, 'unets.npz'), **g)
+
     for f in sorted(os.listdir(HERE)):
         if f.endswith('.npz'):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, 'KiB')

@@ -1,0 +1,116 @@
+"""CPU: drop-in contract of the modules — constructor kwargs, state_dict keys/shapes
+identical to the reference's (tests/golden/state_dict_contract.json, dumped from the
+reference), UNet/UNet3D re-implementations equal to the reference's outputs, and the
+no-fallback rule (CPU tensors are refused, missing library fails loudly)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from util import GOLDEN, load, close
+
+
+def _contract():
+    with open(os.path.join(GOLDEN, 'state_dict_contract.json')) as f:
+        return json.load(f)
+
+
+def test_state_dict_contract():
+    from vtaco_b200.encoder import encoder_dict
+    from vtaco_b200.conv_onet.models import decoder_dict
+    c = _contract()
+    enc_g = encoder_dict['pointnet_local_pool'](dim=3, c_dim=32, padding=0.1, hidden_dim=32, plane_type='grid',
+                                                grid_resolution=64, unet3d=True,
+                                                unet3d_kwargs=dict(num_levels=4, f_maps=32, in_channels=32,
+                                                                   out_channels=32))
+    enc_t = encoder_dict['pointnet_local_pool'](dim=3, c_dim=32, padding=0.1, hidden_dim=32,
+                                                plane_type=['xz', 'xy', 'yz'], plane_resolution=32, unet=True,
+                                                unet_kwargs=dict(depth=4, merge_mode='concat', start_filts=32))
+    dec = decoder_dict['simple_local'](dim=3, c_dim=32, padding=0.1, with_contact=True, sample_mode='bilinear',
+                                       hidden_size=32)
+    for name, m in (('encoder_grid_unet3d', enc_g), ('encoder_tri_unet', enc_t), ('decoder_contact', dec)):
+        mine = {k: list(v.shape) for k, v in m.state_dict().items()}
+        assert mine == c[name], name
+        assert list(mine.keys()) == sorted(c[name].keys(), key=list(mine.keys()).index)
+
+
+def test_shipped_yaml_kwargs_accepted():
+    """the factories pass **encoder_kwargs straight through (conv_onet/config.py:82-93);
+    unknown UNet keys such as the YAML typo `start_flits` are swallowed."""
+    from vtaco_b200.encoder import encoder_dict
+    e = encoder_dict['pointnet_local_pool'](dim=3, c_dim=32, padding=0.1, hidden_dim=32, plane_type=['xz', 'xy', 'yz'],
+                                            plane_resolution=64, unet=True,
+                                            unet_kwargs=dict(depth=4, merge_mode='concat', start_flits=32))
+    assert e.unet.start_filts == 32
+    with pytest.raises(ValueError, match='incorrect scatter type'):
+        encoder_dict['pointnet_local_pool'](c_dim=32, hidden_dim=32, scatter_type='sum')
+    with pytest.raises(NotImplementedError):
+        encoder_dict['pointnet_local_pool'](c_dim=32, hidden_dim=32, out_mano=True, out_dim=51)
+
+
+def test_fc1_zero_init_like_reference():
+    from vtaco_b200.layers import ResnetBlockFC
+    b = ResnetBlockFC(64, 32)
+    assert float(b.fc_1.weight.abs().sum()) == 0.0 and b.shortcut.bias is None
+    assert ResnetBlockFC(32).shortcut is None
+
+
+def test_unets_match_reference():
+    from vtaco_b200.encoder.unet import UNet
+    from vtaco_b200.encoder.unet3d import UNet3D
+    from util import rs_randn
+    g = load('unets.npz')
+    u2 = UNet(8, in_channels=8, depth=3, merge_mode='concat', start_filts=8)
+    u2.load_state_dict({k[3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith('u2.')}, strict=True)
+    u3 = UNet3D(in_channels=8, out_channels=8, num_levels=3, f_maps=8)
+    u3.load_state_dict({k[3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith('u3.')}, strict=True)
+    with torch.no_grad():
+        o2 = u2.eval()(torch.from_numpy(rs_randn(83, 2, 8, 16, 16)))
+        o3 = u3.eval()(torch.from_numpy(rs_randn(84, 1, 8, 8, 8, 8)))
+    assert close(o2.numpy(), g['unet_out']) < 1e-5
+    assert close(o3.numpy(), g['unet3d_out']) < 1e-5
+
+
+def test_no_cpu_fallback():
+    from vtaco_b200.conv_onet.models import decoder_dict
+    from vtaco_b200 import common as vc
+    dec = decoder_dict['simple_local'](dim=3, c_dim=32, hidden_size=32)
+    with torch.no_grad():
+        with pytest.raises(RuntimeError, match='CUDA'):
+            dec(torch.zeros(1, 4, 3), {'grid': torch.zeros(1, 32, 8, 8, 8)})
+        with pytest.raises(RuntimeError, match='CUDA'):
+            vc.normalize_coordinate(torch.zeros(1, 4, 3))
+
+
+def test_unsupported_width_raises():
+    from vtaco_b200.conv_onet.models import decoder_dict
+    dec = decoder_dict['simple_local'](dim=3, c_dim=128, hidden_size=256)  # constructible (state_dict), not runnable
+    assert dec.fc_p.weight.shape == (256, 3)
+    with pytest.raises(NotImplementedError):
+        dec._check_supported()
+
+
+def test_library_exports_every_declared_symbol():
+    """the C-ABI library loads and exports every function include/vtaco_b200.h declares."""
+    import ctypes
+    import re
+    from vtaco_b200 import _abi
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, 'include', 'vtaco_b200.h')).read()
+    hdr = re.sub(r'/\*.*?\*/', '', hdr, flags=re.S)
+    names = set(re.findall(r'\b(vtaco_[a-z0-9_]+)\s*\(', hdr))
+    assert len(names) >= 10
+    L = ctypes.CDLL(_abi.LIB_PATH)
+    for n in sorted(names):
+        assert hasattr(L, n), 'missing export %s' % n
+    assert L.vtaco_abi_version() == 1
+
+
+def test_make_3d_grid_matches_reference():
+    from vtaco_b200.common import make_3d_grid, dense_axis
+    g = load('coords.npz')
+    assert np.array_equal(make_3d_grid((-0.5,) * 3, (0.5,) * 3, (4, 3, 2)).numpy(), g['grid3_4'])
+    for nx in (8, 32, 128, 256):
+        assert np.array_equal(dense_axis(nx).numpy(), g['axis_%d' % nx])

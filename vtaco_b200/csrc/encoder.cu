@@ -1,0 +1,559 @@
+// LocalPoolPointnet (PointNet part) for sm_100a.
+//
+// Replaces reference src/encoder/pointnet.py:135-172 (forward), :116-132 (pool_local),
+// :85-114 (generate_plane_features / generate_grid_features before the UNets) and the
+// torch_scatter scatter_max / scatter_mean kernels they call.
+//
+// Design
+//  * point -> cell once per key (int32), then cell -> SLOT compaction: the lowest point
+//    id that falls into a cell (atomicMin on a dense int32 map) represents the cell, so
+//    every pooling buffer is [points][32] instead of [R^3][32] (33.5 MB/sample at 64^3)
+//    and nothing of size R^3 x 32 is filled or read while pooling.
+//  * per-point MLP: one thread per point, layer inputs in a private shared-memory column,
+//    accumulators in registers, K-major weights broadcast from shared memory.
+//  * scatter: rows are transposed through shared memory so that lane == channel; a warp
+//    walks its 32 points, folds runs of equal slot in registers and issues ONE 128-byte
+//    row atomic per run (warp-aggregated; only the final reduction is atomic).
+//  * max pooling uses atomicMax/atomicMin on the int view of the floats: order
+//    independent, hence bit-exact.  The final scatter_mean is an fp32 atomicAdd sum
+//    (order not fixed -> tolerance), divided by the cell count, written once per occupied
+//    cell into a zero-filled channels-last tensor.
+#include "common.cuh"
+#include <math_constants.h>
+#include <cmath>
+
+namespace vtaco {
+
+constexpr int kET = 128;        // threads per block
+constexpr int kES = kET + 1;    // shared column stride
+constexpr unsigned kFullMask = 0xffffffffu;
+
+// packed encoder weights (hidden_dim = 32, c_dim = 32), K-major
+constexpr int ENC_OFF_WPOS = 0;      // fc_pos.weight^T [3][64]
+constexpr int ENC_OFF_BPOS = 192;    // fc_pos.bias [64]
+constexpr int ENC_OFF_BLOCKS = 256;
+constexpr int ENC_BLOCK_STRIDE = 5184;
+constexpr int ENC_B_W0 = 0;          // fc_0.weight^T [64][32]
+constexpr int ENC_B_B0 = 2048;
+constexpr int ENC_B_W1 = 2080;       // fc_1.weight^T [32][32]
+constexpr int ENC_B_B1 = 3104;
+constexpr int ENC_B_WS = 3136;       // shortcut.weight^T [64][32]
+constexpr int ENC_FCC_FLOATS = 1056; // fc_c.weight^T [32][32] + bias
+
+struct EncParams {
+  const float* p;
+  long long n, T;
+  int B;
+  NormConst nc;
+  int nkeys;
+  int kind[4];
+  int reso[4];
+  long long cells[4];
+  int pool_mean;
+  int n_blocks;
+  const float* W;
+  int32_t* idx[4];
+  int32_t* slot[4];
+  int32_t* map[4];
+  int32_t* count[4];
+  float* net[2];
+  float* pool[3][4];
+  float* sum[4];
+  float* out_cl[4];
+  float* c_out;
+};
+
+__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
+  v += 0.0f;  // -0 -> +0
+  if (v >= 0.0f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+
+__device__ __forceinline__ int cell_index(const float x, const float y, const float z, int kind, int reso,
+                                          const NormConst& nc) {
+  if (kind == VTACO_GRID)
+    return cell_of(norm3d(x, nc), reso) + reso * (cell_of(norm3d(y, nc), reso) + reso * cell_of(norm3d(z, nc), reso));
+  const float a = (kind == VTACO_PLANE_YZ) ? y : x;
+  const float b = (kind == VTACO_PLANE_XY) ? y : z;
+  return cell_of(norm2d(a, nc), reso) + reso * cell_of(norm2d(b, nc), reso);
+}
+
+// pointnet.py:139-152 for every enabled key + election of the cell representative.
+__global__ void __launch_bounds__(256) enc_index_kernel(const __grid_constant__ EncParams P) {
+  const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= P.n) return;
+  const float x = P.p[n * 3], y = P.p[n * 3 + 1], z = P.p[n * 3 + 2];
+  const long long b = n / P.T;
+  for (int k = 0; k < P.nkeys; ++k) {
+    const int c = cell_index(x, y, z, P.kind[k], P.reso[k], P.nc);
+    P.idx[k][n] = c;
+    atomicMin(P.map[k] + b * P.cells[k] + c, (int)n);
+  }
+}
+
+// generic: representative election from precomputed indices
+__global__ void __launch_bounds__(256) map_min_kernel(const int32_t* __restrict__ idx, int32_t* __restrict__ map,
+                                                      long long n, long long T, long long cells) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  atomicMin(map + (i / T) * cells + idx[i], (int)i);
+}
+
+__device__ __forceinline__ void fill_row(float* row, float v) {
+  const float4 f = make_float4(v, v, v, v);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) reinterpret_cast<float4*>(row)[j] = f;
+}
+
+// slot[n] = representative of n's cell; count[rep] += 1; first pooling buffer initialised.
+__global__ void __launch_bounds__(256) enc_slot_kernel(const __grid_constant__ EncParams P, int init_pool) {
+  const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= P.n) return;
+  const long long b = n / P.T;
+  const float init = P.pool_mean ? 0.0f : -CUDART_INF_F;
+  for (int k = 0; k < P.nkeys; ++k) {
+    const int s = P.map[k][b * P.cells[k] + P.idx[k][n]];
+    P.slot[k][n] = s;
+    atomicAdd(P.count[k] + s, 1);
+    if (init_pool) fill_row(P.pool[0][k] + n * 32, init);
+  }
+}
+
+// y[j] += sum_k W[k][j] * x  helpers (W K-major in shared memory, broadcast float4 loads)
+__device__ __forceinline__ void axpy32(float (&acc)[32], const float* __restrict__ Wk, float x) {
+  const float4* w4 = reinterpret_cast<const float4*>(Wk);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 w = w4[j];
+    acc[4 * j] = fmaf(w.x, x, acc[4 * j]);
+    acc[4 * j + 1] = fmaf(w.y, x, acc[4 * j + 1]);
+    acc[4 * j + 2] = fmaf(w.z, x, acc[4 * j + 2]);
+    acc[4 * j + 3] = fmaf(w.w, x, acc[4 * j + 3]);
+  }
+}
+
+// Warp walks its 32 points with lane == channel: store the row, fold runs of equal slot,
+// one row-wide atomic per run.  `col0` = first shared column of the warp.
+template <bool MEAN>
+__device__ __forceinline__ void scatter_rows(const float* __restrict__ sX, int col0, long long n0, long long nmax,
+                                             int lane, int nkeys, const int (&myslot)[4], float* const (&dst)[4],
+                                             float* __restrict__ row_out) {
+  int cur[4] = {-1, -1, -1, -1};
+  float val[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int i = 0; i < 32; ++i) {
+    const long long ni = n0 + i;
+    if (ni >= nmax) break;  // uniform
+    const float v = sX[lane * kES + col0 + i];
+    if (row_out) row_out[ni * 32 + lane] = v;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (k < nkeys && dst[k]) {
+        const int s = __shfl_sync(kFullMask, myslot[k], i);
+        if (s != cur[k]) {
+          if (cur[k] >= 0) {
+            if (MEAN) atomicAdd(dst[k] + (long long)cur[k] * 32 + lane, val[k]);
+            else atomic_max_float(dst[k] + (long long)cur[k] * 32 + lane, val[k]);
+          }
+          cur[k] = s;
+          val[k] = v;
+        } else {
+          val[k] = MEAN ? (val[k] + v) : fmaxf(val[k], v);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (k < nkeys && dst[k] && cur[k] >= 0) {
+      if (MEAN) atomicAdd(dst[k] + (long long)cur[k] * 32 + lane, val[k]);
+      else atomic_max_float(dst[k] + (long long)cur[k] * 32 + lane, val[k]);
+    }
+  }
+}
+
+// One ResnetBlockFC(64 -> 32) per launch (layers.py:41-50) with its input assembly:
+//   FIRST : x = fc_pos(p)                                   pointnet.py:154,156
+//   else  : x = cat[net, pool_local(net)]                   pointnet.py:157-160
+// and the scatter of its output into the next pooling buffer.
+template <bool FIRST>
+__global__ void __launch_bounds__(kET) enc_block_kernel(const __grid_constant__ EncParams P, int blk, int r_read,
+                                                        int r_write, int r_init, int net_in, int net_out) {
+  extern __shared__ __align__(16) float esm[];
+  float* sW = esm;                          // block weights (5184) [+ fc_pos 256]
+  float* sX = sW + ENC_BLOCK_STRIDE + 256;  // [64][kES]
+  const float* Wg = P.W + ENC_OFF_BLOCKS + (long long)blk * ENC_BLOCK_STRIDE;
+  for (int i = threadIdx.x; i < ENC_BLOCK_STRIDE / 4; i += kET)
+    reinterpret_cast<float4*>(sW)[i] = __ldg(reinterpret_cast<const float4*>(Wg) + i);
+  if (FIRST)
+    for (int i = threadIdx.x; i < 256 / 4; i += kET)
+      reinterpret_cast<float4*>(sW + ENC_BLOCK_STRIDE)[i] = __ldg(reinterpret_cast<const float4*>(P.W) + i);
+  __syncthreads();
+
+  const int tid = threadIdx.x, lane = tid & 31, col0 = tid & ~31;
+  const long long nb0 = (long long)blockIdx.x * kET;
+  const long long n = nb0 + tid;
+  const bool valid = n < P.n;
+  int myslot[4] = {0, 0, 0, 0};
+  for (int k = 0; k < P.nkeys; ++k) myslot[k] = valid ? P.slot[k][n] : 0;
+
+  float* xcol = sX + tid;
+  if (FIRST) {
+    const float* Wp = sW + ENC_BLOCK_STRIDE;
+    const float px = valid ? P.p[n * 3] : 0.f, py = valid ? P.p[n * 3 + 1] : 0.f, pz = valid ? P.p[n * 3 + 2] : 0.f;
+#pragma unroll 8
+    for (int j = 0; j < 64; ++j)
+      xcol[j * kES] = fmaf(Wp[128 + j], pz, fmaf(Wp[64 + j], py, fmaf(Wp[j], px, Wp[ENC_OFF_BPOS + j])));
+  } else {
+    const float* netin = P.net[net_in];
+    for (int i = 0; i < 32; ++i) {
+      const long long ni = nb0 + col0 + i;
+      if (ni >= P.n) break;
+      sX[lane * kES + col0 + i] = netin[ni * 32 + lane];
+      float s = 0.f;  // c_out = 0; c_out += fea  (key order xz, xy, yz, grid)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (k < P.nkeys) {
+          const int sl = __shfl_sync(kFullMask, myslot[k], i);
+          float v = P.pool[r_read][k][(long long)sl * 32 + lane];
+          if (P.pool_mean) v = v / (float)P.count[k][sl];
+          s += v;
+        }
+      }
+      sX[(32 + lane) * kES + col0 + i] = s;
+    }
+  }
+  __syncwarp();
+
+  float h[32], o[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) { h[j] = sW[ENC_B_B0 + j]; o[j] = sW[ENC_B_B1 + j]; }
+#pragma unroll 2
+  for (int k = 0; k < 64; ++k) {
+    const float x = xcol[k * kES];
+    axpy32(h, sW + ENC_B_W0 + k * 32, fmaxf(x, 0.f));  // fc_0(relu(x))
+    axpy32(o, sW + ENC_B_WS + k * 32, x);              // shortcut(x), no bias
+  }
+#pragma unroll
+  for (int j = 0; j < 32; ++j) xcol[j * kES] = fmaxf(h[j], 0.f);
+#pragma unroll 4
+  for (int k = 0; k < 32; ++k) axpy32(o, sW + ENC_B_W1 + k * 32, xcol[k * kES]);  // fc_1(relu(net))
+#pragma unroll
+  for (int j = 0; j < 32; ++j) xcol[j * kES] = o[j];
+  __syncwarp();
+
+  float* dst[4] = {nullptr, nullptr, nullptr, nullptr};
+  if (r_write >= 0)
+    for (int k = 0; k < P.nkeys; ++k) dst[k] = P.pool[r_write][k];
+  if (P.pool_mean) scatter_rows<true>(sX, col0, nb0 + col0, P.n, lane, P.nkeys, myslot, dst, P.net[net_out]);
+  else scatter_rows<false>(sX, col0, nb0 + col0, P.n, lane, P.nkeys, myslot, dst, P.net[net_out]);
+
+  if (r_init >= 0 && valid) {
+    const float init = P.pool_mean ? 0.0f : -CUDART_INF_F;
+    for (int k = 0; k < P.nkeys; ++k) fill_row(P.pool[r_init][k] + n * 32, init);
+  }
+}
+
+// c = fc_c(net) (pointnet.py:162) and the atomicAdd half of scatter_mean (:93,108).
+__global__ void __launch_bounds__(kET) enc_final_kernel(const __grid_constant__ EncParams P, int net_in) {
+  extern __shared__ __align__(16) float esm[];
+  float* sW = esm;                   // fc_c (1056)
+  float* sX = sW + ENC_FCC_FLOATS;   // [32][kES]
+  const float* Wg = P.W + ENC_OFF_BLOCKS + (long long)P.n_blocks * ENC_BLOCK_STRIDE;
+  for (int i = threadIdx.x; i < ENC_FCC_FLOATS / 4; i += kET)
+    reinterpret_cast<float4*>(sW)[i] = __ldg(reinterpret_cast<const float4*>(Wg) + i);
+  __syncthreads();
+  const int tid = threadIdx.x, lane = tid & 31, col0 = tid & ~31;
+  const long long nb0 = (long long)blockIdx.x * kET;
+  const long long n = nb0 + tid;
+  const bool valid = n < P.n;
+  int myslot[4] = {0, 0, 0, 0};
+  for (int k = 0; k < P.nkeys; ++k) myslot[k] = valid ? P.slot[k][n] : 0;
+  const float* netin = P.net[net_in];
+  for (int i = 0; i < 32; ++i) {
+    const long long ni = nb0 + col0 + i;
+    if (ni >= P.n) break;
+    sX[lane * kES + col0 + i] = netin[ni * 32 + lane];
+  }
+  __syncwarp();
+  float* xcol = sX + tid;
+  float c[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) c[j] = sW[1024 + j];
+#pragma unroll 4
+  for (int k = 0; k < 32; ++k) axpy32(c, sW + k * 32, xcol[k * kES]);
+#pragma unroll
+  for (int j = 0; j < 32; ++j) xcol[j * kES] = c[j];
+  __syncwarp();
+  float* dst[4] = {nullptr, nullptr, nullptr, nullptr};
+  for (int k = 0; k < P.nkeys; ++k) dst[k] = P.sum[k];
+  scatter_rows<true>(sX, col0, nb0 + col0, P.n, lane, P.nkeys, myslot, dst, P.c_out);
+}
+
+// mean = sum / count, written once per occupied cell (the representative's thread) into the
+// zero-filled channels-last output [B][cells][32].
+__global__ void __launch_bounds__(256) enc_finalize_kernel(const __grid_constant__ EncParams P) {
+  const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= P.n) return;
+  const long long b = n / P.T;
+  for (int k = 0; k < P.nkeys; ++k) {
+    if (P.slot[k][n] != (int)n || !P.out_cl[k]) continue;
+    const float cnt = (float)P.count[k][n];
+    const float4* s4 = reinterpret_cast<const float4*>(P.sum[k] + n * 32);
+    float4* o4 = reinterpret_cast<float4*>(P.out_cl[k] + (b * P.cells[k] + P.idx[k][n]) * 32);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 s = s4[j];
+      o4[j] = make_float4(s.x / cnt, s.y / cnt, s.z / cnt, s.w / cnt);
+    }
+  }
+}
+
+// ---- stand-alone row kernels behind vtaco_pool_local / vtaco_scatter_mean ----
+template <bool MEAN>
+__global__ void __launch_bounds__(kET) rows_scatter_kernel(const float* __restrict__ src, long long n, int nkeys,
+                                                           const int32_t* s0, const int32_t* s1, const int32_t* s2,
+                                                           const int32_t* s3, float* d0, float* d1, float* d2,
+                                                           float* d3) {
+  __shared__ float sX[32 * kES];
+  const int tid = threadIdx.x, lane = tid & 31, col0 = tid & ~31;
+  const long long nb0 = (long long)blockIdx.x * kET;
+  const long long me = nb0 + tid;
+  const int32_t* sl[4] = {s0, s1, s2, s3};
+  float* dst[4] = {d0, d1, d2, d3};
+  int myslot[4] = {0, 0, 0, 0};
+  for (int k = 0; k < nkeys; ++k) myslot[k] = me < n ? sl[k][me] : 0;
+  for (int i = 0; i < 32; ++i) {
+    const long long ni = nb0 + col0 + i;
+    if (ni >= n) break;
+    sX[lane * kES + col0 + i] = src[ni * 32 + lane];
+  }
+  __syncwarp();
+  scatter_rows<MEAN>(sX, col0, nb0 + col0, n, lane, nkeys, myslot, dst, nullptr);
+}
+
+__global__ void __launch_bounds__(256) rows_gather_kernel(float* __restrict__ out, long long n, int nkeys, int mean,
+                                                          const int32_t* s0, const int32_t* s1, const int32_t* s2,
+                                                          const int32_t* s3, const float* d0, const float* d1,
+                                                          const float* d2, const float* d3, const int32_t* c0,
+                                                          const int32_t* c1, const int32_t* c2, const int32_t* c3) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long ni = t >> 5;
+  const int lane = threadIdx.x & 31;
+  if (ni >= n) return;
+  const int32_t* sl[4] = {s0, s1, s2, s3};
+  const float* src[4] = {d0, d1, d2, d3};
+  const int32_t* cnt[4] = {c0, c1, c2, c3};
+  float s = 0.f;
+  for (int k = 0; k < nkeys; ++k) {
+    const int r = sl[k][ni];
+    float v = src[k][(long long)r * 32 + lane];
+    if (mean) v = v / (float)cnt[k][r];
+    s += v;
+  }
+  out[ni * 32 + lane] = s;
+}
+
+__global__ void __launch_bounds__(256) slot_kernel(const int32_t* __restrict__ idx, const int32_t* __restrict__ map,
+                                                   int32_t* __restrict__ slot, int32_t* __restrict__ count,
+                                                   float* __restrict__ pool, float init, long long n, long long T,
+                                                   long long cells) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int s = map[(i / T) * cells + idx[i]];
+  slot[i] = s;
+  atomicAdd(count + s, 1);
+  if (pool) fill_row(pool + i * 32, init);
+}
+
+__global__ void __launch_bounds__(256) mean_finalize_kernel(const int32_t* __restrict__ idx,
+                                                            const int32_t* __restrict__ slot,
+                                                            const int32_t* __restrict__ count,
+                                                            const float* __restrict__ sum, float* __restrict__ out_cl,
+                                                            long long n, long long T, long long cells) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || slot[i] != (int)i) return;
+  const float cnt = (float)count[i];
+  const float4* s4 = reinterpret_cast<const float4*>(sum + i * 32);
+  float4* o4 = reinterpret_cast<float4*>(out_cl + ((i / T) * cells + idx[i]) * 32);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 s = s4[j];
+    o4[j] = make_float4(s.x / cnt, s.y / cnt, s.z / cnt, s.w / cnt);
+  }
+}
+
+static inline long long align_up(long long v, long long a) { return (v + a - 1) / a * a; }
+
+struct Carver {
+  char* base;
+  long long off;
+  template <typename T>
+  T* take(long long count) {
+    T* r = reinterpret_cast<T*>(base + off);
+    off = align_up(off + count * (long long)sizeof(T), 256);
+    return r;
+  }
+};
+
+static long long cells_of(int kind, int reso) {
+  return kind == VTACO_GRID ? (long long)reso * reso * reso : (long long)reso * reso;
+}
+
+}  // namespace vtaco
+
+using namespace vtaco;
+
+extern "C" int64_t vtaco_encoder_workspace_bytes(int32_t B, int64_t T, int32_t n_keys, const int32_t* kind,
+                                                 const int32_t* reso) {
+  if (B <= 0 || T <= 0 || n_keys <= 0 || n_keys > 4 || !kind || !reso) return VTACO_ERR_INVALID_ARG;
+  const long long n = (long long)B * T;
+  Carver c{nullptr, 0};
+  for (int k = 0; k < n_keys; ++k) {
+    c.take<int32_t>(n); c.take<int32_t>(n); c.take<int32_t>(n);
+    c.take<int32_t>((long long)B * cells_of(kind[k], reso[k]));
+    for (int r = 0; r < 3; ++r) c.take<float>(n * 32);
+    c.take<float>(n * 32);
+  }
+  c.take<float>(n * 32); c.take<float>(n * 32);
+  return c.off;
+}
+
+extern "C" int vtaco_encoder_pointnet(const vtaco_encoder_args* a, void* stream) {
+  if (!a || !a->p || !a->weights || !a->workspace) return VTACO_ERR_INVALID_ARG;
+  if (a->B <= 0 || a->T <= 0 || a->n_keys <= 0 || a->n_keys > 4 || a->n_blocks < 1) return VTACO_ERR_INVALID_ARG;
+  const long long n = (long long)a->B * a->T;
+  if (n >= (1ll << 31)) return VTACO_ERR_UNSUPPORTED;
+  for (int k = 0; k < a->n_keys; ++k) {
+    if (a->kind[k] < 0 || a->kind[k] > 3 || a->reso[k] < 1) return VTACO_ERR_INVALID_ARG;
+    if (a->kind[k] == VTACO_GRID ? a->reso[k] > 1290 : a->reso[k] > 46340) return VTACO_ERR_UNSUPPORTED;
+  }
+  if (vtaco_encoder_workspace_bytes(a->B, a->T, a->n_keys, a->kind, a->reso) > a->workspace_bytes)
+    return VTACO_ERR_CAPACITY;
+  cudaStream_t st = (cudaStream_t)stream;
+  EncParams P = {};
+  P.p = a->p; P.n = n; P.T = a->T; P.B = a->B;
+  P.nc = make_norm_const(a->padding, a->div_mode);
+  P.nkeys = a->n_keys; P.pool_mean = a->pool_mean ? 1 : 0; P.n_blocks = a->n_blocks; P.W = a->weights;
+  P.c_out = a->c_out;
+  Carver c{reinterpret_cast<char*>(a->workspace), 0};
+  for (int k = 0; k < a->n_keys; ++k) {
+    P.kind[k] = a->kind[k]; P.reso[k] = a->reso[k]; P.cells[k] = cells_of(a->kind[k], a->reso[k]);
+    P.idx[k] = c.take<int32_t>(n); P.slot[k] = c.take<int32_t>(n); P.count[k] = c.take<int32_t>(n);
+    P.map[k] = c.take<int32_t>((long long)a->B * P.cells[k]);
+    for (int r = 0; r < 3; ++r) P.pool[r][k] = c.take<float>(n * 32);
+    P.sum[k] = c.take<float>(n * 32);
+    P.out_cl[k] = a->out_cl[k];
+    VTACO_CUDA_CHECK(cudaMemsetAsync(P.map[k], 0x7f, sizeof(int32_t) * a->B * P.cells[k], st));
+    VTACO_CUDA_CHECK(cudaMemsetAsync(P.count[k], 0, sizeof(int32_t) * n, st));
+    VTACO_CUDA_CHECK(cudaMemsetAsync(P.sum[k], 0, sizeof(float) * n * 32, st));
+    if (P.out_cl[k])
+      VTACO_CUDA_CHECK(cudaMemsetAsync(P.out_cl[k], 0, sizeof(float) * a->B * P.cells[k] * 32, st));
+  }
+  P.net[0] = c.take<float>(n * 32);
+  P.net[1] = c.take<float>(n * 32);
+
+  const unsigned g256 = (unsigned)((n + 255) / 256), gE = (unsigned)((n + kET - 1) / kET);
+  enc_index_kernel<<<g256, 256, 0, st>>>(P);
+  enc_slot_kernel<<<g256, 256, 0, st>>>(P, 1);
+  const size_t smem_blk = (ENC_BLOCK_STRIDE + 256 + 64 * kES) * sizeof(float);
+  static bool configured[64] = {false};
+  int dev = 0;
+  VTACO_CUDA_CHECK(cudaGetDevice(&dev));
+  if (!configured[dev & 63]) {
+    VTACO_CUDA_CHECK(cudaFuncSetAttribute(enc_block_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_blk));
+    VTACO_CUDA_CHECK(cudaFuncSetAttribute(enc_block_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_blk));
+    configured[dev & 63] = true;
+  }
+  const int nb = a->n_blocks;
+  // kernel i reads pool[(i-1)%3], scatters into pool[i%3], initialises pool[(i+1)%3]
+  enc_block_kernel<true><<<gE, kET, smem_blk, st>>>(P, 0, -1, nb > 1 ? 0 : -1, nb > 2 ? 1 : -1, 0, 0);
+  for (int i = 1; i < nb; ++i) {
+    const bool last = (i == nb - 1);
+    enc_block_kernel<false><<<gE, kET, smem_blk, st>>>(P, i, (i - 1) % 3, last ? -1 : i % 3,
+                                                       (i + 1 < nb - 1) ? (i + 1) % 3 : -1, (i - 1) & 1, i & 1);
+  }
+  const size_t smem_fin = (ENC_FCC_FLOATS + 32 * kES) * sizeof(float);
+  enc_final_kernel<<<gE, kET, smem_fin, st>>>(P, (nb - 1) & 1);
+  enc_finalize_kernel<<<g256, 256, 0, st>>>(P);
+  VTACO_LAUNCH_CHECK();
+  for (int k = 0; k < a->n_keys; ++k)
+    if (a->index_out[k])
+      VTACO_CUDA_CHECK(cudaMemcpyAsync(a->index_out[k], P.idx[k], sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, st));
+  return VTACO_OK;
+}
+
+extern "C" int64_t vtaco_pool_workspace_bytes(int32_t B, int64_t T, int32_t n_keys, const int64_t* cells) {
+  if (B <= 0 || T <= 0 || n_keys <= 0 || n_keys > 4 || !cells) return VTACO_ERR_INVALID_ARG;
+  const long long n = (long long)B * T;
+  Carver c{nullptr, 0};
+  for (int k = 0; k < n_keys; ++k) {
+    c.take<int32_t>(n); c.take<int32_t>(n);
+    c.take<int32_t>((long long)B * cells[k]);
+    c.take<float>(n * 32);
+  }
+  return c.off;
+}
+
+extern "C" int vtaco_pool_local(const float* feat, int32_t B, int64_t T, int32_t n_keys, const int32_t* const* idx32,
+                                const int64_t* cells, int32_t mean, void* workspace, int64_t workspace_bytes,
+                                float* out, void* stream) {
+  if (!feat || !idx32 || !cells || !workspace || !out) return VTACO_ERR_INVALID_ARG;
+  if (B <= 0 || T <= 0 || n_keys <= 0 || n_keys > 4) return VTACO_ERR_INVALID_ARG;
+  if (vtaco_pool_workspace_bytes(B, T, n_keys, cells) > workspace_bytes) return VTACO_ERR_CAPACITY;
+  const long long n = (long long)B * T;
+  if (n >= (1ll << 31)) return VTACO_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  Carver c{reinterpret_cast<char*>(workspace), 0};
+  int32_t* slot[4] = {nullptr, nullptr, nullptr, nullptr};
+  int32_t* count[4] = {nullptr, nullptr, nullptr, nullptr};
+  float* pool[4] = {nullptr, nullptr, nullptr, nullptr};
+  const unsigned g256 = (unsigned)((n + 255) / 256);
+  for (int k = 0; k < n_keys; ++k) {
+    slot[k] = c.take<int32_t>(n); count[k] = c.take<int32_t>(n);
+    int32_t* map = c.take<int32_t>((long long)B * cells[k]);
+    pool[k] = c.take<float>(n * 32);
+    VTACO_CUDA_CHECK(cudaMemsetAsync(map, 0x7f, sizeof(int32_t) * B * cells[k], st));
+    VTACO_CUDA_CHECK(cudaMemsetAsync(count[k], 0, sizeof(int32_t) * n, st));
+    map_min_kernel<<<g256, 256, 0, st>>>(idx32[k], map, n, T, cells[k]);
+    slot_kernel<<<g256, 256, 0, st>>>(idx32[k], map, slot[k], count[k], pool[k], mean ? 0.f : -INFINITY, n, T,
+                                      cells[k]);
+  }
+  const unsigned gE = (unsigned)((n + kET - 1) / kET);
+  if (mean)
+    rows_scatter_kernel<true><<<gE, kET, 0, st>>>(feat, n, n_keys, slot[0], slot[1], slot[2], slot[3], pool[0],
+                                                  pool[1], pool[2], pool[3]);
+  else
+    rows_scatter_kernel<false><<<gE, kET, 0, st>>>(feat, n, n_keys, slot[0], slot[1], slot[2], slot[3], pool[0],
+                                                   pool[1], pool[2], pool[3]);
+  rows_gather_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(
+      out, n, n_keys, mean, slot[0], slot[1], slot[2], slot[3], pool[0], pool[1], pool[2], pool[3], count[0], count[1],
+      count[2], count[3]);
+  VTACO_LAUNCH_CHECK();
+  return VTACO_OK;
+}
+
+extern "C" int vtaco_scatter_mean(const float* c, const int32_t* idx32, int32_t B, int64_t T, int64_t cells,
+                                  void* workspace, int64_t workspace_bytes, float* out_cl, void* stream) {
+  if (!c || !idx32 || !workspace || !out_cl || B <= 0 || T <= 0 || cells <= 0) return VTACO_ERR_INVALID_ARG;
+  const int64_t cells1[1] = {cells};
+  if (vtaco_pool_workspace_bytes(B, T, 1, cells1) > workspace_bytes) return VTACO_ERR_CAPACITY;
+  const long long n = (long long)B * T;
+  if (n >= (1ll << 31)) return VTACO_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  Carver cv{reinterpret_cast<char*>(workspace), 0};
+  int32_t* slot = cv.take<int32_t>(n);
+  int32_t* count = cv.take<int32_t>(n);
+  int32_t* map = cv.take<int32_t>((long long)B * cells);
+  float* sum = cv.take<float>(n * 32);
+  VTACO_CUDA_CHECK(cudaMemsetAsync(map, 0x7f, sizeof(int32_t) * B * cells, st));
+  VTACO_CUDA_CHECK(cudaMemsetAsync(count, 0, sizeof(int32_t) * n, st));
+  VTACO_CUDA_CHECK(cudaMemsetAsync(out_cl, 0, sizeof(float) * B * cells * 32, st));
+  const unsigned g256 = (unsigned)((n + 255) / 256), gE = (unsigned)((n + kET - 1) / kET);
+  map_min_kernel<<<g256, 256, 0, st>>>(idx32, map, n, T, cells);
+  slot_kernel<<<g256, 256, 0, st>>>(idx32, map, slot, count, sum, 0.f, n, T, cells);
+  rows_scatter_kernel<true><<<gE, kET, 0, st>>>(c, n, 1, slot, nullptr, nullptr, nullptr, sum, nullptr, nullptr,
+                                                nullptr);
+  mean_finalize_kernel<<<g256, 256, 0, st>>>(idx32, slot, count, sum, out_cl, n, T, cells);
+  VTACO_LAUNCH_CHECK();
+  return VTACO_OK;
+}

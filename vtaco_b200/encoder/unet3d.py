@@ -1,0 +1,98 @@
+"""3-D U-Net applied to the feature grid — state_dict-compatible with reference
+src/encoder/unet3d.py:361-491 (encoders.N.basic_module.SingleConv{1,2}.{groupnorm,conv,...},
+decoders.N.basic_module..., final_conv).  Library-backed (torch.nn / cuDNN), SURVEY §2 row 8."""
+from collections import OrderedDict
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+def _single_conv(cin, cout, order, num_groups, kernel_size=3, padding=1):
+    assert 'c' in order, 'Conv layer MUST be present'
+    assert order[0] not in 'rle', 'Non-linearity cannot be the first operation in the layer'
+    mods = OrderedDict()
+    for i, ch in enumerate(order):
+        if ch == 'r':
+            mods['ReLU'] = nn.ReLU(inplace=True)
+        elif ch == 'l':
+            mods['LeakyReLU'] = nn.LeakyReLU(negative_slope=0.1, inplace=True)
+        elif ch == 'e':
+            mods['ELU'] = nn.ELU(inplace=True)
+        elif ch == 'c':
+            mods['conv'] = nn.Conv3d(cin, cout, kernel_size, padding=padding, bias=not ('g' in order or 'b' in order))
+        elif ch == 'g':
+            nch = cin if i < order.index('c') else cout
+            groups = 1 if nch < num_groups else num_groups
+            assert nch % groups == 0
+            mods['groupnorm'] = nn.GroupNorm(num_groups=groups, num_channels=nch)
+        elif ch == 'b':
+            mods['batchnorm'] = nn.BatchNorm3d(cin if i < order.index('c') else cout)
+        else:
+            raise ValueError("Unsupported layer type '%s'. MUST be one of ['b', 'g', 'r', 'l', 'e', 'c']" % ch)
+    return nn.Sequential(mods)
+
+
+def _double_conv(cin, cout, encoder, order, num_groups):
+    if encoder:
+        c1 = max(cout // 2, cin)
+        shapes = ((cin, c1), (c1, cout))
+    else:
+        shapes = ((cin, cout), (cout, cout))
+    return nn.Sequential(OrderedDict([
+        ('SingleConv1', _single_conv(shapes[0][0], shapes[0][1], order, num_groups)),
+        ('SingleConv2', _single_conv(shapes[1][0], shapes[1][1], order, num_groups))]))
+
+
+class _Encoder(nn.Module):
+    def __init__(self, cin, cout, apply_pooling, order, num_groups):
+        super().__init__()
+        self.pooling = nn.MaxPool3d(kernel_size=(2, 2, 2)) if apply_pooling else None
+        self.basic_module = _double_conv(cin, cout, True, order, num_groups)
+
+    def forward(self, x):
+        if self.pooling is not None:
+            x = self.pooling(x)
+        return self.basic_module(x)
+
+
+class _Decoder(nn.Module):
+    def __init__(self, cin, cout, order, num_groups):
+        super().__init__()
+        self.basic_module = _double_conv(cin, cout, False, order, num_groups)
+
+    def forward(self, skip, x):
+        x = F.interpolate(x, size=skip.size()[2:], mode='nearest')
+        return self.basic_module(torch.cat((skip, x), dim=1))
+
+
+class UNet3D(nn.Module):
+    def __init__(self, in_channels, out_channels, final_sigmoid=True, f_maps=64, layer_order='gcr',
+                 num_groups=8, num_levels=4, is_segmentation=True, testing=False, **kwargs):
+        super().__init__()
+        self.testing = testing
+        if isinstance(f_maps, int):
+            f_maps = [f_maps * 2 ** k for k in range(num_levels)]
+        self.encoders = nn.ModuleList([
+            _Encoder(in_channels if i == 0 else f_maps[i - 1], f, i > 0, layer_order, num_groups)
+            for i, f in enumerate(f_maps)])
+        rev = list(reversed(f_maps))
+        self.decoders = nn.ModuleList([
+            _Decoder(rev[i] + rev[i + 1], rev[i + 1], layer_order, num_groups) for i in range(len(rev) - 1)])
+        self.final_conv = nn.Conv3d(f_maps[0], out_channels, 1)
+        if is_segmentation:
+            self.final_activation = nn.Sigmoid() if final_sigmoid else nn.Softmax(dim=1)
+        else:
+            self.final_activation = None
+
+    def forward(self, x):
+        feats = []
+        for enc in self.encoders:
+            x = enc(x)
+            feats.insert(0, x)
+        for dec, skip in zip(self.decoders, feats[1:]):
+            x = dec(skip, x)
+        x = self.final_conv(x)
+        if self.testing and self.final_activation is not None:
+            x = self.final_activation(x)
+        return x
