@@ -210,6 +210,43 @@ int vtaco_scatter_mean(const float* c, const int32_t* idx32, int32_t B, int64_t 
                        int64_t workspace_bytes, float* out_cl, void* stream);
 
 /* ------------------------------------------------------------------------- *
+ * (6) marching cubes over the decoded grid.
+ * Replaces skimage.measure.marching_cubes(value_grid, gradient_direction='ascent')
+ * and the vertex rescale of Generator3D.generate_obj_mesh_wnf
+ * (src/conv_onet/generation.py:268-272).  grid: [nx][ny][nz] fp32 (axis0 = x).
+ * level = `level`, or 0.5f*(min+max) decoded from `level_keys` (the ordered-int keys
+ * the decoder kernel / vtaco_grid_minmax maintain) — skimage's level=None.
+ * A corner is above iff value > level; one vertex per cut grid edge (id order =
+ * lattice order of the owning point, then axis); faces in lattice order of the
+ * cell, then table order (oracle/mc_tables.py); vertices are
+ * (index_coordinate - voffset) * vscale  (0,1 -> array-index coordinates).
+ * counts (device int64[2]) always receives {V, F}; if V > vertex_capacity or
+ * F > face_capacity nothing is emitted and the caller re-runs phase 2 with
+ * larger buffers.  phase: 1 = count, 2 = emit (after a count on the same
+ * scratch), 3 = both.
+ * ------------------------------------------------------------------------- */
+typedef struct vtaco_mc_args {
+  const float* grid;
+  int32_t nx, ny, nz;
+  float level;
+  const int32_t* level_keys;   /* optional device int32[2] */
+  void* scratch;               /* >= vtaco_mc_scratch_bytes(nx,ny,nz) */
+  int64_t scratch_bytes;
+  float* vertices;             /* [vertex_capacity][3] */
+  int64_t vertex_capacity;
+  int32_t* faces;              /* [face_capacity][3] */
+  int64_t face_capacity;
+  int64_t* counts;             /* device int64[2] */
+  float voffset, vscale;
+  int32_t phase;
+} vtaco_mc_args;
+
+int64_t vtaco_mc_scratch_bytes(int32_t nx, int32_t ny, int32_t nz);
+int vtaco_marching_cubes(const vtaco_mc_args* args, void* stream);
+/* keys[0..1] <- ordered-int keys of min / max of grid[0..n) (initialised by the call) */
+int vtaco_grid_minmax(const float* grid, int64_t n, int32_t* keys, void* stream);
+
+/* ------------------------------------------------------------------------- *
  * (4) self-measured FP32 FMA peak (roofline denominator of the decoder).
  * Runs a register-resident FMA loop on every SM and returns achieved FLOP/s in
  * *flops_per_s_host.  variant 0: scalar FFMA, 1: packed FFMA2 (fma.rn.f32x2).

@@ -45,13 +45,12 @@ class DecoderArgs(C.Structure):
 class McArgs(C.Structure):
     _fields_ = [
         ('grid', C.c_void_p), ('nx', C.c_int32), ('ny', C.c_int32), ('nz', C.c_int32),
-        ('x0', C.c_int32), ('x1', C.c_int32),
-        ('level', C.c_float), ('level_from_keys', C.c_void_p),
+        ('level', C.c_float), ('level_keys', C.c_void_p),
         ('scratch', C.c_void_p), ('scratch_bytes', C.c_int64),
         ('vertices', C.c_void_p), ('vertex_capacity', C.c_int64),
         ('faces', C.c_void_p), ('face_capacity', C.c_int64),
         ('counts', C.c_void_p),
-        ('vscale', C.c_float), ('voffset', C.c_float),
+        ('voffset', C.c_float), ('vscale', C.c_float), ('phase', C.c_int32),
     ]
 
 
@@ -82,8 +81,8 @@ def lib():
     L.vtaco_key_to_float_host.argtypes = [C.c_int32]
     L.vtaco_fp32_peak.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double), C.c_void_p]
     for name, argtypes in _OPTIONAL.items():
-        if hasattr(L, name):
-            getattr(L, name).argtypes = argtypes
+        getattr(L, name).argtypes = argtypes
+    L.vtaco_mc_scratch_bytes.restype = C.c_int64
     if L.vtaco_abi_version() != 1:
         raise RuntimeError('vtaco_b200: ABI version mismatch')
     _lib = L
@@ -91,13 +90,9 @@ def lib():
 
 
 _OPTIONAL = {
-    'vtaco_scatter_max_gather': [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int,
-                                 C.c_int64, C.c_int, C.c_void_p],
-    'vtaco_scatter_mean': [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int,
-                           C.c_int64, C.c_void_p],
-    'vtaco_encoder_pointnet': [C.c_void_p, C.c_void_p],
     'vtaco_marching_cubes': [C.POINTER(McArgs), C.c_void_p],
-    'vtaco_mc_scratch_bytes': [C.c_int, C.c_int, C.c_int],
+    'vtaco_mc_scratch_bytes': [C.c_int32, C.c_int32, C.c_int32],
+    'vtaco_grid_minmax': [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p],
 }
 
 
