@@ -1,0 +1,419 @@
+#!/usr/bin/env python
+"""bench.py — occupancy query-points/sec of the conv-occupancy hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[3], the one the metric's target is quoted on: "decodes a
+256^3 occupancy grid"): VTacOH_YCB shapes — LocalPoolPointnet(grid 64^3, hidden 32) +
+UNet3D features, LocalDecoder(simple_local, hidden 32, 5 blocks, forward_img with
+fingertip conditioning), dense 256^3 lattice (resolution_0 = 64), marching cubes at
+level 0.5*(min+max).  Synthetic cloud (3000 visual + 5x128 tactile points), random-init
+weights (fc_1 re-randomised, it is zero-initialised in the reference).
+
+A step = one pass over the whole lattice: fused decode of nx^3 queries (x-slabs over the
+ranks + NCCL all-gather of the logits and min/max exchange when N>1) + marching cubes.
+`value`  : nx^3 / step time, features already resident in HBM (device timed, CUDA events).
+`e2e`    : the same through Generator3D.generate_mesh with HOST buffers: pinned point
+           cloud -> H2D -> encoder (PointNet kernels + UNet3D) -> decode -> MC -> mesh D2H.
+`--impl reference`: the reference's CPU implementation of the path (the oracle port: same
+           torch CPU ops as the reference's modules; the reference is Python and is not
+           present on the GPU box) on a bounded sample of the same lattice.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'occupancy query-points/sec (dense lattice decode + marching cubes)'
+UNIT = 'query-points/s'
+FLOP_PER_QUERY = 30976          # executed MLP FLOPs/query (LocalDecoder.forward)
+FLOP_PER_QUERY_IMG = 33024      # forward_img with a dense c_img tensor
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+# --------------------------------------------------------------------------------------
+# synthetic scene
+# --------------------------------------------------------------------------------------
+def synthetic_scene(seed=0):
+    rs = np.random.RandomState(seed)
+    vis = rs.uniform(-0.5, 0.5, size=(3000, 3))
+    tips = rs.uniform(-0.35, 0.35, size=(5, 3))
+    tac = (tips[:, None, :] + rs.randn(5, 128, 3) * 0.01).reshape(-1, 3)
+    cloud = (np.concatenate([vis, tac], 0) + rs.randn(3640, 3) * 0.005).astype(np.float32)
+    tip_feat = rs.randn(5, 32).astype(np.float32)
+    touch = np.array([True, True, False, True, True])
+    return cloud, tips.astype(np.float64), tip_feat, touch
+
+
+def build_models(device, seed=0):
+    from vtaco_b200.encoder import encoder_dict
+    from vtaco_b200.conv_onet.models import decoder_dict, ConvolutionalOccupancyNetwork
+    torch.manual_seed(seed)
+    enc = encoder_dict['pointnet_local_pool'](dim=3, c_dim=32, padding=0.1, hidden_dim=32, plane_type='grid',
+                                              grid_resolution=64, unet3d=True,
+                                              unet3d_kwargs=dict(num_levels=4, f_maps=32, in_channels=32,
+                                                                 out_channels=32))
+    dec = decoder_dict['simple_local'](dim=3, c_dim=32, padding=0.1, with_contact=False, sample_mode='bilinear',
+                                       hidden_size=32)
+    with torch.no_grad():
+        for m in (enc, dec):
+            for b in m.blocks:
+                b.fc_1.weight.normal_(0, 0.1)
+    return ConvolutionalOccupancyNetwork(dec, enc, device=device).eval()
+
+
+# --------------------------------------------------------------------------------------
+# clocks during the timed region
+# --------------------------------------------------------------------------------------
+class ClockSampler(object):
+    REASONS = {0x1: 'gpu_idle', 0x2: 'applications_clocks_setting', 0x4: 'sw_power_cap', 0x8: 'hw_slowdown',
+               0x10: 'sync_boost', 0x20: 'sw_thermal_slowdown', 0x40: 'hw_thermal_slowdown',
+               0x80: 'hw_power_brake_slowdown', 0x100: 'display_clock_setting'}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._h = None
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        nv = self._nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self._h))
+                for bit, name in self.REASONS.items():
+                    if r & bit and name != 'gpu_idle':
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def __enter__(self):
+        if self._h is not None:
+            self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._h is not None:
+            self._t.join(timeout=1.0)
+
+    def summary(self):
+        if not self.samples:
+            return {'sm_mhz': None, 'sm_max_mhz': self.max_mhz, 'reasons': [], 'note': 'NVML unavailable'}
+        return {'sm_mhz': float(np.median(self.samples)), 'sm_max_mhz': self.max_mhz,
+                'reasons': sorted(self.reasons), 'samples': len(self.samples)}
+
+
+# --------------------------------------------------------------------------------------
+# CPU reference (oracle port) on a bounded sample of the lattice
+# --------------------------------------------------------------------------------------
+class CpuReference(object):
+    """The reference CPU path on a bounded sample: Generator3D.eval_points chunking (100k)
+    through LocalDecoder.forward_img with a dense c_img_all (generation.py:338-383) on
+    `n_sample` consecutive lattice points (whole x-rows from the middle of the nx^3
+    lattice, so fingertip rows are hit), grid-64 features; all host threads."""
+
+    def __init__(self, nx, n_sample, seed=0):
+        from oracle import convonet as oc
+        from vtaco_b200.conv_onet.models import decoder_dict
+        self.oc = oc
+        torch.set_num_threads(os.cpu_count() or 1)
+        g = torch.Generator().manual_seed(seed)
+        self.feats = {'grid': torch.randn(1, 32, 64, 64, 64, generator=g)}
+        torch.manual_seed(seed)
+        dec = decoder_dict['simple_local'](dim=3, c_dim=32, hidden_size=32)
+        with torch.no_grad():
+            for b in dec.blocks:
+                b.fc_1.weight.normal_(0, 0.1)
+        self.W = {k: v.detach() for k, v in dec.state_dict().items()}
+        cloud, tips, tip_feat, touch = synthetic_scene(seed)
+        ax = 1.1 * torch.linspace(-0.5, 0.5, nx)
+        rows = max(1, -(-n_sample // (nx * nx)))
+        x0 = max(0, nx // 2 - rows // 2)
+        gx, gy, gz = torch.meshgrid(ax[x0:x0 + rows], ax, ax, indexing='ij')
+        self.p = torch.stack([gx, gy, gz], -1).reshape(-1, 3)[:n_sample].contiguous()
+        self.c_img = oc.fingertip_c_img(self.p, tips, torch.from_numpy(tip_feat), touch, 0.05)
+        self.n = self.p.shape[0]
+        self.cores = torch.get_num_threads()
+
+    def run(self):
+        t0 = time.perf_counter()
+        self.oc.eval_points(self.p, self.feats, self.W, self.c_img, points_batch_size=100000)
+        return time.perf_counter() - t0
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    nx = args.nx
+    t_all = time.perf_counter()
+    ref = CpuReference(nx, args.cpu_sample)
+    for _ in range(args.warmup):
+        ref.run()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ref.run()
+    dt = time.perf_counter() - t0
+    n, cores = ref.n, ref.cores
+    value = float(n * args.steps / dt)
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3,
+        'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': workload_config(nx, args),
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                         'sample': '%d consecutive lattice points (x-rows from the middle of the %d^3 lattice) per '
+                                   'step through the oracle port of Generator3D.eval_points + '
+                                   'LocalDecoder.forward_img (torch CPU ops, 100k chunks)' % (n, nx)},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0, 'wall_s': time.perf_counter() - t_all,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(nx, args):
+    return {'workload': 'VTacOH_YCB dense %d^3 occupancy-lattice decode (LocalDecoder.forward_img, grid-64 '
+                        'features, fingertip conditioning) + marching cubes' % nx,
+            'nx': nx, 'queries_per_step': nx ** 3, 'encoder': 'LocalPoolPointnet grid64 hidden32 + UNet3D(4 levels)',
+            'decoder': 'LocalDecoder simple_local hidden32 c_dim32 n_blocks5 bilinear', 'input_points': 3640,
+            'parallelism': 'x-slabs of the lattice over %d GPU(s), features replicated, logits all-gathered' % args.gpus,
+            'l2': 'flushed between timed steps (256 MiB write outside the step events)',
+            'kernel_variant': args.variant}
+
+
+# --------------------------------------------------------------------------------------
+# ours
+# --------------------------------------------------------------------------------------
+def run_ours(args, rank, local_rank, world):
+    import torch.distributed as dist
+    from vtaco_b200 import _abi
+    from vtaco_b200.conv_onet.generation import Generator3D
+    import ctypes as C
+
+    dev = torch.device('cuda', local_rank)
+    torch.cuda.set_device(dev)
+    group = None
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+        group = dist.group.WORLD
+    nx = args.nx
+    net = build_models(dev)
+    net.decoder.kernel_variant = args.variant
+    gen = Generator3D(net, device=dev, resolution0=nx // 4, with_img=True, padding=0.1, input_type='pointcloud')
+    cloud_np, tips, tip_feat_np, touch = synthetic_scene(0)
+    cloud_host = torch.from_numpy(cloud_np)[None].pin_memory()
+    tip_feat_host = torch.from_numpy(tip_feat_np).pin_memory()
+    tip_feat = tip_feat_host.to(dev)
+
+    def encode_features():
+        with torch.no_grad():
+            if rank == 0:
+                c = net.encode_inputs(cloud_host.to(dev, non_blocking=True))
+                g = c['grid']
+            else:
+                g = torch.empty((1, 64, 64, 64, 32), dtype=torch.float32, device=dev).permute(0, 4, 1, 2, 3)
+            if world > 1:
+                # broadcast the channels-last storage so every rank decodes from identical bits
+                flat = g.permute(0, 2, 3, 4, 1)
+                flat = flat if flat.is_contiguous() else flat.contiguous()
+                dist.broadcast(flat, 0, group=group)
+                g = flat.permute(0, 4, 1, 2, 3)
+            return {'grid': g}
+
+    c = encode_features()
+    tips_arg = (tips, tip_feat, touch, 0.05)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+
+    def device_step():
+        grid, keys = gen.eval_lattice(c, tips=tips_arg, group=group)
+        return gen.mc(grid, level_keys=keys, voffset=np.float32(nx / 2), vscale=np.float32(1.1 / nx), sync=False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier(group=group)
+        torch.cuda.synchronize(dev)
+
+    # ---- FP32 FMA peak (roofline denominator, self-measured) ----
+    peaks = {}
+    for v in (0, 1):
+        r = C.c_double(0)
+        _abi.check(_abi.lib().vtaco_fp32_peak(v, 4096, C.byref(r), _abi.stream_ptr(dev)), 'fp32_peak')
+        peaks[v] = r.value
+    fp32_peak = max(peaks.values())
+
+    # ---- warm-up ----
+    for _ in range(max(args.warmup, 1)):
+        device_step()
+    # make sure the MC buffers are large enough, then no more host reads inside the steps
+    v_, f_, counts = device_step()
+    V, F = [int(x) for x in counts.cpu()]
+    if V > v_.shape[0] or F > f_.shape[0]:
+        gen.mc._ensure(0, int(V * 1.25) + 16, int(F * 1.25) + 16)
+        device_step()
+
+    # ---- timed region: K steps, per-step CUDA events, L2 flushed in between ----
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
+           torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    wall0 = time.perf_counter()
+    with ClockSampler(local_rank) as clocks:
+        for s in range(args.steps):
+            flush.fill_(float(s))
+            e0, e_dec, e1 = ev[s]
+            e0.record()
+            grid, keys = gen.eval_lattice(c, tips=tips_arg, group=None if world == 1 else group)
+            e_dec.record()
+            gen.mc(grid, level_keys=keys, voffset=np.float32(nx / 2), vscale=np.float32(1.1 / nx), sync=False)
+            e1.record()
+        barrier()
+    wall = time.perf_counter() - wall0
+    step_ms = [e0.elapsed_time(e1) for e0, _, e1 in ev]
+    dec_ms = [e0.elapsed_time(ed) for e0, ed, _ in ev]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX, group=group)
+    total_ms = float(total_ms.item())
+    value = nx ** 3 * args.steps / (total_ms * 1e-3)
+
+    # ---- decoder kernel alone (dominant kernel) for the roofline: events around the launch ----
+    x0, x1 = __import__('vtaco_b200.dist', fromlist=['slab']).slab(nx, rank, world)
+    kq = (x1 - x0) * nx * nx
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    out_grid = gen._grid
+    with torch.no_grad():
+        for a, b in kev:
+            flush.fill_(1.0)
+            a.record()
+            net.decoder.forward_dense(c, nx, x0=x0, x1=x1, use_img=True, tips=tips_arg, out=out_grid, axis=gen._axis)
+            b.record()
+    torch.cuda.synchronize(dev)
+    k_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    achieved = kq * FLOP_PER_QUERY / (k_ms * 1e-3)
+
+    # ---- end-to-end through Generator3D.generate_mesh with host buffers ----
+    e2e_times, h2d, d2h = [], 0, 0
+    for s in range(max(args.warmup, 1) + args.steps):
+        barrier()
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            cc = encode_features()                               # H2D of the pinned cloud + encoder (+ broadcast)
+            tf = tip_feat_host.to(dev, non_blocking=True)        # H2D of the fingertip features
+            grid, keys = gen.eval_lattice(cc, tips=(tips, tf, touch, 0.05), group=group)
+            vv, ff = gen.extract_mesh(grid, keys)                # reads the two counters (D2H)
+            if rank == 0:
+                vh, fh = vv.cpu(), ff.cpu()                      # mesh D2H
+        barrier()
+        if s >= max(args.warmup, 1):
+            e2e_times.append(time.perf_counter() - t0)
+            if rank == 0:
+                h2d = cloud_host.numel() * 4 + tip_feat_host.numel() * 4
+                d2h = vh.numel() * 4 + fh.numel() * 4 + 16
+    e2e_t = torch.tensor([sum(e2e_times)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX, group=group)
+    e2e_value = nx ** 3 * args.steps / float(e2e_t.item())
+
+    if rank == 0:
+        peaks_file = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+        measured = json.load(open(peaks_file)) if os.path.exists(peaks_file) else {}
+        traffic = None
+        prof = os.path.join(ROOT, 'profiles', 'decoder_ncu_summary.json')
+        if os.path.exists(prof):
+            try:
+                traffic = json.load(open(prof)).get('dram_bytes_per_launch')
+            except Exception:
+                traffic = None
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True,
+            'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': workload_config(nx, args),
+            'roofline': {
+                'bound': 'fp32',  # FP32 FMA pipe: 30976 FLOP vs 4 B of HBM traffic per query
+                'kernel': 'decoder_kernel<dense>', 'achieved': achieved / 1e12, 'peak': fp32_peak / 1e12,
+                'unit': 'TFLOP/s', 'frac': achieved / fp32_peak,
+                'peak_source': 'self-measured register-resident FMA loop (vtaco_fp32_peak: scalar %.1f, packed '
+                               'FFMA2 %.1f TFLOP/s); MEASURED_PEAKS.json has no FP32 figure' %
+                               (peaks[0] / 1e12, peaks[1] / 1e12),
+                'flop_per_query': FLOP_PER_QUERY, 'queries_per_launch': kq, 'kernel_ms': k_ms,
+                'frac_of_measured_bf16_tensor_peak': (achieved / 1e12) / measured['bf16_tflops']
+                if 'bf16_tflops' in measured else None,
+                'hbm_algorithmic_gbs': kq * 4 / (k_ms * 1e-3) / 1e9,
+                'hbm_frac_of_measured': (kq * 4 / (k_ms * 1e-3) / 1e9) / measured['hbm_gbs']
+                if 'hbm_gbs' in measured else None,
+                'traffic': traffic,
+            },
+            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                    'ms_per_step': float(e2e_t.item()) / args.steps * 1e3,
+                    'path': 'Generator3D.generate_mesh: pinned cloud -> H2D -> LocalPoolPointnet+UNet3D -> '
+                            'decode -> marching cubes -> mesh D2H'},
+            'gpu_launches': args.steps * 5,  # per step: 1 fused decoder + 4 marching-cubes kernels
+            'stage_ms': {'decode_plus_exchange': float(np.mean(dec_ms)), 'marching_cubes':
+                         float(np.mean(step_ms)) - float(np.mean(dec_ms))},
+            'mesh': {'vertices': V, 'faces': F},
+            'clocks': clocks.summary(), 'wall_s_timed_region': wall,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            ref = CpuReference(nx, args.cpu_sample)
+            ref.run()
+            sec = min(ref.run() for _ in range(3))
+            line['cpu_baseline'] = {
+                'value': ref.n / sec, 'unit': UNIT, 'cores': ref.cores, 'kind': 'port',
+                'sample': '%d consecutive lattice points of the %d^3 lattice, best of 3 after 1 warm-up, oracle port '
+                          'of Generator3D.eval_points + LocalDecoder.forward_img (torch CPU ops, 100k chunks)'
+                          % (ref.n, nx)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--nx', type=int, default=256)
+    ap.add_argument('--variant', type=int, default=1, help='decoder inner loop: 0 scalar FFMA, 1 packed FFMA2')
+    ap.add_argument('--cpu-sample', type=int, default=4 * 256 * 256)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    rank, local_rank, world = env_int('RANK', 0), env_int('LOCAL_RANK', 0), env_int('WORLD_SIZE', 1)
+    os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device — the product path has no CPU fallback '
+                         '(use --impl reference for the CPU arm)')
+    run_ours(args, rank, local_rank, world)
+
+
+if __name__ == '__main__':
+    main()

@@ -58,6 +58,13 @@ class Generator3D(object):
         self._mc = None
         self._grid = None
         self._keys = None
+        self._keys_init = None
+
+    @property
+    def mc(self):
+        if self._mc is None:
+            self._mc = MarchingCubes(self.device)
+        return self._mc
 
     # ------------------------------------------------------------------ reference API
     def eval_points(self, p, c=None, c_img_all=None, vol_bound=None, **kwargs):
@@ -94,7 +101,11 @@ class Generator3D(object):
         if self._grid is None or self._grid.shape[0] != nx:
             self._grid = torch.empty((nx, nx, nx), dtype=torch.float32, device=dev)
             self._axis = dense_axis(nx, self.padding, dev)
-        keys = new_minmax_key(dev)
+        if self._keys is None:
+            self._keys_init = new_minmax_key(dev)
+            self._keys = self._keys_init.clone()
+        keys = self._keys
+        keys.copy_(self._keys_init)
         rank, world = vdist.rank_world(group)
         x0, x1 = vdist.slab(nx, rank, world)
         with torch.no_grad():
@@ -110,12 +121,10 @@ class Generator3D(object):
         """marching cubes at level 0.5*(min+max) + `(v - nx/2) * (1+padding)/nx`
         (reference generation.py:268-272).  Returns device tensors (vertices, faces)."""
         nx = grid.shape[0]
-        if self._mc is None:
-            self._mc = MarchingCubes(self.device)
         box = 1 + self.padding
         if rescale:
-            return self._mc(grid, level=level, level_keys=keys, voffset=np.float32(nx / 2), vscale=np.float32(box / nx))
-        return self._mc(grid, level=level, level_keys=keys)
+            return self.mc(grid, level=level, level_keys=keys, voffset=np.float32(nx / 2), vscale=np.float32(box / nx))
+        return self.mc(grid, level=level, level_keys=keys)
 
     def generate_mesh(self, inputs=None, c=None, tips=None, c_img_all=None, group=None, to_host=True):
         """inputs (1,T,3) point cloud -> encoder -> lattice logits -> mesh.
