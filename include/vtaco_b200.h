@@ -140,7 +140,12 @@ typedef struct vtaco_decoder_args {
   float* contact;          /* optional second head (forward_contact), same shape, or NULL */
   int32_t* minmax_key;     /* optional [2]: ordered-int keys of min / max logit, updated with
                               atomicMin/atomicMax (caller initialises to INT32_MAX, INT32_MIN) */
-  int32_t variant;         /* 0 = default inner loop; 1 = packed FFMA2 inner loop (tuning knob) */
+  int32_t variant;         /* 0 = scalar-FFMA SIMT kernel; 1 = packed-FFMA2 SIMT kernel; 2 = tcgen05 3xTF32 kernel */
+  /* variant 2 only: the 3*n_blocks hidden matrices (per block: fc_c[i], fc_0, fc_1) as TF32 hi / lo
+   * pairs in the UMMA canonical K-major no-swizzle layout, 2048 floats per matrix:
+   *   float index of element (n = out, k = in) = (k/4)*128 + (n/8)*32 + (n%8)*4 + (k%4),
+   *   hi block (1024 floats) = rn_tf32(W), lo block (1024 floats) = tf32(W - hi). */
+  const float* weights_tc;
 } vtaco_decoder_args;
 
 int vtaco_decoder_forward(const vtaco_decoder_args* args, void* stream);

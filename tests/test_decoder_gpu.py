@@ -23,7 +23,7 @@ def make_decoder(W, leaky=False, contact=None, mode='bilinear', division='true')
     return dec
 
 
-@pytest.mark.parametrize('variant', [0, 1])
+@pytest.mark.parametrize('variant', [0, 1, 2])
 @pytest.mark.parametrize('tag', ['relu', 'leaky'])
 def test_decoder_golden(tag, variant):
     g = load('decoder_%s.npz' % tag)
@@ -54,21 +54,27 @@ def test_decoder_golden(tag, variant):
         assert close(dec.sample_plane_feature(p, feats['yz'], 'yz').cpu().numpy(), g['sample_yz']) < 1e-5
 
 
+@pytest.mark.parametrize('variant', [1, 2])
 @pytest.mark.parametrize('B,N', [(1, 1), (1, 511), (3, 513), (2, 100000), (32, 2048)])
-def test_decoder_vs_oracle_shapes(B, N):
+def test_decoder_vs_oracle_shapes(B, N, variant):
     """ragged / tiny / training-shape batches against the oracle (CPU)."""
     from oracle import convonet as oc
     g = load('decoder_relu.npz')
     W = weights(g)
     dec = make_decoder(W, contact=True)
+    dec.kernel_variant = variant
     Rg = 24
     feats = {'grid': torch.from_numpy(rs_randn(7, B, 32, Rg, Rg, Rg))}
     p = torch.from_numpy(rs_uniform(8, -0.6, 0.6, B, N, 3))
     c_img = torch.from_numpy(rs_randn(9, B, N, 32))
     with torch.no_grad():
+        fc = {k: v.cuda() for k, v in feats.items()}
         ref = oc.decoder_forward(p, feats, W, 'img', c_img=c_img)
-        got = dec.forward_img(p.cuda(), {k: v.cuda() for k, v in feats.items()}, c_img.cuda())
-    assert close(got.cpu().numpy(), ref.numpy()) < TOL
+        got = dec.forward_img(p.cuda(), fc, c_img.cuda())
+        assert close(got.cpu().numpy(), ref.numpy()) < TOL
+        ref = oc.decoder_forward(p, feats, W, 'contact')
+        got = dec.forward_contact(p.cuda(), fc)
+        assert close(got[0].cpu().numpy(), ref[0].numpy()) < TOL and close(got[1].cpu().numpy(), ref[1].numpy()) < TOL
 
 
 def test_decoder_empty_and_errors():
@@ -97,12 +103,14 @@ def test_channels_last_features_zero_copy():
     assert torch.equal(a, b)
 
 
-def test_dense_matches_flat_and_golden():
+@pytest.mark.parametrize('variant', [1, 2])
+def test_dense_matches_flat_and_golden(variant):
     """dense-lattice mode == flat mode on the same lattice; both == reference eval_points."""
     from vtaco_b200.common import make_3d_grid
     g = load('eval_points.npz')
     W = weights(g)
     dec = make_decoder(W)
+    dec.kernel_variant = variant
     nx, Rg = int(g['nx']), int(g['Rg'])
     c = {'grid': torch.from_numpy(rs_randn(int(g['feat_seed']), 1, 32, Rg, Rg, Rg)).cuda()}
     pts = (1.1 * make_3d_grid((-0.5,) * 3, (0.5,) * 3, (nx,) * 3)).cuda()

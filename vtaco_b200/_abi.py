@@ -38,7 +38,7 @@ class DecoderArgs(C.Structure):
         ('n_tips', C.c_int32), ('tips', (C.c_double * 3) * MAX_TIPS), ('tip_touch', C.c_int32 * MAX_TIPS),
         ('tip_radius', C.c_double), ('tip_feat', C.c_void_p),
         ('logits', C.c_void_p), ('contact', C.c_void_p), ('minmax_key', C.c_void_p),
-        ('variant', C.c_int32),
+        ('variant', C.c_int32), ('weights_tc', C.c_void_p),
     ]
 
 

@@ -75,6 +75,7 @@ class LocalDecoder(nn.Module):
         self.division = 'cuda'
         self.kernel_variant = 0
         self._pack_cache = None
+        self._pack_tc_cache = None
         self._cl_cache = {}
 
     # ------------------------------------------------------------------ packing
@@ -121,7 +122,34 @@ class LocalDecoder(nn.Module):
                 buf[o + H:o + 2 * H] = self.fc_out_contact.weight.reshape(-1)
                 buf[o + 65] = self.fc_out_contact.bias[0]
         self._pack_cache = (key, buf)
+        self._pack_tc_cache = None
         return buf
+
+    def _packed_weights_tc(self):
+        """TF32 hi/lo pairs of the 3*n_blocks hidden matrices in the UMMA canonical K-major
+        layout expected by the tcgen05 kernel (include/vtaco_b200.h, `weights_tc`)."""
+        self._packed_weights()
+        if self._pack_tc_cache is not None:
+            return self._pack_tc_cache
+        dev = self.fc_p.weight.device
+        n = torch.arange(32, device=dev).view(32, 1)
+        k = torch.arange(32, device=dev).view(1, 32)
+        idx = ((k // 4) * 128 + (n // 8) * 32 + (n % 8) * 4 + (k % 4)).reshape(-1)
+        mats = []
+        with torch.no_grad():
+            for i in range(self.n_blocks):
+                wc = self.fc_c[i].weight if self.c_dim else torch.zeros(32, 32, device=dev)
+                mats += [wc, self.blocks[i].fc_0.weight, self.blocks[i].fc_1.weight]
+            out = torch.zeros(len(mats), 2, 1024, dtype=torch.float32, device=dev)
+            for m, w in enumerate(mats):
+                w = w.detach().float().contiguous()
+                bits = w.view(torch.int32)
+                hi = ((bits + 0x1000) & ~0x1fff).view(torch.float32)       # round-to-nearest TF32 (ties away)
+                lo = ((w - hi).view(torch.int32) & ~0x1fff).view(torch.float32)
+                out[m, 0, idx] = hi.reshape(-1)
+                out[m, 1, idx] = lo.reshape(-1)
+        self._pack_tc_cache = out.reshape(-1).contiguous()
+        return self._pack_tc_cache
 
     def _features_cl(self, c_plane):
         """Channels-last views/copies of the feature tensors (cached per tensor version)."""
@@ -184,7 +212,12 @@ class LocalDecoder(nn.Module):
         a.n_blocks = self.n_blocks
         a.leaky = int(self.leaky)
         a.variant = int(self.kernel_variant)
-        return a, (cl, w)
+        keep = [cl, w]
+        if a.variant == 2:
+            wtc = self._packed_weights_tc()
+            a.weights_tc = wtc.data_ptr()
+            keep.append(wtc)
+        return a, keep
 
     def _decode(self, p, c_plane, use_img=False, c_img=None, contact=False):
         _abi.require_cuda(p, 'p')
@@ -209,6 +242,8 @@ class LocalDecoder(nn.Module):
                 raise ValueError('c_img must have shape (B, N, c_dim)')
             cic = c_img.contiguous()
             a.c_img = cic.data_ptr() if self.c_dim else None
+            if a.variant == 2 and self.c_dim:
+                a.variant = 1  # per-query c_img tensor: packed-FFMA2 SIMT kernel
         a.logits = out.data_ptr()
         if contact:
             if not hasattr(self, 'fc_out_contact'):
@@ -280,6 +315,8 @@ class LocalDecoder(nn.Module):
             if cic.size(0) != nx ** 3:
                 raise ValueError('dense c_img must have nx^3 rows')
             a.c_img = cic.data_ptr()
+            if a.variant == 2:
+                a.variant = 1
         if use_img and tips is not None:
             pos, feat, touch, radius = tips
             F_ = len(pos)

@@ -1,0 +1,442 @@
+// Fused LocalDecoder on the 5th-gen tensor cores (tcgen05 + TMEM), sm_100a.
+//
+// Same contract as decoder.cu (reference src/conv_onet/models/decoder.py:71-161); selected
+// with vtaco_decoder_args.variant == 2.  Why: ncu on the SIMT kernel shows the 32-wide
+// contraction is pipe-bound (shared-memory wavefronts 71 %, FMA pipe 62 %), not latency
+// bound (profiles/decoder_ncu_summary.json) — the condition the design brief sets for moving
+// it to the tensor pipe.
+//
+// fp32 fidelity on a TF32 pipe: every operand is split x = hi + lo with hi = rn_tf32(x) and the
+// product is evaluated as hi*hi + lo*hi + hi*lo (3xTF32, fp32 accumulation in TMEM); the
+// dropped lo*lo term and the truncation of lo are ~2^-22 relative.
+//
+// Structure (one persistent CTA per SM, 256 threads = 2 independent groups of 4 warps):
+//   * a group owns a tile of 128 queries = the 128 TMEM lanes; thread t <-> query t <-> lane t;
+//   * all 3*n_blocks weight matrices (hi and lo, UMMA canonical K-major, no swizzle) stay in
+//     shared memory for the life of the CTA (120 KB); they are the B operands;
+//   * activations are the A operands and live in TMEM (tcgen05.st from registers), so a layer
+//     costs per thread: tcgen05.ld of 32 accumulator columns, bias/residual/ReLU/split
+//     (~4 ALU ops per element), tcgen05.st of hi and lo — no shared-memory traffic at all;
+//   * one elected thread per group issues the 12 tcgen05.mma (M128 N32 K8, kind::tf32) of a
+//     layer and commits to the group's mbarrier; the two groups interleave on the tensor pipe,
+//     so one group's ALU phase overlaps the other's MMA phase;
+//   * the residual stream stays in registers; feature gather, fc_p, tips and fc_out run on the
+//     CUDA cores exactly as in the SIMT kernel.
+#include "decoder_common.cuh"
+
+namespace vtaco {
+
+constexpr int kTcThreads = 256;
+constexpr int kTcGroups = 2;
+constexpr int kTcTile = 128;
+constexpr int kColsPerGroup = 192;   // C_hi 0, C_lo 32, X_hi 64, X_lo 96, D 128, DC 160
+constexpr int kStageStride = 36;     // floats per staged query row (conflict-free LDS.128)
+constexpr uint32_t kIdescTf32 = (1u << 4) | (2u << 7) | (2u << 10) | (4u << 17) | (8u << 24);  // F32 acc, TF32 x TF32, K-major, N=32, M=128
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory"); }
+
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem desc]
+__device__ __forceinline__ void tc_mma_ts(uint32_t d, uint32_t a, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(d), "r"(a), "l"(bdesc), "r"(kIdescTf32), "r"(accumulate)
+      : "memory");
+}
+// K-major, no swizzle: 8 rows x 16 B core matrices; K-chunk stride 512 B, 8-row-group stride 128 B
+__device__ __forceinline__ uint64_t make_bdesc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);
+  d |= (uint64_t)(512 >> 4) << 16;   // leading (K) byte offset
+  d |= (uint64_t)(128 >> 4) << 32;   // stride (N) byte offset
+  d |= (uint64_t)1 << 46;            // descriptor version (Blackwell)
+  return d;
+}
+
+#define TC_R32(r) r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7], r[8], r[9], r[10], r[11], r[12], r[13], r[14], r[15], \
+                  r[16], r[17], r[18], r[19], r[20], r[21], r[22], r[23], r[24], r[25], r[26], r[27], r[28], r[29], r[30], r[31]
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%32], "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31};"
+      ::"r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+        "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+        "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]), "r"(taddr)
+      : "memory");
+}
+
+__device__ __forceinline__ uint32_t rn_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return u;
+}
+
+// x[32] (fp32) -> hi/lo TF32 operands stored to TMEM columns [col, col+32) and [col+32, col+64)
+__device__ __forceinline__ void split_store(uint32_t taddr, const float (&x)[32]) {
+  uint32_t hi[32], lo[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    hi[j] = rn_tf32(x[j]);
+    lo[j] = __float_as_uint(x[j] - __uint_as_float(hi[j]));
+  }
+  tmem_st32(taddr, hi);
+  tmem_st32(taddr + 32, lo);
+}
+
+// one layer: D (fresh) = A_hi*W_hi + A_lo*W_hi + A_hi*W_lo ; issued by one thread
+__device__ __forceinline__ void issue_layer(uint32_t d, uint32_t a_hi, uint32_t w_smem) {
+  const uint32_t a_lo = a_hi + 32;
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) tc_mma_ts(d, a_lo + 8 * kk, make_bdesc(w_smem + kk * 1024), kk > 0);
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) tc_mma_ts(d, a_hi + 8 * kk, make_bdesc(w_smem + 4096 + kk * 1024), 1);
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) tc_mma_ts(d, a_hi + 8 * kk, make_bdesc(w_smem + kk * 1024), 1);
+}
+
+struct TcSmem {
+  // byte offsets into dynamic shared memory
+  int w, bias, small, tips, stage, bars, tmem_ptr, total;
+};
+__host__ __device__ inline TcSmem tc_smem_layout(int n_blocks) {
+  TcSmem s;
+  s.w = 0;
+  s.bias = s.w + 3 * n_blocks * 8192;
+  s.small = s.bias + 3 * n_blocks * 32 * 4;       // Wp[3][32], bp[32], Wout[64], bout[2]+pad
+  s.tips = s.small + (128 + 68) * 4;
+  s.stage = s.tips + VTACO_MAX_TIPS * 32 * 4;
+  s.stage = (s.stage + 15) / 16 * 16;
+  s.bars = s.stage + 8 * 32 * kStageStride * 4;
+  s.tmem_ptr = s.bars + 64;
+  s.total = s.tmem_ptr + 16;
+  return s;
+}
+
+template <bool DENSE>
+__global__ void __launch_bounds__(kTcThreads, 1) decoder_tc_kernel(const __grid_constant__ DecParams P,
+                                                                   const float* __restrict__ wtc) {
+  extern __shared__ __align__(1024) unsigned char tsm[];
+  const TcSmem L = tc_smem_layout(P.n_blocks);
+  float* sWtc = reinterpret_cast<float*>(tsm + L.w);
+  float* sBias = reinterpret_cast<float*>(tsm + L.bias);
+  float* sSmall = reinterpret_cast<float*>(tsm + L.small);
+  float* sTip = reinterpret_cast<float*>(tsm + L.tips);
+  float* sStage = reinterpret_cast<float*>(tsm + L.stage);
+  uint64_t* sBars = reinterpret_cast<uint64_t*>(tsm + L.bars);
+  uint32_t* sTmem = reinterpret_cast<uint32_t*>(tsm + L.tmem_ptr);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = warp >> 2, wg = warp & 3, tg = tid & 127;
+  const int nb = P.n_blocks;
+
+  // ---- one-time setup: weights, biases, barriers, TMEM ----
+  for (int i = tid; i < 3 * nb * 2048 / 4; i += kTcThreads)
+    reinterpret_cast<float4*>(sWtc)[i] = __ldg(reinterpret_cast<const float4*>(wtc) + i);
+  for (int i = tid; i < nb * 32; i += kTcThreads) {
+    const int b = i >> 5, j = i & 31;
+    const float* Wb = P.weights + VTACO_DEC_OFF_BLOCKS + b * VTACO_DEC_BLOCK_STRIDE;
+    sBias[(3 * b + 0) * 32 + j] = Wb[1024 + j];
+    sBias[(3 * b + 1) * 32 + j] = Wb[1056 + 1024 + j];
+    sBias[(3 * b + 2) * 32 + j] = Wb[2112 + 1024 + j];
+  }
+  for (int i = tid; i < 128; i += kTcThreads) sSmall[i] = P.weights[(P.use_img ? VTACO_DEC_OFF_WPI : VTACO_DEC_OFF_WP) + i];
+  for (int i = tid; i < 68; i += kTcThreads)
+    sSmall[128 + i] = P.weights[VTACO_DEC_OFF_BLOCKS + nb * VTACO_DEC_BLOCK_STRIDE + i];
+  if (P.n_tips > 0) {
+    for (int o = tid; o < P.n_tips * 32; o += kTcThreads) {
+      const int f = o >> 5, j = o & 31;
+      float a = 0.f;
+      for (int k = 0; k < 32; ++k)
+        a = fmaf(__ldg(P.weights + VTACO_DEC_OFF_WIMG + k * 32 + j), __ldg(P.tip_feat + f * 32 + k), a);
+      sTip[o] = a;
+    }
+  }
+  if (tid == 0) {
+    for (int i = 0; i < 2 * kTcGroups; ++i) mbar_init(smem_u32(sBars + i), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sTmem)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *sTmem;
+  // this warp's TMEM window: lanes 32*wg.., columns of group g
+  const uint32_t tbase = tmem_base + ((uint32_t)(32 * wg) << 16) + (uint32_t)(g * kColsPerGroup);
+  const uint32_t tC = tbase, tX = tbase + 64, tD = tbase + 128, tDC = tbase + 160;
+  // accumulator / operand addresses as seen by the MMA (lane 0 of the CTA, group's columns)
+  const uint32_t mbase = tmem_base + (uint32_t)(g * kColsPerGroup);
+  const uint32_t mC = mbase, mX = mbase + 64, mD = mbase + 128, mDC = mbase + 160;
+  const uint32_t barD = smem_u32(sBars + 2 * g), barDC = smem_u32(sBars + 2 * g + 1);
+  const uint32_t wsm = smem_u32(sWtc);
+  uint32_t phD = 0, phDC = 0;
+  float* stage = sStage + warp * 32 * kStageStride;
+  const int grp = lane >> 3, sub = lane & 7;
+  const int nx = P.nx;
+  float vmin = CUDART_INF_F, vmax = -CUDART_INF_F;
+
+  for (long long tile = (long long)blockIdx.x * kTcGroups + g; tile < P.n_tiles;
+       tile += (long long)gridDim.x * kTcGroups) {
+    // ---------------- this thread's query ----------------
+    float px, py, pz;
+    long long oidx;
+    int qb;
+    bool valid;
+    if (DENSE) {
+      long long t = tile;
+      const int bz = (int)(t % P.t_nbz); t /= P.t_nbz;   // bricks: 4 (x) x 4 (y) x 8 (z)
+      const int by = (int)(t % P.t_nby); t /= P.t_nby;
+      const int bx = (int)(t % P.t_nbx);
+      const int b = (int)(t / P.t_nbx);
+      const int ix = P.x0 + bx * 4 + (tg >> 5), iy = by * 4 + ((tg >> 3) & 3), iz = bz * 8 + (tg & 7);
+      valid = (ix < P.t_xend) && (iy < nx) && (iz < nx);
+      px = __ldg(P.axis + min(ix, nx - 1));
+      py = __ldg(P.axis + min(iy, nx - 1));
+      pz = __ldg(P.axis + min(iz, nx - 1));
+      qb = b;
+      oidx = (((long long)b * nx + ix) * nx + iy) * nx + iz;
+    } else {
+      const long long n = tile * kTcTile + tg;
+      valid = n < P.total;
+      const long long nn = valid ? n : 0;
+      px = __ldg(P.p + nn * 3 + 0);
+      py = __ldg(P.p + nn * 3 + 1);
+      pz = __ldg(P.p + nn * 3 + 2);
+      qb = (int)(nn / P.N);
+      oidx = nn;
+    }
+    if (!valid) oidx = 0;
+
+    // ---------------- gather: 8 lanes per query -> staged rows ----------------
+    if (P.has_c) {
+#pragma unroll 2
+      for (int it = 0; it < 8; ++it) {
+        const int src = it * 4 + grp;
+        const float x = __shfl_sync(kFull, px, src);
+        const float y = __shfl_sync(kFull, py, src);
+        const float z = __shfl_sync(kFull, pz, src);
+        const int b = __shfl_sync(kFull, qb, src);
+        float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (P.grid) {
+          const int R = P.Rg;
+          const float4* vol = reinterpret_cast<const float4*>(P.grid) + (size_t)b * R * R * R * 8 + sub;
+          c = sample_volume(vol, R, norm3d(x, P.nc), norm3d(y, P.nc), norm3d(z, P.nc), P.nearest);
+        }
+        if (P.plane[0] || P.plane[1] || P.plane[2]) {
+          const int R = P.Rp;
+          const float ux = norm2d(x, P.nc), uy = norm2d(y, P.nc), uz = norm2d(z, P.nc);
+          const size_t boff = (size_t)b * R * R * 8 + sub;
+          if (P.plane[0]) c = f4_add(c, sample_plane(reinterpret_cast<const float4*>(P.plane[0]) + boff, R, ux, uz, P.nearest));
+          if (P.plane[1]) c = f4_add(c, sample_plane(reinterpret_cast<const float4*>(P.plane[1]) + boff, R, ux, uy, P.nearest));
+          if (P.plane[2]) c = f4_add(c, sample_plane(reinterpret_cast<const float4*>(P.plane[2]) + boff, R, uy, uz, P.nearest));
+        }
+        *reinterpret_cast<float4*>(stage + src * kStageStride + 4 * sub) = c;
+      }
+      __syncwarp();
+      float cv[32];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 v = *reinterpret_cast<const float4*>(stage + lane * kStageStride + 4 * j);
+        cv[4 * j] = v.x; cv[4 * j + 1] = v.y; cv[4 * j + 2] = v.z; cv[4 * j + 3] = v.w;
+      }
+      __syncwarp();
+      split_store(tC, cv);
+      tc_wait_st();
+      tc_fence_before();
+      group_sync(g);
+      if (tg == 0) {
+        tc_fence_after();
+        issue_layer(mDC, mC, wsm + 0 * 8192);
+        tc_commit(barDC);
+      }
+    }
+
+    // ---------------- net = fc_p(p) | fc_p_img(p, tip feature) on the CUDA cores ----------------
+    float net[32];
+    {
+      const float4* w0 = reinterpret_cast<const float4*>(sSmall);
+      const float4* w1 = reinterpret_cast<const float4*>(sSmall + 32);
+      const float4* w2 = reinterpret_cast<const float4*>(sSmall + 64);
+      const float4* bp = reinterpret_cast<const float4*>(sSmall + 96);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 a0 = w0[j], a1 = w1[j], a2 = w2[j], bb = bp[j];
+        net[4 * j + 0] = fmaf(a2.x, pz, fmaf(a1.x, py, fmaf(a0.x, px, bb.x)));
+        net[4 * j + 1] = fmaf(a2.y, pz, fmaf(a1.y, py, fmaf(a0.y, px, bb.y)));
+        net[4 * j + 2] = fmaf(a2.z, pz, fmaf(a1.z, py, fmaf(a0.z, px, bb.z)));
+        net[4 * j + 3] = fmaf(a2.w, pz, fmaf(a1.w, py, fmaf(a0.w, px, bb.w)));
+      }
+    }
+    if (P.use_img && P.n_tips > 0) {
+      const int f = tip_assign(P, px, py, pz);
+      if (f >= 0) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) net[j] += sTip[f * 32 + j];
+      }
+    }
+
+    // ---------------- residual blocks ----------------
+    for (int i = 0; i < nb; ++i) {
+      uint32_t r[32];
+      float x[32];
+      if (P.has_c) {  // net = net + fc_c[i](c)
+        mbar_wait(barDC, phDC); phDC ^= 1;
+        tc_fence_after();
+        tmem_ld32(tDC, r);
+        tc_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) net[j] += __uint_as_float(r[j]) + sBias[(3 * i) * 32 + j];
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[j] = fmaxf(net[j], 0.f);
+      split_store(tX, x);
+      tc_wait_st();
+      tc_fence_before();
+      group_sync(g);
+      if (tg == 0) {
+        tc_fence_after();
+        issue_layer(mD, mX, wsm + (3 * i + 1) * 8192);      // fc_0(relu(net))
+        tc_commit(barD);
+        if (P.has_c && i + 1 < nb) {                        // next block's fc_c(c): overlaps the ALU phases
+          issue_layer(mDC, mC, wsm + (3 * (i + 1)) * 8192);
+          tc_commit(barDC);
+        }
+      }
+      mbar_wait(barD, phD); phD ^= 1;
+      tc_fence_after();
+      tmem_ld32(tD, r);
+      tc_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[j] = fmaxf(__uint_as_float(r[j]) + sBias[(3 * i + 1) * 32 + j], 0.f);
+      split_store(tX, x);
+      tc_wait_st();
+      tc_fence_before();
+      group_sync(g);
+      if (tg == 0) {
+        tc_fence_after();
+        issue_layer(mD, mX, wsm + (3 * i + 2) * 8192);      // fc_1(relu(h))
+        tc_commit(barD);
+      }
+      mbar_wait(barD, phD); phD ^= 1;
+      tc_fence_after();
+      tmem_ld32(tD, r);
+      tc_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) net[j] += __uint_as_float(r[j]) + sBias[(3 * i + 2) * 32 + j];
+    }
+
+    // ---------------- heads ----------------
+    {
+      const float* Wo = sSmall + 128;
+      const float slope = P.leaky ? 0.2f : 0.0f;
+      float o = Wo[64], oc = Wo[65];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float a = net[j] > 0.f ? net[j] : net[j] * slope;
+        o = fmaf(Wo[j], a, o);
+        oc = fmaf(Wo[32 + j], a, oc);
+      }
+      if (valid) {
+        P.logits[oidx] = o;
+        if (P.contact) P.contact[oidx] = oc;
+        vmin = fminf(vmin, o);
+        vmax = fmaxf(vmax, o);
+      }
+    }
+    // all TMEM reads of this tile are complete (wait::ld) before the next tile's stores:
+    tc_fence_before();
+    group_sync(g);
+    tc_fence_after();
+  }
+
+  if (P.minmax_key) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      vmin = fminf(vmin, __shfl_xor_sync(kFull, vmin, d));
+      vmax = fmaxf(vmax, __shfl_xor_sync(kFull, vmax, d));
+    }
+    if (lane == 0 && vmin <= vmax) {
+      atomicMin(P.minmax_key, float_to_key(vmin));
+      atomicMax(P.minmax_key + 1, float_to_key(vmax));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+int launch_decoder_tc(DecParams P, bool dense, const float* wtc, cudaStream_t stream) {
+  if (!wtc) return VTACO_ERR_INVALID_ARG;
+  if (P.use_img && P.c_img) return VTACO_ERR_UNSUPPORTED;  // dense c_img tensor: SIMT kernel
+  if (dense) {
+    P.t_xend = P.x1;
+    P.t_nbz = (P.nx + 7) / 8;
+    P.t_nby = (P.nx + 3) / 4;
+    P.t_nbx = (P.x1 - P.x0 + 3) / 4;
+    P.n_tiles = (long long)P.B * P.t_nbx * P.t_nby * P.t_nbz;
+  } else {
+    P.n_tiles = (P.total + kTcTile - 1) / kTcTile;
+  }
+  const TcSmem L = tc_smem_layout(P.n_blocks);
+  if (L.total > 227 * 1024) return VTACO_ERR_UNSUPPORTED;
+  static size_t configured[2][64] = {{0}};
+  int dev = 0;
+  VTACO_CUDA_CHECK(cudaGetDevice(&dev));
+  if (configured[dense][dev & 63] < (size_t)L.total) {
+    if (dense) VTACO_CUDA_CHECK(cudaFuncSetAttribute(decoder_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+    else VTACO_CUDA_CHECK(cudaFuncSetAttribute(decoder_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+    configured[dense][dev & 63] = L.total;
+  }
+  long long grid = (P.n_tiles + kTcGroups - 1) / kTcGroups;
+  if (grid > num_sms()) grid = num_sms();
+  if (dense) decoder_tc_kernel<true><<<(unsigned)grid, kTcThreads, L.total, stream>>>(P, wtc);
+  else decoder_tc_kernel<false><<<(unsigned)grid, kTcThreads, L.total, stream>>>(P, wtc);
+  VTACO_LAUNCH_CHECK();
+  return VTACO_OK;
+}
+
+}  // namespace vtaco
