@@ -144,7 +144,9 @@ typedef struct vtaco_decoder_args {
   /* variant 2 only: the 3*n_blocks hidden matrices (per block: fc_c[i], fc_0, fc_1) as TF32 hi / lo
    * pairs in the UMMA canonical K-major no-swizzle layout, 2048 floats per matrix:
    *   float index of element (n = out, k = in) = (k/4)*128 + (n/8)*32 + (n%8)*4 + (k%4),
-   *   hi block (1024 floats) = rn_tf32(W), lo block (1024 floats) = tf32(W - hi). */
+   *   hi block (1024 floats) = rn_tf32(W), lo block (1024 floats) = tf32(W - hi);
+   * followed by 2*n_blocks+1 bias K-blocks of 256 floats in the same layout with k in [0,8): row k=0
+   * = bias hi, k=1 = bias lo, for the steps bc_0 | b0_i, b1_i + bc_{i+1} (i = 0..n_blocks-1). */
   const float* weights_tc;
 } vtaco_decoder_args;
 

@@ -140,14 +140,34 @@ class LocalDecoder(nn.Module):
             for i in range(self.n_blocks):
                 wc = self.fc_c[i].weight if self.c_dim else torch.zeros(32, 32, device=dev)
                 mats += [wc, self.blocks[i].fc_0.weight, self.blocks[i].fc_1.weight]
+            def split(w):
+                w = w.detach().float().contiguous()
+                hi = ((w.view(torch.int32) + 0x1000) & ~0x1fff).view(torch.float32)   # round-to-nearest TF32 (ties away)
+                lo = ((w - hi).view(torch.int32) & ~0x1fff).view(torch.float32)
+                return hi, lo
+
             out = torch.zeros(len(mats), 2, 1024, dtype=torch.float32, device=dev)
             for m, w in enumerate(mats):
-                w = w.detach().float().contiguous()
-                bits = w.view(torch.int32)
-                hi = ((bits + 0x1000) & ~0x1fff).view(torch.float32)       # round-to-nearest TF32 (ties away)
-                lo = ((w - hi).view(torch.int32) & ~0x1fff).view(torch.float32)
+                hi, lo = split(w)
                 out[m, 0, idx] = hi.reshape(-1)
                 out[m, 1, idx] = lo.reshape(-1)
+            # bias K-blocks (K=8, N=32): row k=0 holds bias_hi, row k=1 bias_lo; step order
+            # bc_0 | b0_0, b1_0+bc_1 | b0_1, b1_1+bc_2 | ...
+            zero = torch.zeros(32, device=dev)
+            bc = [self.fc_c[i].bias.detach().float() if self.c_dim else zero for i in range(self.n_blocks)]
+            steps = [bc[0]]
+            for i in range(self.n_blocks):
+                steps.append(self.blocks[i].fc_0.bias.detach().float())
+                nxt = bc[i + 1] if i + 1 < self.n_blocks else zero
+                steps.append(self.blocks[i].fc_1.bias.detach().float() + nxt)
+            nn_ = torch.arange(32, device=dev)
+            bidx0 = (nn_ // 8) * 32 + (nn_ % 8) * 4          # k = 0
+            bias = torch.zeros(len(steps), 256, dtype=torch.float32, device=dev)
+            for m, b in enumerate(steps):
+                hi, lo = split(b)
+                bias[m, bidx0] = hi
+                bias[m, bidx0 + 1] = lo
+            out = torch.cat([out.reshape(-1), bias.reshape(-1)])
         self._pack_tc_cache = out.reshape(-1).contiguous()
         return self._pack_tc_cache
 

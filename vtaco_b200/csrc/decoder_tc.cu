@@ -10,26 +10,29 @@
 // product is evaluated as hi*hi + lo*hi + hi*lo (3xTF32, fp32 accumulation in TMEM); the
 // dropped lo*lo term and the truncation of lo are ~2^-22 relative.
 //
-// Structure (one persistent CTA per SM, 256 threads = 2 independent groups of 4 warps):
+// Structure (one persistent CTA per SM, 384 threads = 3 independent groups of 4 warps):
 //   * a group owns a tile of 128 queries = the 128 TMEM lanes; thread t <-> query t <-> lane t;
 //   * all 3*n_blocks weight matrices (hi and lo, UMMA canonical K-major, no swizzle) stay in
 //     shared memory for the life of the CTA (120 KB); they are the B operands;
 //   * activations are the A operands and live in TMEM (tcgen05.st from registers), so a layer
 //     costs per thread: tcgen05.ld of 32 accumulator columns, bias/residual/ReLU/split
 //     (~4 ALU ops per element), tcgen05.st of hi and lo — no shared-memory traffic at all;
-//   * one elected thread per group issues the 12 tcgen05.mma (M128 N32 K8, kind::tf32) of a
-//     layer and commits to the group's mbarrier; the two groups interleave on the tensor pipe,
-//     so one group's ALU phase overlaps the other's MMA phase;
+//   * biases ride along as one more K-block: a constant (1,1,0,..) A block times a B block
+//     whose rows 0/1 hold the bias hi/lo; fc_c[i+1](c) accumulates into the same TMEM
+//     accumulator as fc_1 of block i, so a block costs 2 accumulator reads, not 3;
+//   * one elected thread per group (the role rotates over the 4 warps) issues the tcgen05.mma
+//     (M128 N32 K8, kind::tf32) of a step and commits to the group's mbarrier; the groups
+//     interleave on the tensor pipe, so one group's ALU phase overlaps the others' MMA phases;
 //   * the residual stream stays in registers; feature gather, fc_p, tips and fc_out run on the
 //     CUDA cores exactly as in the SIMT kernel.
 #include "decoder_common.cuh"
 
 namespace vtaco {
 
-constexpr int kTcThreads = 256;
-constexpr int kTcGroups = 2;
+constexpr int kTcThreads = 384;
+constexpr int kTcGroups = 3;
 constexpr int kTcTile = 128;
-constexpr int kColsPerGroup = 192;   // C_hi 0, C_lo 32, X_hi 64, X_lo 96, D 128, DC 160
+constexpr int kColsPerGroup = 168;   // C_hi 0, C_lo 32, X_hi 64, X_lo 96, ones 128 (8), D 136 (32)
 constexpr int kStageStride = 36;     // floats per staged query row (conflict-free LDS.128)
 constexpr uint32_t kIdescTf32 = (1u << 4) | (2u << 7) | (2u << 10) | (4u << 17) | (8u << 24);  // F32 acc, TF32 x TF32, K-major, N=32, M=128
 
@@ -122,15 +125,89 @@ __device__ __forceinline__ void split_store(uint32_t taddr, const float (&x)[32]
   tmem_st32(taddr + 32, lo);
 }
 
-// one layer: D (fresh) = A_hi*W_hi + A_lo*W_hi + A_hi*W_lo ; issued by one thread
-__device__ __forceinline__ void issue_layer(uint32_t d, uint32_t a_hi, uint32_t w_smem) {
-  const uint32_t a_lo = a_hi + 32;
-#pragma unroll
-  for (int kk = 0; kk < 4; ++kk) tc_mma_ts(d, a_lo + 8 * kk, make_bdesc(w_smem + kk * 1024), kk > 0);
-#pragma unroll
-  for (int kk = 0; kk < 4; ++kk) tc_mma_ts(d, a_hi + 8 * kk, make_bdesc(w_smem + 4096 + kk * 1024), 1);
-#pragma unroll
-  for (int kk = 0; kk < 4; ++kk) tc_mma_ts(d, a_hi + 8 * kk, make_bdesc(w_smem + kk * 1024), 1);
+// ---------------------------------------------------------------------------------------
+// Interpolation set-up computed ONCE per query by its owner thread and broadcast to the 8
+// lanes that fetch the taps (the SIMT kernel recomputes it in every lane).
+// ---------------------------------------------------------------------------------------
+struct TapInfo {
+  int base;       // index (in taps) of corner (x0,y0[,z0])
+  int step;       // bit0: x0+1 < R, bit1: y0+1 < R, bit2: z0+1 < R   (else the weight is 0 and the address is clamped)
+  float fx, fy, fz;
+};
+__device__ __forceinline__ TapInfo tap_volume(float ux, float uy, float uz, int R, bool nearest) {
+  const float tx = unnormalize(ux, R), ty = unnormalize(uy, R), tz = unnormalize(uz, R);
+  TapInfo t;
+  if (nearest) {
+    const int x = (int)nearbyintf(tx), y = (int)nearbyintf(ty), z = (int)nearbyintf(tz);
+    t.base = (z * R + y) * R + x; t.step = 0; t.fx = t.fy = t.fz = 0.f;
+    return t;
+  }
+  const float flx = floorf(tx), fly = floorf(ty), flz = floorf(tz);
+  const int x0 = (int)flx, y0 = (int)fly, z0 = (int)flz;
+  t.base = (z0 * R + y0) * R + x0;
+  t.step = (int)(x0 + 1 < R) | ((int)(y0 + 1 < R) << 1) | ((int)(z0 + 1 < R) << 2);
+  t.fx = tx - flx; t.fy = ty - fly; t.fz = tz - flz;
+  return t;
+}
+__device__ __forceinline__ TapInfo tap_plane(float ua, float ub, int R, bool nearest) {
+  const float tx = unnormalize(ua, R), ty = unnormalize(ub, R);
+  TapInfo t;
+  t.fz = 0.f;
+  if (nearest) {
+    const int x = (int)nearbyintf(tx), y = (int)nearbyintf(ty);
+    t.base = y * R + x; t.step = 0; t.fx = t.fy = 0.f;
+    return t;
+  }
+  const float flx = floorf(tx), fly = floorf(ty);
+  const int x0 = (int)flx, y0 = (int)fly;
+  t.base = y0 * R + x0;
+  t.step = (int)(x0 + 1 < R) | ((int)(y0 + 1 < R) << 1);
+  t.fx = tx - flx; t.fy = ty - fly;
+  return t;
+}
+__device__ __forceinline__ TapInfo tap_bcast(const TapInfo& t, int src) {
+  TapInfo r;
+  r.base = __shfl_sync(kFull, t.base, src);
+  r.step = __shfl_sync(kFull, t.step, src);
+  r.fx = __shfl_sync(kFull, t.fx, src);
+  r.fy = __shfl_sync(kFull, t.fy, src);
+  r.fz = __shfl_sync(kFull, t.fz, src);
+  return r;
+}
+// ATen corner order / weights (see sample_volume in decoder_common.cuh); the weight of a
+// clamped corner is exactly 0 because its fraction is 0.
+__device__ __forceinline__ float4 fetch_volume(const float4* __restrict__ vol, int R, const TapInfo& t, bool nearest) {
+  if (nearest) return __ldg(vol + (size_t)t.base * 8);
+  const int dx = (t.step & 1) ? 8 : 0, dy = (t.step & 2) ? R * 8 : 0, dz = (t.step & 4) ? R * R * 8 : 0;
+  const float4* p = vol + (size_t)t.base * 8;
+  const float4 v000 = __ldg(p), v001 = __ldg(p + dx), v010 = __ldg(p + dy), v011 = __ldg(p + dy + dx);
+  const float4 v100 = __ldg(p + dz), v101 = __ldg(p + dz + dx), v110 = __ldg(p + dz + dy), v111 = __ldg(p + dz + dy + dx);
+  const float fx1 = (t.step & 1) ? t.fx : 0.f, fy1 = (t.step & 2) ? t.fy : 0.f, fz1 = (t.step & 4) ? t.fz : 0.f;
+  const float fx0 = 1.0f - t.fx, fy0 = 1.0f - t.fy, fz0 = 1.0f - t.fz;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  a = f4_fma(fx0 * fy0 * fz0, v000, a);
+  a = f4_fma(fx1 * fy0 * fz0, v001, a);
+  a = f4_fma(fx0 * fy1 * fz0, v010, a);
+  a = f4_fma(fx1 * fy1 * fz0, v011, a);
+  a = f4_fma(fx0 * fy0 * fz1, v100, a);
+  a = f4_fma(fx1 * fy0 * fz1, v101, a);
+  a = f4_fma(fx0 * fy1 * fz1, v110, a);
+  a = f4_fma(fx1 * fy1 * fz1, v111, a);
+  return a;
+}
+__device__ __forceinline__ float4 fetch_plane(const float4* __restrict__ pl, int R, const TapInfo& t, bool nearest) {
+  if (nearest) return __ldg(pl + (size_t)t.base * 8);
+  const int dx = (t.step & 1) ? 8 : 0, dy = (t.step & 2) ? R * 8 : 0;
+  const float4* p = pl + (size_t)t.base * 8;
+  const float4 v00 = __ldg(p), v01 = __ldg(p + dx), v10 = __ldg(p + dy), v11 = __ldg(p + dy + dx);
+  const float fx1 = (t.step & 1) ? t.fx : 0.f, fy1 = (t.step & 2) ? t.fy : 0.f;
+  const float fx0 = 1.0f - t.fx, fy0 = 1.0f - t.fy;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  a = f4_fma(fx0 * fy0, v00, a);
+  a = f4_fma(fx1 * fy0, v01, a);
+  a = f4_fma(fx0 * fy1, v10, a);
+  a = f4_fma(fx1 * fy1, v11, a);
+  return a;
 }
 
 struct TcSmem {
@@ -139,16 +216,27 @@ struct TcSmem {
 };
 __host__ __device__ inline TcSmem tc_smem_layout(int n_blocks) {
   TcSmem s;
-  s.w = 0;
-  s.bias = s.w + 3 * n_blocks * 8192;
-  s.small = s.bias + 3 * n_blocks * 32 * 4;       // Wp[3][32], bp[32], Wout[64], bout[2]+pad
+  s.w = 0;                                          // 3*nb matrices x (hi 4 KB | lo 4 KB)
+  s.bias = s.w + 3 * n_blocks * 8192;               // (2*nb+1) bias K-blocks of 1 KB
+  s.small = s.bias + (2 * n_blocks + 1) * 1024;     // Wp[3][32], bp[32], Wout[64], bout[2]+pad
   s.tips = s.small + (128 + 68) * 4;
   s.stage = s.tips + VTACO_MAX_TIPS * 32 * 4;
   s.stage = (s.stage + 15) / 16 * 16;
-  s.bars = s.stage + 8 * 32 * kStageStride * 4;
+  s.bars = s.stage + (kTcThreads / 32) * 32 * kStageStride * 4;
   s.tmem_ptr = s.bars + 64;
   s.total = s.tmem_ptr + 16;
   return s;
+}
+
+// MMAs of one accumulation step, issued by one thread.  D = [A_x * W] + ones * Bias [+ C * Wc]
+__device__ __forceinline__ void issue_product(uint32_t d, uint32_t a_hi, uint32_t w_smem, uint32_t accumulate_first) {
+  const uint32_t a_lo = a_hi + 32;
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) tc_mma_ts(d, a_lo + 8 * kk, make_bdesc(w_smem + kk * 1024), kk > 0 ? 1u : accumulate_first);
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) tc_mma_ts(d, a_hi + 8 * kk, make_bdesc(w_smem + 4096 + kk * 1024), 1);
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) tc_mma_ts(d, a_hi + 8 * kk, make_bdesc(w_smem + kk * 1024), 1);
 }
 
 template <bool DENSE>
@@ -157,7 +245,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) decoder_tc_kernel(const __grid_
   extern __shared__ __align__(1024) unsigned char tsm[];
   const TcSmem L = tc_smem_layout(P.n_blocks);
   float* sWtc = reinterpret_cast<float*>(tsm + L.w);
-  float* sBias = reinterpret_cast<float*>(tsm + L.bias);
   float* sSmall = reinterpret_cast<float*>(tsm + L.small);
   float* sTip = reinterpret_cast<float*>(tsm + L.tips);
   float* sStage = reinterpret_cast<float*>(tsm + L.stage);
@@ -168,16 +255,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) decoder_tc_kernel(const __grid_
   const int g = warp >> 2, wg = warp & 3, tg = tid & 127;
   const int nb = P.n_blocks;
 
-  // ---- one-time setup: weights, biases, barriers, TMEM ----
-  for (int i = tid; i < 3 * nb * 2048 / 4; i += kTcThreads)
+  // ---- one-time setup: weights + bias blocks (contiguous in wtc), small vectors, barriers, TMEM ----
+  const int wtc_floats = 3 * nb * 2048 + (2 * nb + 1) * 256;
+  for (int i = tid; i < wtc_floats / 4; i += kTcThreads)
     reinterpret_cast<float4*>(sWtc)[i] = __ldg(reinterpret_cast<const float4*>(wtc) + i);
-  for (int i = tid; i < nb * 32; i += kTcThreads) {
-    const int b = i >> 5, j = i & 31;
-    const float* Wb = P.weights + VTACO_DEC_OFF_BLOCKS + b * VTACO_DEC_BLOCK_STRIDE;
-    sBias[(3 * b + 0) * 32 + j] = Wb[1024 + j];
-    sBias[(3 * b + 1) * 32 + j] = Wb[1056 + 1024 + j];
-    sBias[(3 * b + 2) * 32 + j] = Wb[2112 + 1024 + j];
-  }
   for (int i = tid; i < 128; i += kTcThreads) sSmall[i] = P.weights[(P.use_img ? VTACO_DEC_OFF_WPI : VTACO_DEC_OFF_WP) + i];
   for (int i = tid; i < 68; i += kTcThreads)
     sSmall[128 + i] = P.weights[VTACO_DEC_OFF_BLOCKS + nb * VTACO_DEC_BLOCK_STRIDE + i];
@@ -191,7 +272,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) decoder_tc_kernel(const __grid_
     }
   }
   if (tid == 0) {
-    for (int i = 0; i < 2 * kTcGroups; ++i) mbar_init(smem_u32(sBars + i), 1);
+    for (int i = 0; i < kTcGroups; ++i) mbar_init(smem_u32(sBars + i), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -203,19 +284,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) decoder_tc_kernel(const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *sTmem;
-  // this warp's TMEM window: lanes 32*wg.., columns of group g
+  // group columns: C_hi 0, C_lo 32, X_hi 64, X_lo 96, ones 128 (8), D 136 (32)
   const uint32_t tbase = tmem_base + ((uint32_t)(32 * wg) << 16) + (uint32_t)(g * kColsPerGroup);
-  const uint32_t tC = tbase, tX = tbase + 64, tD = tbase + 128, tDC = tbase + 160;
-  // accumulator / operand addresses as seen by the MMA (lane 0 of the CTA, group's columns)
+  const uint32_t tC = tbase, tX = tbase + 64, tOnes = tbase + 128, tD = tbase + 136;
   const uint32_t mbase = tmem_base + (uint32_t)(g * kColsPerGroup);
-  const uint32_t mC = mbase, mX = mbase + 64, mD = mbase + 128, mDC = mbase + 160;
-  const uint32_t barD = smem_u32(sBars + 2 * g), barDC = smem_u32(sBars + 2 * g + 1);
-  const uint32_t wsm = smem_u32(sWtc);
-  uint32_t phD = 0, phDC = 0;
+  const uint32_t mC = mbase, mX = mbase + 64, mOnes = mbase + 128, mD = mbase + 136;
+  const uint32_t bar = smem_u32(sBars + g);
+  const uint32_t wsm = smem_u32(sWtc), bsm = smem_u32(tsm + L.bias);
+  uint32_t ph = 0;
+  {  // the constant A block that multiplies the bias rows: columns (1, 1, 0, 0, 0, 0, 0, 0)
+    const uint32_t one = __float_as_uint(1.0f);
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(tOnes), "r"(one),
+                 "r"(one), "r"(0u), "r"(0u), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+                 : "memory");
+    tc_wait_st();
+  }
   float* stage = sStage + warp * 32 * kStageStride;
   const int grp = lane >> 3, sub = lane & 7;
   const int nx = P.nx;
   float vmin = CUDART_INF_F, vmax = -CUDART_INF_F;
+  int step = 0;  // accumulation steps issued so far by this group (rotates the issuing warp)
 
   for (long long tile = (long long)blockIdx.x * kTcGroups + g; tile < P.n_tiles;
        tile += (long long)gridDim.x * kTcGroups) {
@@ -249,28 +337,33 @@ __global__ void __launch_bounds__(kTcThreads, 1) decoder_tc_kernel(const __grid_
     }
     if (!valid) oidx = 0;
 
-    // ---------------- gather: 8 lanes per query -> staged rows ----------------
+    // ---------------- gather: owner computes the taps, 8 lanes fetch them ----------------
     if (P.has_c) {
+      TapInfo tv, tp0, tp1, tp2;
+      if (P.grid) tv = tap_volume(norm3d(px, P.nc), norm3d(py, P.nc), norm3d(pz, P.nc), P.Rg, P.nearest);
+      const bool planes = P.plane[0] || P.plane[1] || P.plane[2];
+      if (planes) {
+        const float ux = norm2d(px, P.nc), uy = norm2d(py, P.nc), uz = norm2d(pz, P.nc);
+        if (P.plane[0]) tp0 = tap_plane(ux, uz, P.Rp, P.nearest);
+        if (P.plane[1]) tp1 = tap_plane(ux, uy, P.Rp, P.nearest);
+        if (P.plane[2]) tp2 = tap_plane(uy, uz, P.Rp, P.nearest);
+      }
 #pragma unroll 2
       for (int it = 0; it < 8; ++it) {
         const int src = it * 4 + grp;
-        const float x = __shfl_sync(kFull, px, src);
-        const float y = __shfl_sync(kFull, py, src);
-        const float z = __shfl_sync(kFull, pz, src);
         const int b = __shfl_sync(kFull, qb, src);
         float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
         if (P.grid) {
           const int R = P.Rg;
           const float4* vol = reinterpret_cast<const float4*>(P.grid) + (size_t)b * R * R * R * 8 + sub;
-          c = sample_volume(vol, R, norm3d(x, P.nc), norm3d(y, P.nc), norm3d(z, P.nc), P.nearest);
+          c = fetch_volume(vol, R, tap_bcast(tv, src), P.nearest);
         }
-        if (P.plane[0] || P.plane[1] || P.plane[2]) {
+        if (planes) {
           const int R = P.Rp;
-          const float ux = norm2d(x, P.nc), uy = norm2d(y, P.nc), uz = norm2d(z, P.nc);
           const size_t boff = (size_t)b * R * R * 8 + sub;
-          if (P.plane[0]) c = f4_add(c, sample_plane(reinterpret_cast<const float4*>(P.plane[0]) + boff, R, ux, uz, P.nearest));
-          if (P.plane[1]) c = f4_add(c, sample_plane(reinterpret_cast<const float4*>(P.plane[1]) + boff, R, ux, uy, P.nearest));
-          if (P.plane[2]) c = f4_add(c, sample_plane(reinterpret_cast<const float4*>(P.plane[2]) + boff, R, uy, uz, P.nearest));
+          if (P.plane[0]) c = f4_add(c, fetch_plane(reinterpret_cast<const float4*>(P.plane[0]) + boff, R, tap_bcast(tp0, src), P.nearest));
+          if (P.plane[1]) c = f4_add(c, fetch_plane(reinterpret_cast<const float4*>(P.plane[1]) + boff, R, tap_bcast(tp1, src), P.nearest));
+          if (P.plane[2]) c = f4_add(c, fetch_plane(reinterpret_cast<const float4*>(P.plane[2]) + boff, R, tap_bcast(tp2, src), P.nearest));
         }
         *reinterpret_cast<float4*>(stage + src * kStageStride + 4 * sub) = c;
       }
@@ -286,11 +379,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) decoder_tc_kernel(const __grid_
       tc_wait_st();
       tc_fence_before();
       group_sync(g);
-      if (tg == 0) {
+      if (wg == (step & 3) && lane == 0) {       // step 0: D = C*Wc_0 + ones*bc_0
         tc_fence_after();
-        issue_layer(mDC, mC, wsm + 0 * 8192);
-        tc_commit(barDC);
+        issue_product(mD, mC, wsm, 0);
+        tc_mma_ts(mD, mOnes, make_bdesc(bsm), 1);
+        tc_commit(bar);
       }
+      ++step;
     }
 
     // ---------------- net = fc_p(p) | fc_p_img(p, tip feature) on the CUDA cores ----------------
@@ -316,55 +411,56 @@ __global__ void __launch_bounds__(kTcThreads, 1) decoder_tc_kernel(const __grid_
         for (int j = 0; j < 32; ++j) net[j] += sTip[f * 32 + j];
       }
     }
-
-    // ---------------- residual blocks ----------------
-    for (int i = 0; i < nb; ++i) {
-      uint32_t r[32];
-      float x[32];
-      if (P.has_c) {  // net = net + fc_c[i](c)
-        mbar_wait(barDC, phDC); phDC ^= 1;
-        tc_fence_after();
-        tmem_ld32(tDC, r);
-        tc_wait_ld();
+    uint32_t r[32];
+    float x[32];
+    if (P.has_c) {  // net += fc_c[0](c)
+      mbar_wait(bar, ph); ph ^= 1;
+      tc_fence_after();
+      tmem_ld32(tD, r);
+      tc_wait_ld();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) net[j] += __uint_as_float(r[j]) + sBias[(3 * i) * 32 + j];
-      }
+      for (int j = 0; j < 32; ++j) net[j] += __uint_as_float(r[j]);
+    }
+
+    // ---------------- residual blocks: 2 accumulation steps each ----------------
+    for (int i = 0; i < nb; ++i) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) x[j] = fmaxf(net[j], 0.f);
       split_store(tX, x);
       tc_wait_st();
       tc_fence_before();
       group_sync(g);
-      if (tg == 0) {
+      if (wg == (step & 3) && lane == 0) {       // D = relu(net)*W0_i + ones*b0_i
         tc_fence_after();
-        issue_layer(mD, mX, wsm + (3 * i + 1) * 8192);      // fc_0(relu(net))
-        tc_commit(barD);
-        if (P.has_c && i + 1 < nb) {                        // next block's fc_c(c): overlaps the ALU phases
-          issue_layer(mDC, mC, wsm + (3 * (i + 1)) * 8192);
-          tc_commit(barDC);
-        }
+        issue_product(mD, mX, wsm + (3 * i + 1) * 8192, 0);
+        tc_mma_ts(mD, mOnes, make_bdesc(bsm + (2 * i + 1) * 1024), 1);
+        tc_commit(bar);
       }
-      mbar_wait(barD, phD); phD ^= 1;
+      ++step;
+      mbar_wait(bar, ph); ph ^= 1;
       tc_fence_after();
       tmem_ld32(tD, r);
       tc_wait_ld();
 #pragma unroll
-      for (int j = 0; j < 32; ++j) x[j] = fmaxf(__uint_as_float(r[j]) + sBias[(3 * i + 1) * 32 + j], 0.f);
+      for (int j = 0; j < 32; ++j) x[j] = fmaxf(__uint_as_float(r[j]), 0.f);
       split_store(tX, x);
       tc_wait_st();
       tc_fence_before();
       group_sync(g);
-      if (tg == 0) {
+      if (wg == (step & 3) && lane == 0) {       // D = relu(h)*W1_i + ones*(b1_i + bc_{i+1}) [+ C*Wc_{i+1}]
         tc_fence_after();
-        issue_layer(mD, mX, wsm + (3 * i + 2) * 8192);      // fc_1(relu(h))
-        tc_commit(barD);
+        issue_product(mD, mX, wsm + (3 * i + 2) * 8192, 0);
+        tc_mma_ts(mD, mOnes, make_bdesc(bsm + (2 * i + 2) * 1024), 1);
+        if (P.has_c && i + 1 < nb) issue_product(mD, mC, wsm + (3 * (i + 1)) * 8192, 1);
+        tc_commit(bar);
       }
-      mbar_wait(barD, phD); phD ^= 1;
+      ++step;
+      mbar_wait(bar, ph); ph ^= 1;
       tc_fence_after();
       tmem_ld32(tD, r);
       tc_wait_ld();
 #pragma unroll
-      for (int j = 0; j < 32; ++j) net[j] += __uint_as_float(r[j]) + sBias[(3 * i + 2) * 32 + j];
+      for (int j = 0; j < 32; ++j) net[j] += __uint_as_float(r[j]);
     }
 
     // ---------------- heads ----------------
@@ -385,10 +481,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) decoder_tc_kernel(const __grid_
         vmax = fmaxf(vmax, o);
       }
     }
-    // all TMEM reads of this tile are complete (wait::ld) before the next tile's stores:
-    tc_fence_before();
-    group_sync(g);
-    tc_fence_after();
   }
 
   if (P.minmax_key) {
