@@ -342,33 +342,55 @@ def run_ours(args, rank, local_rank, world):
     if rank == 0:
         peaks_file = os.path.join(ROOT, 'MEASURED_PEAKS.json')
         measured = json.load(open(peaks_file)) if os.path.exists(peaks_file) else {}
+        bf16_peak = measured.get('bf16_tflops', 1590.0)        # burst figure: the kernel is timed alone
+        peak_tag = 'of measured' if 'bf16_tflops' in measured else 'of fallback'
         traffic = None
-        prof = os.path.join(ROOT, 'profiles', 'decoder_ncu_summary.json')
+        prof = os.path.join(ROOT, 'profiles', 'decoder_ncu_summary.json' if args.variant != 2
+                            else 'decoder_tc_ncu_summary.json')
         if os.path.exists(prof):
             try:
                 traffic = json.load(open(prof)).get('dram_bytes_per_launch')
             except Exception:
                 traffic = None
+        hbm_gbs = kq * 4 / (k_ms * 1e-3) / 1e9
+        common = {'flop_per_query_algorithmic': FLOP_PER_QUERY, 'queries_per_launch': kq, 'kernel_ms': k_ms,
+                  'fp32_equivalent_tflops': achieved / 1e12,
+                  'fp32_ffma_peak_self_measured_tflops': fp32_peak / 1e12,
+                  'frac_of_self_measured_ffma_peak': achieved / fp32_peak,
+                  'hbm_algorithmic_gbs': hbm_gbs,
+                  'hbm_frac_of_measured': hbm_gbs / measured['hbm_gbs'] if 'hbm_gbs' in measured else None,
+                  'traffic': traffic}
+        if args.variant == 2:
+            # executed tensor work: per 128-query tile (12 MMAs per 32x32 product, 3 products per block + 1,
+            # one bias MMA per step), each MMA = M128 x N32 x K8 x 2 FLOP
+            nb_ = 5
+            mmas = 12 * (3 * nb_) + (2 * nb_ + 1)
+            tensor_flop_per_query = mmas * 128 * 32 * 8 * 2 / 128.0
+            t_achieved = kq * tensor_flop_per_query / (k_ms * 1e-3) / 1e12
+            tf32_peak = bf16_peak / 2.0
+            roofline = dict(common, bound='tensor', kernel='decoder_tc_kernel<dense> (tcgen05 kind::tf32, 3xTF32)',
+                            achieved=t_achieved, peak=tf32_peak, unit='TFLOP/s', frac=t_achieved / tf32_peak,
+                            peak_source='TF32 dense = 1/2 of the %s bf16 cuBLAS burst peak (%.1f TFLOP/s, %s); '
+                                        'MEASURED_PEAKS.json has no TF32 figure' % ('measured' if 'bf16_tflops' in
+                                                                                   measured else 'fallback',
+                                                                                   bf16_peak, peak_tag),
+                            tensor_flop_per_query=tensor_flop_per_query,
+                            note='3xTF32 executes 3.36x the algorithmic FLOPs to keep fp32 accuracy; the kernel is '
+                                 'latency/issue-bound (tensor pipe ~26%% busy, issue slots ~43%%), see '
+                                 'profiles/decoder_tc_ncu_summary.json')
+        else:
+            roofline = dict(common, bound='fp32', kernel='decoder_kernel<dense> (SIMT)', achieved=achieved / 1e12,
+                            peak=fp32_peak / 1e12, unit='TFLOP/s', frac=achieved / fp32_peak,
+                            peak_source='self-measured register-resident FMA loop (vtaco_fp32_peak: scalar %.1f, '
+                                        'packed FFMA2 %.1f TFLOP/s); MEASURED_PEAKS.json has no FP32 figure'
+                                        % (peaks[0] / 1e12, peaks[1] / 1e12),
+                            frac_of_measured_bf16_tensor_peak=(achieved / 1e12) / bf16_peak)
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True,
             'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': workload_config(nx, args),
-            'roofline': {
-                'bound': 'fp32',  # FP32 FMA pipe: 30976 FLOP vs 4 B of HBM traffic per query
-                'kernel': 'decoder_kernel<dense>', 'achieved': achieved / 1e12, 'peak': fp32_peak / 1e12,
-                'unit': 'TFLOP/s', 'frac': achieved / fp32_peak,
-                'peak_source': 'self-measured register-resident FMA loop (vtaco_fp32_peak: scalar %.1f, packed '
-                               'FFMA2 %.1f TFLOP/s); MEASURED_PEAKS.json has no FP32 figure' %
-                               (peaks[0] / 1e12, peaks[1] / 1e12),
-                'flop_per_query': FLOP_PER_QUERY, 'queries_per_launch': kq, 'kernel_ms': k_ms,
-                'frac_of_measured_bf16_tensor_peak': (achieved / 1e12) / measured['bf16_tflops']
-                if 'bf16_tflops' in measured else None,
-                'hbm_algorithmic_gbs': kq * 4 / (k_ms * 1e-3) / 1e9,
-                'hbm_frac_of_measured': (kq * 4 / (k_ms * 1e-3) / 1e9) / measured['hbm_gbs']
-                if 'hbm_gbs' in measured else None,
-                'traffic': traffic,
-            },
+            'roofline': roofline,
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'ms_per_step': float(e2e_t.item()) / args.steps * 1e3,
                     'path': 'Generator3D.generate_mesh: pinned cloud -> H2D -> LocalPoolPointnet+UNet3D -> '
@@ -400,7 +422,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--nx', type=int, default=256)
-    ap.add_argument('--variant', type=int, default=1, help='decoder inner loop: 0 scalar FFMA, 1 packed FFMA2')
+    ap.add_argument('--variant', type=int, default=2,
+                    help='decoder kernel: 0 scalar-FFMA SIMT, 1 packed-FFMA2 SIMT, 2 tcgen05 3xTF32 (default)')
     ap.add_argument('--cpu-sample', type=int, default=4 * 256 * 256)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()

@@ -8,30 +8,36 @@
 // bit-exact on case indices / faces and to rounding on vertices).
 //
 // HBM-bound stream compaction in four launches:
-//   classify : 1 thread / lattice point — 8 corner loads (L1/L2 hits after the first),
-//              3-bit own-edge mask + triangle count -> 1 byte code, per-block totals
+//   classify : 1 thread / run of 8 consecutive z points — four rows of 9 samples as float4
+//              loads -> "above" bit rows -> per point 3-bit own-edge mask + triangle count
+//              (1 byte code, 8 B store per thread), per-block totals
 //   scan     : one block, exclusive scan of the per-block totals, grand totals
-//   vertices : intra-block scan -> vertex base id per point (4 B), vertices of the point's
-//              own cut edges (inverse-distance weighting in double, like Lewiner's code)
-//   faces    : intra-block scan -> triangle base per cell, vertex ids looked up from the
-//              owners' base ids; output order = lattice order, then table order.
-// Algorithmic bytes: 4*n (grid) + 12*V + 12*F; scratch traffic adds ~10 B / point.
+//   vertices : blocks without a cut edge exit at once; otherwise intra-block scan -> vertex
+//              base id per point, vertices of the point's own cut edges (inverse-distance
+//              weighting in double, like Lewiner's code)
+//   faces    : blocks without a triangle exit at once; otherwise intra-block scan -> triangle
+//              base per cell, vertex ids looked up from the owners' base ids;
+//              output order = lattice order, then table order.
+// Algorithmic bytes: 4*n (grid) + 12*V + 12*F; scratch traffic adds ~1 B / point + the
+// active blocks' base ids.
 #include "common.cuh"
 #include "mc_tables.h"
 #include <float.h>
 
 namespace vtaco {
 
-constexpr int kMcThreads = 512;
+constexpr int kMcThreads = 256;   // threads per block
+constexpr int kMcRun = 8;         // consecutive z points per thread
+constexpr int kMcBlockPts = kMcThreads * kMcRun;
 
 struct McParams {
   const float* grid;
-  int nx, ny, nz;
-  long long npts;
+  int nx, ny, nz, nzc;            // nzc = ceil(nz / kMcRun) runs per (x,y) row
+  long long npts, nruns;
   float level;
   const int32_t* level_keys;
-  uint8_t* code;
-  uint32_t* vbase;
+  uint8_t* code;                  // [nruns][8]: bits 0-2 own-edge mask (x,y,z), bits 3-5 triangle count
+  uint32_t* vbase;                // [nruns][8]: id of the first vertex owned by the point (active blocks only)
   uint2* block_sums;
   ulonglong2* block_offs;
   int nblocks;
@@ -79,41 +85,72 @@ __device__ __forceinline__ unsigned block_scan_excl(unsigned v, unsigned& total)
   return warp_excl[w] + inc - v;
 }
 
-__device__ __forceinline__ int mc_case(const McParams& P, long long p, int i, int j, int k, float level,
-                                       unsigned& flags) {
-  const long long sy = P.nz, sx = (long long)P.ny * P.nz;
-  const bool hx = i + 1 < P.nx, hy = j + 1 < P.ny, hz = k + 1 < P.nz;
-  const float v0 = P.grid[p];
-  const bool a0 = v0 > level;
-  bool a[8];
-  a[0] = a0;
-  a[1] = hx ? (P.grid[p + sx] > level) : a0;
-  a[2] = hy ? (P.grid[p + sy] > level) : a0;
-  a[4] = hz ? (P.grid[p + 1] > level) : a0;
-  flags = (unsigned)(hx && a[1] != a0) | ((unsigned)(hy && a[2] != a0) << 1) | ((unsigned)(hz && a[4] != a0) << 2);
-  if (!(hx && hy && hz)) return -1;
-  a[3] = P.grid[p + sx + sy] > level;
-  a[5] = P.grid[p + sx + 1] > level;
-  a[6] = P.grid[p + sy + 1] > level;
-  a[7] = P.grid[p + sx + sy + 1] > level;
-  int c = 0;
+// run -> lattice coordinates of its first point
+__device__ __forceinline__ void run_coords(const McParams& P, long long run, int& i, int& j, int& k0) {
+  const int kc = (int)(run % P.nzc);
+  const long long r = run / P.nzc;
+  j = (int)(r % P.ny);
+  i = (int)(r / P.ny);
+  k0 = kc * kMcRun;
+}
+
+// "above" bits of kMcRun+1 consecutive z samples of row (i,j), bit t <-> k0+t; rows or samples
+// outside the lattice replicate the last valid sample (their cells/edges are masked out later).
+__device__ __forceinline__ unsigned row_bits(const McParams& P, int i, int j, int k0, float level) {
+  i = min(i, P.nx - 1);
+  j = min(j, P.ny - 1);
+  const float* row = P.grid + ((long long)i * P.ny + j) * P.nz;
+  unsigned bits = 0;
+  if (k0 + kMcRun < P.nz && (P.nz & 3) == 0) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(row + k0));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(row + k0 + 4));
+    const float c = __ldg(row + k0 + 8);
+    bits = (unsigned)(a.x > level) | ((unsigned)(a.y > level) << 1) | ((unsigned)(a.z > level) << 2) |
+           ((unsigned)(a.w > level) << 3) | ((unsigned)(b.x > level) << 4) | ((unsigned)(b.y > level) << 5) |
+           ((unsigned)(b.z > level) << 6) | ((unsigned)(b.w > level) << 7) | ((unsigned)(c > level) << 8);
+  } else {
 #pragma unroll
-  for (int b = 0; b < 8; ++b) c |= (int)a[b] << b;
-  return c;
+    for (int t = 0; t <= kMcRun; ++t) bits |= (unsigned)(__ldg(row + min(k0 + t, P.nz - 1)) > level) << t;
+  }
+  return bits;
+}
+
+// codes of the 8 points of a run (see McParams::code); returns packed (ntris << 16 | nverts)
+__device__ __forceinline__ unsigned run_codes(const McParams& P, int i, int j, int k0, float level,
+                                               unsigned long long& codes) {
+  const unsigned r00 = row_bits(P, i, j, k0, level), r01 = row_bits(P, i, j + 1, k0, level);
+  const unsigned r10 = row_bits(P, i + 1, j, k0, level), r11 = row_bits(P, i + 1, j + 1, k0, level);
+  const bool hx = i + 1 < P.nx, hy = j + 1 < P.ny;
+  unsigned packed = 0;
+  codes = 0;
+#pragma unroll
+  for (int t = 0; t < kMcRun; ++t) {
+    const int k = k0 + t;
+    if (k >= P.nz) break;
+    const bool hz = k + 1 < P.nz;
+    const unsigned a0 = (r00 >> t) & 1u;
+    // corner c = x | y<<1 | z<<2
+    const unsigned cs = a0 | (((r10 >> t) & 1u) << 1) | (((r01 >> t) & 1u) << 2) | (((r11 >> t) & 1u) << 3) |
+                        (((r00 >> (t + 1)) & 1u) << 4) | (((r10 >> (t + 1)) & 1u) << 5) |
+                        (((r01 >> (t + 1)) & 1u) << 6) | (((r11 >> (t + 1)) & 1u) << 7);
+    const unsigned flags = (unsigned)(hx && (((cs >> 1) & 1u) != a0)) | ((unsigned)(hy && (((cs >> 2) & 1u) != a0)) << 1) |
+                           ((unsigned)(hz && (((cs >> 4) & 1u) != a0)) << 2);
+    const unsigned nt = (hx && hy && hz) ? (unsigned)kMcTriCount[cs] : 0u;
+    codes |= (unsigned long long)(flags | (nt << 3)) << (8 * t);
+    packed += (nt << 16) | __popc(flags);
+  }
+  return packed;
 }
 
 __global__ void __launch_bounds__(kMcThreads) mc_classify_kernel(const __grid_constant__ McParams P) {
-  const long long p = (long long)blockIdx.x * kMcThreads + threadIdx.x;
+  const long long run = (long long)blockIdx.x * kMcThreads + threadIdx.x;
   unsigned packed = 0;
-  if (p < P.npts) {
-    const int k = (int)(p % P.nz);
-    const long long r = p / P.nz;
-    const int j = (int)(r % P.ny), i = (int)(r / P.ny);
-    unsigned flags;
-    const int c = mc_case(P, p, i, j, k, mc_level(P), flags);
-    const unsigned nt = c >= 0 ? (unsigned)kMcTriCount[c] : 0u;
-    P.code[p] = (uint8_t)(flags | (nt << 3));
-    packed = (nt << 16) | __popc(flags);
+  if (run < P.nruns) {
+    int i, j, k0;
+    run_coords(P, run, i, j, k0);
+    unsigned long long codes;
+    packed = run_codes(P, i, j, k0, mc_level(P), codes);
+    reinterpret_cast<unsigned long long*>(P.code)[run] = codes;
   }
   unsigned total;
   block_scan_excl(packed, total);
@@ -145,66 +182,99 @@ __global__ void __launch_bounds__(1024) mc_scan_blocks_kernel(const __grid_const
   if (t == 1023) { P.counts[0] = (long long)sv[1023]; P.counts[1] = (long long)sf[1023]; }
 }
 
+// vertex base ids + vertices; blocks without any cut edge return at once.
 __global__ void __launch_bounds__(kMcThreads) mc_vertices_kernel(const __grid_constant__ McParams P) {
-  const long long p = (long long)blockIdx.x * kMcThreads + threadIdx.x;
+  if (P.block_sums[blockIdx.x].x == 0) return;
+  const long long run = (long long)blockIdx.x * kMcThreads + threadIdx.x;
   const bool fits = P.counts[0] <= P.vcap && P.counts[1] <= P.fcap && P.counts[0] < 0x7fffffffll;
-  unsigned flags = 0;
-  if (p < P.npts) flags = P.code[p] & 7u;
-  unsigned total;
-  const unsigned excl = block_scan_excl(__popc(flags), total);
-  if (p >= P.npts) return;
-  const unsigned long long vb = P.block_offs[blockIdx.x].x + excl;
-  P.vbase[p] = (uint32_t)vb;
-  if (!flags || !fits) return;
-  const int k = (int)(p % P.nz);
-  const long long r = p / P.nz;
-  const int j = (int)(r % P.ny), i = (int)(r / P.ny);
-  const double level = (double)mc_level(P);
-  const double d0 = fabs((double)P.grid[p] - level);
-  const float base[3] = {(float)i, (float)j, (float)k};
-  const long long stride[3] = {(long long)P.ny * P.nz, (long long)P.nz, 1};
-  unsigned rank = 0;
+  unsigned long long codes = 0;
+  if (run < P.nruns) codes = reinterpret_cast<const unsigned long long*>(P.code)[run];
+  unsigned nv = 0;
 #pragma unroll
-  for (int a = 0; a < 3; ++a) {
-    if (flags & (1u << a)) {
-      const double d1 = fabs((double)P.grid[p + stride[a]] - level);
-      const double w0 = 1.0 / ((double)FLT_EPSILON + d0), w1 = 1.0 / ((double)FLT_EPSILON + d1);
-      const double t = w1 / (w0 + w1);
-      float pos[3] = {base[0], base[1], base[2]};
-      pos[a] = (float)((double)base[a] + t);
-      float* o = P.verts + (vb + rank) * 3;
-      o[0] = (pos[0] - P.voffset) * P.vscale;
-      o[1] = (pos[1] - P.voffset) * P.vscale;
-      o[2] = (pos[2] - P.voffset) * P.vscale;
-      ++rank;
+  for (int t = 0; t < kMcRun; ++t) nv += __popc((unsigned)(codes >> (8 * t)) & 7u);
+  unsigned total;
+  const unsigned excl = block_scan_excl(nv, total);
+  if (run >= P.nruns) return;
+  unsigned long long vb = P.block_offs[blockIdx.x].x + excl;
+  int i, j, k0;
+  run_coords(P, run, i, j, k0);
+  const double level = (double)mc_level(P);
+  const long long stride[3] = {(long long)P.ny * P.nz, (long long)P.nz, 1};
+  uint32_t vb_out[kMcRun];
+#pragma unroll
+  for (int t = 0; t < kMcRun; ++t) {
+    vb_out[t] = (uint32_t)vb;
+    const unsigned flags = (unsigned)(codes >> (8 * t)) & 7u;
+    if (flags && fits) {
+      const int k = k0 + t;
+      const long long p = ((long long)i * P.ny + j) * P.nz + k;
+      const double d0 = fabs((double)P.grid[p] - level);
+      const float base[3] = {(float)i, (float)j, (float)k};
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        if (flags & (1u << a)) {
+          const double d1 = fabs((double)P.grid[p + stride[a]] - level);
+          const double w0 = 1.0 / ((double)FLT_EPSILON + d0), w1 = 1.0 / ((double)FLT_EPSILON + d1);
+          const double tt = w1 / (w0 + w1);
+          float pos[3] = {base[0], base[1], base[2]};
+          pos[a] = (float)((double)base[a] + tt);
+          float* o = P.verts + vb * 3;
+          o[0] = (pos[0] - P.voffset) * P.vscale;
+          o[1] = (pos[1] - P.voffset) * P.vscale;
+          o[2] = (pos[2] - P.voffset) * P.vscale;
+          ++vb;
+        }
+      }
+    } else {
+      vb += __popc(flags);
     }
   }
+  uint4* dst = reinterpret_cast<uint4*>(P.vbase + run * kMcRun);
+  dst[0] = make_uint4(vb_out[0], vb_out[1], vb_out[2], vb_out[3]);
+  dst[1] = make_uint4(vb_out[4], vb_out[5], vb_out[6], vb_out[7]);
+}
+
+// point (i,j,k) -> index into the run-major code / vbase arrays
+__device__ __forceinline__ long long run_slot(const McParams& P, int i, int j, int k) {
+  return (((long long)i * P.ny + j) * P.nzc + (k >> 3)) * kMcRun + (k & 7);
 }
 
 __global__ void __launch_bounds__(kMcThreads) mc_faces_kernel(const __grid_constant__ McParams P) {
-  const long long p = (long long)blockIdx.x * kMcThreads + threadIdx.x;
+  if (P.block_sums[blockIdx.x].y == 0) return;
+  const long long run = (long long)blockIdx.x * kMcThreads + threadIdx.x;
   const bool fits = P.counts[0] <= P.vcap && P.counts[1] <= P.fcap && P.counts[0] < 0x7fffffffll;
-  unsigned nt = 0;
-  if (p < P.npts) nt = P.code[p] >> 3;
-  unsigned total;
-  const unsigned excl = block_scan_excl(nt, total);
-  if (p >= P.npts || !nt || !fits) return;
-  const unsigned long long tb = P.block_offs[blockIdx.x].y + excl;
-  const int k = (int)(p % P.nz);
-  const long long r = p / P.nz;
-  const int j = (int)(r % P.ny), i = (int)(r / P.ny);
-  unsigned flags;
-  const int c = mc_case(P, p, i, j, k, mc_level(P), flags);
-  const long long sy = P.nz, sx = (long long)P.ny * P.nz;
-  for (unsigned t = 0; t < nt; ++t) {
-    int32_t* o = P.faces + (tb + t) * 3;
+  unsigned long long codes = 0;
+  if (run < P.nruns) codes = reinterpret_cast<const unsigned long long*>(P.code)[run];
+  unsigned nt_run = 0;
 #pragma unroll
-    for (int corner = 0; corner < 3; ++corner) {
-      const int e = kMcTriTable[c][3 * t + corner];
-      const int a = kMcEdge[e][0];
-      const long long q = p + kMcEdge[e][1] * sx + kMcEdge[e][2] * sy + kMcEdge[e][3];
-      o[corner] = (int32_t)(P.vbase[q] + __popc((P.code[q] & 7u) & ((1u << a) - 1u)));
+  for (int t = 0; t < kMcRun; ++t) nt_run += ((unsigned)(codes >> (8 * t)) & 0xffu) >> 3;
+  unsigned total;
+  const unsigned excl = block_scan_excl(nt_run, total);
+  if (run >= P.nruns || !nt_run || !fits) return;
+  unsigned long long tb = P.block_offs[blockIdx.x].y + excl;
+  int i, j, k0;
+  run_coords(P, run, i, j, k0);
+  const float level = mc_level(P);
+  const unsigned r00 = row_bits(P, i, j, k0, level), r01 = row_bits(P, i, j + 1, k0, level);
+  const unsigned r10 = row_bits(P, i + 1, j, k0, level), r11 = row_bits(P, i + 1, j + 1, k0, level);
+  for (int t = 0; t < kMcRun; ++t) {
+    const unsigned nt = ((unsigned)(codes >> (8 * t)) & 0xffu) >> 3;
+    if (!nt) continue;
+    const unsigned cs = ((r00 >> t) & 1u) | (((r10 >> t) & 1u) << 1) | (((r01 >> t) & 1u) << 2) |
+                        (((r11 >> t) & 1u) << 3) | (((r00 >> (t + 1)) & 1u) << 4) | (((r10 >> (t + 1)) & 1u) << 5) |
+                        (((r01 >> (t + 1)) & 1u) << 6) | (((r11 >> (t + 1)) & 1u) << 7);
+    const int k = k0 + t;
+    for (unsigned tr = 0; tr < nt; ++tr) {
+      int32_t* o = P.faces + (tb + tr) * 3;
+#pragma unroll
+      for (int corner = 0; corner < 3; ++corner) {
+        const int e = kMcTriTable[cs][3 * tr + corner];
+        const int a = kMcEdge[e][0];
+        const long long q = run_slot(P, i + kMcEdge[e][1], j + kMcEdge[e][2], k + kMcEdge[e][3]);
+        o[corner] = (int32_t)(P.vbase[q] + __popc((P.code[q] & 7u) & ((1u << a) - 1u)));
+      }
     }
+    tb += nt;
   }
 }
 
@@ -242,9 +312,9 @@ using namespace vtaco;
 
 extern "C" int64_t vtaco_mc_scratch_bytes(int32_t nx, int32_t ny, int32_t nz) {
   if (nx < 1 || ny < 1 || nz < 1) return VTACO_ERR_INVALID_ARG;
-  const long long n = (long long)nx * ny * nz;
-  const long long nb = (n + kMcThreads - 1) / kMcThreads;
-  return mc_align(n) + mc_align(4 * n) + mc_align(8 * nb) + mc_align(16 * nb);
+  const long long nruns = (long long)nx * ny * ((nz + kMcRun - 1) / kMcRun);
+  const long long nb = (nruns + kMcThreads - 1) / kMcThreads;
+  return mc_align(nruns * kMcRun) + mc_align(4 * nruns * kMcRun) + mc_align(8 * nb) + mc_align(16 * nb);
 }
 
 extern "C" int vtaco_grid_minmax(const float* grid, int64_t n, int32_t* keys, void* stream) {
@@ -272,10 +342,12 @@ extern "C" int vtaco_marching_cubes(const vtaco_mc_args* a, void* stream) {
   McParams P = {};
   P.grid = a->grid; P.nx = a->nx; P.ny = a->ny; P.nz = a->nz; P.npts = n;
   P.level = a->level; P.level_keys = a->level_keys;
-  P.nblocks = (int)((n + kMcThreads - 1) / kMcThreads);
+  P.nzc = (a->nz + kMcRun - 1) / kMcRun;
+  P.nruns = (long long)a->nx * a->ny * P.nzc;
+  P.nblocks = (int)((P.nruns + kMcThreads - 1) / kMcThreads);
   char* s = reinterpret_cast<char*>(a->scratch);
-  P.code = reinterpret_cast<uint8_t*>(s); s += mc_align(n);
-  P.vbase = reinterpret_cast<uint32_t*>(s); s += mc_align(4 * n);
+  P.code = reinterpret_cast<uint8_t*>(s); s += mc_align(P.nruns * kMcRun);
+  P.vbase = reinterpret_cast<uint32_t*>(s); s += mc_align(4 * P.nruns * kMcRun);
   P.block_sums = reinterpret_cast<uint2*>(s); s += mc_align(8ll * P.nblocks);
   P.block_offs = reinterpret_cast<ulonglong2*>(s);
   P.counts = reinterpret_cast<long long*>(a->counts);
