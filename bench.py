@@ -327,13 +327,13 @@ def run_ours(args, rank, local_rank, world):
             grid, keys = gen.eval_lattice(cc, tips=(tips, tf, touch, 0.05), group=group)
             vv, ff = gen.extract_mesh(grid, keys)                # reads the two counters (D2H)
             if rank == 0:
-                vh, fh = vv.cpu(), ff.cpu()                      # mesh D2H
+                vh, fh = gen._to_host(vv, ff)                    # mesh D2H into pinned buffers
         barrier()
         if s >= max(args.warmup, 1):
             e2e_times.append(time.perf_counter() - t0)
             if rank == 0:
                 h2d = cloud_host.numel() * 4 + tip_feat_host.numel() * 4
-                d2h = vh.numel() * 4 + fh.numel() * 4 + 16
+                d2h = vh.size * 4 + fh.size * 4 + 16
     e2e_t = torch.tensor([sum(e2e_times)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX, group=group)

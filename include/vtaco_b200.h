@@ -254,6 +254,16 @@ int vtaco_marching_cubes(const vtaco_mc_args* args, void* stream);
 int vtaco_grid_minmax(const float* grid, int64_t n, int32_t* keys, void* stream);
 
 /* ------------------------------------------------------------------------- *
+ * (7) GroupNorm of the UNet3D that post-processes the feature grid
+ * (reference src/encoder/unet3d.py, layer order 'gcr': nn.GroupNorm before every Conv3d).
+ * x, y: contiguous [N][C][S] fp32 (y may alias x); gamma/beta [C] or NULL;
+ * stats_ws: device double[2*N*G] scratch.  Same result as torch.nn.functional.group_norm
+ * to fp32 rounding (biased variance, eps inside the sqrt).
+ * ------------------------------------------------------------------------- */
+int vtaco_group_norm(const float* x, float* y, const float* gamma, const float* beta, int32_t N, int32_t C,
+                     int32_t G, int64_t S, double eps, double* stats_ws, void* stream);
+
+/* ------------------------------------------------------------------------- *
  * (4) self-measured FP32 FMA peak (roofline denominator of the decoder).
  * Runs a register-resident FMA loop on every SM and returns achieved FLOP/s in
  * *flops_per_s_host.  variant 0: scalar FFMA, 1: packed FFMA2 (fma.rn.f32x2).

@@ -162,3 +162,19 @@ def test_encoder_decoder_end_to_end_with_unet3d():
     finally:
         torch.backends.cudnn.allow_tf32 = prev
     assert close(logits.cpu().numpy(), ref_logits.numpy()) < TOL
+
+
+@pytest.mark.parametrize('shape,groups', [((1, 32, 64, 64, 64), 8), ((2, 64, 16, 16, 16), 8), ((3, 8, 5, 7, 3), 1),
+                                          ((1, 256, 8, 8, 8), 8)])
+def test_group_norm_kernel(shape, groups):
+    """vtaco_group_norm == torch.nn.functional.group_norm (UNet3D 'g' layers)."""
+    from vtaco_b200.encoder.unet3d import GroupNorm
+    torch.manual_seed(0)
+    gn = GroupNorm(groups, shape[1]).cuda()
+    with torch.no_grad():
+        gn.weight.normal_()
+        gn.bias.normal_()
+        x = torch.randn(*shape, device='cuda') * 3 + 1.5
+        ref = torch.nn.functional.group_norm(x, groups, gn.weight, gn.bias, gn.eps)
+        got = gn(x)
+    assert close(got.cpu().numpy(), ref.cpu().numpy()) < 1e-5

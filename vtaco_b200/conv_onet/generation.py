@@ -59,6 +59,7 @@ class Generator3D(object):
         self._grid = None
         self._keys = None
         self._keys_init = None
+        self._pin = None
 
     @property
     def mc(self):
@@ -137,5 +138,16 @@ class Generator3D(object):
             grid, keys = self.eval_lattice(c, tips=tips, c_img_all=c_img_all, group=group)
             v, f = self.extract_mesh(grid, keys)
         if to_host:
-            return v.cpu().numpy(), f.cpu().numpy()
+            return self._to_host(v, f)
         return v, f
+
+    def _to_host(self, v, f):
+        """mesh D2H through cached pinned staging buffers (one synchronisation)."""
+        if self._pin is None or self._pin[0].shape[0] < v.shape[0] or self._pin[1].shape[0] < f.shape[0]:
+            self._pin = (torch.empty((int(v.shape[0] * 1.25) + 16, 3), dtype=torch.float32, pin_memory=True),
+                         torch.empty((int(f.shape[0] * 1.25) + 16, 3), dtype=torch.int32, pin_memory=True))
+        hv, hf = self._pin[0][:v.shape[0]], self._pin[1][:f.shape[0]]
+        hv.copy_(v, non_blocking=True)
+        hf.copy_(f, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return hv.numpy(), hf.numpy()

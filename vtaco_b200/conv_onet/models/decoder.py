@@ -73,7 +73,9 @@ class LocalDecoder(nn.Module):
         self.padding = padding
         # how `tensor / python_scalar` of normalize_* is evaluated ('cuda' | 'true'), SURVEY §7.2-1
         self.division = 'cuda'
-        self.kernel_variant = 0
+        # 0 scalar-FFMA SIMT, 1 packed-FFMA2 SIMT, 2 tcgen05 3xTF32 (fp32-accurate, fastest; calls with a
+        # per-query c_img tensor are routed to variant 1)
+        self.kernel_variant = 2
         self._pack_cache = None
         self._pack_tc_cache = None
         self._cl_cache = {}

@@ -8,6 +8,29 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 
+class GroupNorm(nn.GroupNorm):
+    """nn.GroupNorm with the same parameters / state_dict; on CUDA fp32 inference it runs
+    vtaco_group_norm (chip-wide reduction) instead of ATen's one-block-per-group kernel."""
+
+    def forward(self, x):
+        if (x.is_cuda and x.dtype == torch.float32 and x.dim() >= 3
+                and not (torch.is_grad_enabled() and (x.requires_grad or self.weight.requires_grad))):
+            from .. import _abi
+            import ctypes as C
+            xc = x.contiguous()
+            y = torch.empty_like(xc)
+            N, Cc = xc.shape[0], xc.shape[1]
+            S = xc[0, 0].numel()
+            ws = torch.empty(2 * N * self.num_groups, dtype=torch.float64, device=x.device)
+            with torch.cuda.device(x.device):
+                st = _abi.lib().vtaco_group_norm(_abi.ptr(xc), _abi.ptr(y), _abi.ptr(self.weight), _abi.ptr(self.bias),
+                                                 N, Cc, self.num_groups, S, float(self.eps), _abi.ptr(ws),
+                                                 _abi.stream_ptr(x.device))
+            _abi.check(st, 'group_norm')
+            return y
+        return super().forward(x)
+
+
 def _single_conv(cin, cout, order, num_groups, kernel_size=3, padding=1):
     assert 'c' in order, 'Conv layer MUST be present'
     assert order[0] not in 'rle', 'Non-linearity cannot be the first operation in the layer'
@@ -25,7 +48,7 @@ def _single_conv(cin, cout, order, num_groups, kernel_size=3, padding=1):
             nch = cin if i < order.index('c') else cout
             groups = 1 if nch < num_groups else num_groups
             assert nch % groups == 0
-            mods['groupnorm'] = nn.GroupNorm(num_groups=groups, num_channels=nch)
+            mods['groupnorm'] = GroupNorm(num_groups=groups, num_channels=nch)
         elif ch == 'b':
             mods['batchnorm'] = nn.BatchNorm3d(cin if i < order.index('c') else cout)
         else:
