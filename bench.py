@@ -202,7 +202,9 @@ def workload_config(nx, args):
                         'features, fingertip conditioning) + marching cubes' % nx,
             'nx': nx, 'queries_per_step': nx ** 3, 'encoder': 'LocalPoolPointnet grid64 hidden32 + UNet3D(4 levels)',
             'decoder': 'LocalDecoder simple_local hidden32 c_dim32 n_blocks5 bilinear', 'input_points': 3640,
-            'parallelism': 'x-slabs of the lattice over %d GPU(s), features replicated, logits all-gathered' % args.gpus,
+            'parallelism': 'x-slabs of the lattice over %d GPU(s), features replicated, logit slabs %s' % (
+                args.gpus, 'stored into every rank over NVLink peer memory by the decoder kernel (fused all-gather)'
+                if getattr(args, 'exchange', 'fused') == 'fused' else 'all-gathered with NCCL'),
             'l2': 'flushed between timed steps (256 MiB write outside the step events)',
             'kernel_variant': args.variant}
 
@@ -251,7 +253,7 @@ def run_ours(args, rank, local_rank, world):
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
 
     def device_step():
-        grid, keys = gen.eval_lattice(c, tips=tips_arg, group=group)
+        grid, keys = gen.eval_lattice(c, tips=tips_arg, group=group, exchange=args.exchange)
         return gen.mc(grid, level_keys=keys, voffset=np.float32(nx / 2), vscale=np.float32(1.1 / nx), sync=False)
 
     def barrier():
@@ -287,7 +289,7 @@ def run_ours(args, rank, local_rank, world):
             flush.fill_(float(s))
             e0, e_dec, e1 = ev[s]
             e0.record()
-            grid, keys = gen.eval_lattice(c, tips=tips_arg, group=None if world == 1 else group)
+            grid, keys = gen.eval_lattice(c, tips=tips_arg, group=None if world == 1 else group, exchange=args.exchange)
             e_dec.record()
             gen.mc(grid, level_keys=keys, voffset=np.float32(nx / 2), vscale=np.float32(1.1 / nx), sync=False)
             e1.record()
@@ -324,7 +326,7 @@ def run_ours(args, rank, local_rank, world):
         with torch.no_grad():
             cc = encode_features()                               # H2D of the pinned cloud + encoder (+ broadcast)
             tf = tip_feat_host.to(dev, non_blocking=True)        # H2D of the fingertip features
-            grid, keys = gen.eval_lattice(cc, tips=(tips, tf, touch, 0.05), group=group)
+            grid, keys = gen.eval_lattice(cc, tips=(tips, tf, touch, 0.05), group=group, exchange=args.exchange)
             vv, ff = gen.extract_mesh(grid, keys)                # reads the two counters (D2H)
             if rank == 0:
                 vh, fh = gen._to_host(vv, ff)                    # mesh D2H into pinned buffers
@@ -426,6 +428,8 @@ def main():
                     help='decoder kernel: 0 scalar-FFMA SIMT, 1 packed-FFMA2 SIMT, 2 tcgen05 3xTF32 (default)')
     ap.add_argument('--cpu-sample', type=int, default=4 * 256 * 256)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--exchange', default='fused', choices=['fused', 'nccl'],
+                    help='N>1: fused = decoder stores slabs into peer grids over NVLink; nccl = all-gather')
     args = ap.parse_args()
     rank, local_rank, world = env_int('RANK', 0), env_int('LOCAL_RANK', 0), env_int('WORLD_SIZE', 1)
     os.environ.setdefault('MASTER_ADDR', '127.0.0.1')

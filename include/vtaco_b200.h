@@ -148,6 +148,12 @@ typedef struct vtaco_decoder_args {
    * followed by 2*n_blocks+1 bias K-blocks of 256 floats in the same layout with k in [0,8): row k=0
    * = bias hi, k=1 = bias lo, for the steps bc_0 | b0_i, b1_i + bc_{i+1} (i = 0..n_blocks-1). */
   const float* weights_tc;
+  /* dense mode, multi-GPU: when n_peers > 0 every logit of the slab is stored to
+   * logits_peers[0..n_peers) instead of `logits` — the (nx,nx,nx) grids of all ranks (own one
+   * included), peer-mapped over NVLink (torch symmetric memory / CUDA IPC).  This fuses the
+   * all-gather of the logit slabs into the decoder epilogue: no separate collective. */
+  float* logits_peers[8];
+  int32_t n_peers;
 } vtaco_decoder_args;
 
 int vtaco_decoder_forward(const vtaco_decoder_args* args, void* stream);
@@ -236,7 +242,8 @@ typedef struct vtaco_mc_args {
   const float* grid;
   int32_t nx, ny, nz;
   float level;
-  const int32_t* level_keys;   /* optional device int32[2] */
+  const int32_t* level_keys;   /* optional device int32[2 * n_level_keys]: (min,max) key pairs, reduced over the pairs */
+  int32_t n_level_keys;        /* number of pairs (0 or 1 = one pair); >1: one pair per rank (fused exchange) */
   void* scratch;               /* >= vtaco_mc_scratch_bytes(nx,ny,nz) */
   int64_t scratch_bytes;
   float* vertices;             /* [vertex_capacity][3] */
@@ -252,6 +259,10 @@ int64_t vtaco_mc_scratch_bytes(int32_t nx, int32_t ny, int32_t nz);
 int vtaco_marching_cubes(const vtaco_mc_args* args, void* stream);
 /* keys[0..1] <- ordered-int keys of min / max of grid[0..n) (initialised by the call) */
 int vtaco_grid_minmax(const float* grid, int64_t n, int32_t* keys, void* stream);
+/* multi-GPU iso-level exchange without a collective: copy this rank's (min,max) key pair into
+ * slot `rank` of every peer's int32[n_peers][2] table (peer-mapped pointers), then reset `keys`
+ * to (INT32_MAX, INT32_MIN) for the next step. */
+int vtaco_publish_keys(int32_t* keys, int32_t* const* tables_host_array, int32_t n_peers, int32_t rank, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * (7) GroupNorm of the UNet3D that post-processes the feature grid

@@ -34,7 +34,7 @@ def _build(dev, nx):
     return gen, c
 
 
-def _worker(rank, world, port, nx, q):
+def _worker(rank, world, port, nx, q, exchange='nccl'):
     import sys
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     os.environ['MASTER_ADDR'] = '127.0.0.1'
@@ -44,12 +44,15 @@ def _worker(rank, world, port, nx, q):
     dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
     try:
         gen, c = _build(dev, nx)
-        grid, keys = gen.eval_lattice(c, group=dist.group.WORLD)
+        grid, keys = gen.eval_lattice(c, group=dist.group.WORLD, exchange=exchange)
         v, f = gen.extract_mesh(grid, keys)
+        v, f = v.clone(), f.clone()
         single, skeys = gen.eval_lattice(c, group=False)   # this rank alone, whole lattice
         single = single.clone()
-        grid2, _ = gen.eval_lattice(c, group=dist.group.WORLD)
-        ok = torch.equal(grid2, single) and torch.equal(keys, skeys)
+        from vtaco_b200.mcubes import keys_to_level
+        lvl = keys_to_level(keys)
+        grid2, _ = gen.eval_lattice(c, group=dist.group.WORLD, exchange=exchange)
+        ok = torch.equal(grid2, single) and lvl == keys_to_level(skeys)
         v1, f1 = gen.extract_mesh(single, skeys)
         ok_mesh = torch.equal(v, v1) and torch.equal(f, f1)
         q.put((rank, bool(ok), bool(ok_mesh), int(f.shape[0])))
@@ -57,15 +60,16 @@ def _worker(rank, world, port, nx, q):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize('exchange', ['fused', 'nccl'])
 @pytest.mark.parametrize('nx', [64, 40])
-def test_sharded_extraction_matches_single_gpu(nx):
+def test_sharded_extraction_matches_single_gpu(nx, exchange):
     world = min(torch.cuda.device_count(), 4)
     if world < 2:
         pytest.skip('needs >= 2 GPUs')
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, nx, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, nx, q, exchange)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=300) for _ in range(world)]

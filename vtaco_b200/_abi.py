@@ -39,13 +39,14 @@ class DecoderArgs(C.Structure):
         ('tip_radius', C.c_double), ('tip_feat', C.c_void_p),
         ('logits', C.c_void_p), ('contact', C.c_void_p), ('minmax_key', C.c_void_p),
         ('variant', C.c_int32), ('weights_tc', C.c_void_p),
+        ('logits_peers', C.c_void_p * 8), ('n_peers', C.c_int32),
     ]
 
 
 class McArgs(C.Structure):
     _fields_ = [
         ('grid', C.c_void_p), ('nx', C.c_int32), ('ny', C.c_int32), ('nz', C.c_int32),
-        ('level', C.c_float), ('level_keys', C.c_void_p),
+        ('level', C.c_float), ('level_keys', C.c_void_p), ('n_level_keys', C.c_int32),
         ('scratch', C.c_void_p), ('scratch_bytes', C.c_int64),
         ('vertices', C.c_void_p), ('vertex_capacity', C.c_int64),
         ('faces', C.c_void_p), ('face_capacity', C.c_int64),
@@ -93,6 +94,7 @@ _OPTIONAL = {
     'vtaco_marching_cubes': [C.POINTER(McArgs), C.c_void_p],
     'vtaco_mc_scratch_bytes': [C.c_int32, C.c_int32, C.c_int32],
     'vtaco_grid_minmax': [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p],
+    'vtaco_publish_keys': [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_void_p],
     'vtaco_group_norm': [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64,
                          C.c_double, C.c_void_p, C.c_void_p],
 }

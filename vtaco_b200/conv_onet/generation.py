@@ -60,6 +60,7 @@ class Generator3D(object):
         self._keys = None
         self._keys_init = None
         self._pin = None
+        self._fused = None
 
     @property
     def mc(self):
@@ -93,9 +94,13 @@ class Generator3D(object):
         nx = self.resolution0 * 4
         return (1 + self.padding) * make_3d_grid((-0.5,) * 3, (0.5,) * 3, (nx,) * 3)
 
-    def eval_lattice(self, c, tips=None, c_img_all=None, group=None):
-        """Logits on the dense lattice, device tensor (nx,nx,nx), + int32[2] min/max keys.
-        With a process group the x-slabs are decoded by different ranks and all-gathered."""
+    def eval_lattice(self, c, tips=None, c_img_all=None, group=None, exchange=None):
+        """Logits on the dense lattice, device tensor (nx,nx,nx), + int32 min/max keys.
+        With a process group the x-slabs are decoded by different ranks; `exchange`:
+          'fused' (default): the decoder kernel stores its slab into every rank's grid over
+                   NVLink peer memory (torch symmetric memory) — no collective on the data path;
+          'nccl' : all_gather_into_tensor of the slabs + MAX all-reduce of the keys.
+        Returns (grid, keys); with the fused exchange `keys` holds one (min,max) pair per rank."""
         nx = self.resolution0 * 4
         dev = self.device
         dec = self.model.decoder
@@ -109,6 +114,18 @@ class Generator3D(object):
         keys.copy_(self._keys_init)
         rank, world = vdist.rank_world(group)
         x0, x1 = vdist.slab(nx, rank, world)
+        if world > 1 and (exchange or 'fused') == 'fused':
+            if self._fused is None or self._fused.grid.shape[0] != nx:
+                self._fused = vdist.FusedExchange(nx, dev, group)
+            ex = self._fused
+            with torch.no_grad():
+                ex.barrier()                       # every rank is done reading the previous grid
+                if x1 > x0:
+                    dec.forward_dense(c, nx, x0=x0, x1=x1, use_img=self.with_img, c_img=c_img_all, tips=tips,
+                                      out=ex.grid, minmax_key=keys, axis=self._axis, peers=ex.grid_ptrs)
+                ex.publish(keys)                   # (min,max) -> slot `rank` of every table; resets keys
+                ex.barrier()                       # all slabs and key pairs have landed
+            return ex.grid, ex.table
         with torch.no_grad():
             if x1 > x0:
                 dec.forward_dense(c, nx, x0=x0, x1=x1, use_img=self.with_img, c_img=c_img_all, tips=tips,
@@ -118,16 +135,17 @@ class Generator3D(object):
                 vdist.all_reduce_minmax(keys, group)
         return self._grid, keys
 
-    def extract_mesh(self, grid, keys=None, level=None, rescale=True):
+    def extract_mesh(self, grid, keys=None, level=None, rescale=True, sync=True):
         """marching cubes at level 0.5*(min+max) + `(v - nx/2) * (1+padding)/nx`
         (reference generation.py:268-272).  Returns device tensors (vertices, faces)."""
         nx = grid.shape[0]
         box = 1 + self.padding
         if rescale:
-            return self.mc(grid, level=level, level_keys=keys, voffset=np.float32(nx / 2), vscale=np.float32(box / nx))
-        return self.mc(grid, level=level, level_keys=keys)
+            return self.mc(grid, level=level, level_keys=keys, voffset=np.float32(nx / 2), vscale=np.float32(box / nx),
+                           sync=sync)
+        return self.mc(grid, level=level, level_keys=keys, sync=sync)
 
-    def generate_mesh(self, inputs=None, c=None, tips=None, c_img_all=None, group=None, to_host=True):
+    def generate_mesh(self, inputs=None, c=None, tips=None, c_img_all=None, group=None, to_host=True, exchange=None):
         """inputs (1,T,3) point cloud -> encoder -> lattice logits -> mesh.
         tips = (positions (F,3) float64, features (F,c_dim) device tensor, touch (F,), radius)."""
         self.model.eval()
@@ -135,7 +153,7 @@ class Generator3D(object):
         with torch.no_grad():
             if c is None:
                 c = self.model.encode_inputs(inputs.to(dev, non_blocking=True))
-            grid, keys = self.eval_lattice(c, tips=tips, c_img_all=c_img_all, group=group)
+            grid, keys = self.eval_lattice(c, tips=tips, c_img_all=c_img_all, group=group, exchange=exchange)
             v, f = self.extract_mesh(grid, keys)
         if to_host:
             return self._to_host(v, f)

@@ -310,7 +310,7 @@ class LocalDecoder(nn.Module):
 
     # ------------------------------------------------------------------ dense lattice (Generator3D fast path)
     def forward_dense(self, c_plane, nx, x0=0, x1=None, use_img=False, c_img=None, tips=None,
-                      out=None, minmax_key=None, axis=None):
+                      out=None, minmax_key=None, axis=None, peers=None):
         """Evaluate the extraction lattice (1+padding)*make_3d_grid(nx^3) (reference
         generation.py:155-157) for rows x in [x0,x1) directly into `out` (nx,nx,nx).
 
@@ -354,6 +354,12 @@ class LocalDecoder(nn.Module):
             featc = feat.contiguous()
             a.tip_feat = featc.data_ptr()
         a.logits = out.data_ptr()
+        if peers:  # fused all-gather: device pointers of every rank's (nx,nx,nx) grid (vtaco_b200.dist.FusedExchange)
+            if len(peers) > 8:
+                raise ValueError('at most 8 peers')
+            a.n_peers = len(peers)
+            for r, ptr_ in enumerate(peers):
+                a.logits_peers[r] = int(ptr_)
         if minmax_key is not None:
             a.minmax_key = minmax_key.data_ptr()
         self._run(a, dev)

@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const __grid_const
 #pragma unroll
       for (int s = 0; s < 2; ++s) {
         if (valid[s]) {
-          P.logits[oidx[s]] = o[s];
+          store_logit(P, oidx[s], o[s]);
           if (P.contact) P.contact[oidx[s]] = oc[s];
           vmin = fminf(vmin, o[s]);
           vmax = fmaxf(vmax, o[s]);
@@ -465,6 +465,16 @@ extern "C" int vtaco_decoder_forward(const vtaco_decoder_args* a, void* stream) 
   }
   cudaStream_t st = (cudaStream_t)stream;
   P.t_nbx = P.t_nby = P.t_nbz = P.t_xend = 0;
+  P.n_peers = 0;
+  if (a->n_peers < 0 || a->n_peers > 8) return VTACO_ERR_INVALID_ARG;
+  if (a->n_peers > 0) {
+    if (!dense) return VTACO_ERR_UNSUPPORTED;
+    P.n_peers = a->n_peers;
+    for (int r = 0; r < a->n_peers; ++r) {
+      if (!a->logits_peers[r]) return VTACO_ERR_INVALID_ARG;
+      P.peers[r] = a->logits_peers[r];
+    }
+  }
   if (a->variant == 2) return launch_decoder_tc(P, dense, a->weights_tc, st);
   const bool f2 = (a->variant == 1);
   if (dense) return f2 ? launch_decoder<true, true>(P, smem_bytes, st) : launch_decoder<true, false>(P, smem_bytes, st);

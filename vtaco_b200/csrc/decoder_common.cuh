@@ -28,6 +28,8 @@ struct DecParams {
   long long n_tiles;
   int B, nx, x0, x1, nbx, nby;  // dense: bricks along x (slab) and along y/z
   int Rg, Rp, n_blocks, leaky, use_img, nearest, n_tips, wfloats, has_c;
+  float* peers[8];   // dense multi-GPU: logit grids of all ranks (fused all-gather)
+  int n_peers;
   int t_nbx, t_nby, t_nbz, t_xend;  // tcgen05 kernel, dense mode: 4x4x8 bricks and slab end row
   NormConst nc;
   double tips[VTACO_MAX_TIPS][3];
@@ -35,6 +37,15 @@ struct DecParams {
   double tip_radius;
   float tip_r2_hi;  // fp32 prefilter threshold (squared, padded)
 };
+
+__device__ __forceinline__ void store_logit(const DecParams& P, long long idx, float v) {
+  if (P.n_peers > 0) {
+#pragma unroll 1
+    for (int r = 0; r < P.n_peers; ++r) P.peers[r][idx] = v;
+  } else {
+    P.logits[idx] = v;
+  }
+}
 
 // ---- ATen grid_sampler arithmetic (align_corners=True, padding_mode='border') ----
 // decoder.py:58 `vgrid = 2.0 * xy - 1.0`, then grid_sampler_unnormalize:

@@ -475,7 +475,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) decoder_tc_kernel(const __grid_
         oc = fmaf(Wo[32 + j], a, oc);
       }
       if (valid) {
-        P.logits[oidx] = o;
+        store_logit(P, oidx, o);
         if (P.contact) P.contact[oidx] = oc;
         vmin = fminf(vmin, o);
         vmax = fmaxf(vmax, o);

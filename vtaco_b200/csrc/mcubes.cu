@@ -36,6 +36,7 @@ struct McParams {
   long long npts, nruns;
   float level;
   const int32_t* level_keys;
+  int n_level_keys;
   uint8_t* code;                  // [nruns][8]: bits 0-2 own-edge mask (x,y,z), bits 3-5 triangle count
   uint32_t* vbase;                // [nruns][8]: id of the first vertex owned by the point (active blocks only)
   uint2* block_sums;
@@ -50,7 +51,14 @@ struct McParams {
 };
 
 __device__ __forceinline__ float mc_level(const McParams& P) {
-  if (P.level_keys) return 0.5f * (key_to_float(P.level_keys[0]) + key_to_float(P.level_keys[1]));
+  if (P.level_keys) {
+    int32_t lo = P.level_keys[0], hi = P.level_keys[1];
+    for (int r = 1; r < P.n_level_keys; ++r) {
+      lo = min(lo, P.level_keys[2 * r]);
+      hi = max(hi, P.level_keys[2 * r + 1]);
+    }
+    return 0.5f * (key_to_float(lo) + key_to_float(hi));
+  }
   return P.level;
 }
 
@@ -304,6 +312,18 @@ __global__ void init_keys_kernel(int32_t* keys) {
   keys[1] = (int32_t)0x80000000;
 }
 
+struct PeerTables { int32_t* t[8]; };
+__global__ void publish_keys_kernel(int32_t* keys, PeerTables tabs, int n_peers, int rank) {
+  const int32_t lo = keys[0], hi = keys[1];
+  for (int r = 0; r < n_peers; ++r) {
+    tabs.t[r][2 * rank] = lo;
+    tabs.t[r][2 * rank + 1] = hi;
+  }
+  __threadfence_system();
+  keys[0] = 0x7fffffff;
+  keys[1] = (int32_t)0x80000000;
+}
+
 static long long mc_align(long long v) { return (v + 255) / 256 * 256; }
 
 }  // namespace vtaco
@@ -342,6 +362,7 @@ extern "C" int vtaco_marching_cubes(const vtaco_mc_args* a, void* stream) {
   McParams P = {};
   P.grid = a->grid; P.nx = a->nx; P.ny = a->ny; P.nz = a->nz; P.npts = n;
   P.level = a->level; P.level_keys = a->level_keys;
+  P.n_level_keys = a->n_level_keys > 1 ? a->n_level_keys : 1;
   P.nzc = (a->nz + kMcRun - 1) / kMcRun;
   P.nruns = (long long)a->nx * a->ny * P.nzc;
   P.nblocks = (int)((P.nruns + kMcThreads - 1) / kMcThreads);
@@ -362,6 +383,15 @@ extern "C" int vtaco_marching_cubes(const vtaco_mc_args* a, void* stream) {
     mc_vertices_kernel<<<P.nblocks, kMcThreads, 0, st>>>(P);
     mc_faces_kernel<<<P.nblocks, kMcThreads, 0, st>>>(P);
   }
+  VTACO_LAUNCH_CHECK();
+  return VTACO_OK;
+}
+
+extern "C" int vtaco_publish_keys(int32_t* keys, int32_t* const* tables, int32_t n_peers, int32_t rank, void* stream) {
+  if (!keys || !tables || n_peers < 1 || n_peers > 8 || rank < 0 || rank >= n_peers) return VTACO_ERR_INVALID_ARG;
+  PeerTables t;
+  for (int r = 0; r < 8; ++r) t.t[r] = r < n_peers ? tables[r] : nullptr;
+  publish_keys_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(keys, t, n_peers, rank);
   VTACO_LAUNCH_CHECK();
   return VTACO_OK;
 }

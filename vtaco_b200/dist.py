@@ -55,3 +55,39 @@ def all_reduce_minmax(keys, group=None):
     k[0] = -k[0]
     keys.copy_(k.to(torch.int32))
     return keys
+
+
+class FusedExchange(object):
+    """Logit grid + iso-level key table in torch symmetric memory (peer-mapped over NVLink).
+
+    The decoder kernel stores every logit of its slab straight into the grids of ALL ranks
+    (`vtaco_decoder_args.logits_peers`), so the all-gather is fused into the decoder epilogue and
+    overlaps the math; the (min,max) key pairs are published into a per-rank slot of every
+    peer's table by a one-thread kernel.  Two symmetric-memory barriers per step order the
+    writers against the marching-cubes readers.  No NCCL collective is on the data path."""
+
+    def __init__(self, nx, device, group):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if self.world > 8:
+            raise ValueError('fused exchange supports up to 8 ranks (one NVSwitch domain)')
+        self.grid = symm.empty((nx, nx, nx), dtype=torch.float32, device=device)
+        self.table = symm.empty((2 * self.world,), dtype=torch.int32, device=device)
+        self.h_grid = symm.rendezvous(self.grid, group)
+        self.h_table = symm.rendezvous(self.table, group)
+        self.grid_ptrs = [int(p) + int(getattr(self.h_grid, 'offset', 0)) for p in self.h_grid.buffer_ptrs]
+        self.table_ptrs = [int(p) + int(getattr(self.h_table, 'offset', 0)) for p in self.h_table.buffer_ptrs]
+        assert self.grid_ptrs[self.rank] == self.grid.data_ptr(), 'symmetric buffer pointer mismatch'
+        self._tabs = (C.c_void_p * self.world)(*self.table_ptrs)
+        self.device = device
+
+    def barrier(self):
+        self.h_grid.barrier()
+
+    def publish(self, keys):
+        from . import _abi
+        with torch.cuda.device(self.device):
+            st = _abi.lib().vtaco_publish_keys(_abi.ptr(keys), self._tabs, self.world, self.rank,
+                                               _abi.stream_ptr(self.device))
+        _abi.check(st, 'publish_keys')

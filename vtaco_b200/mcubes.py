@@ -18,7 +18,8 @@ def new_minmax_key(device):
 def keys_to_level(keys):
     """level=None of skimage: 0.5*(min+max) in fp32 (host helper; syncs)."""
     L = _abi.lib()
-    lo, hi = [L.vtaco_key_to_float_host(int(k)) for k in keys.cpu()]
+    k = keys.cpu().reshape(-1, 2)
+    lo, hi = L.vtaco_key_to_float_host(int(k[:, 0].min())), L.vtaco_key_to_float_host(int(k[:, 1].max()))
     return float(torch.tensor(0.5, dtype=torch.float32) * (torch.tensor(lo, dtype=torch.float32) +
                                                             torch.tensor(hi, dtype=torch.float32)))
 
@@ -69,6 +70,7 @@ class MarchingCubes(object):
                     _abi.check(L.vtaco_grid_minmax(_abi.ptr(volume), n, _abi.ptr(self._keys), st), 'grid_minmax')
                     level_keys = self._keys
                 a.level_keys = level_keys.data_ptr()
+                a.n_level_keys = max(1, level_keys.numel() // 2)
             else:
                 a.level = float(level)
             a.scratch, a.scratch_bytes = self._scratch.data_ptr(), self._scratch.numel()
