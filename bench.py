@@ -250,6 +250,20 @@ def run_ours(args, rank, local_rank, world):
 
     c = encode_features()
     tips_arg = (tips, tip_feat, touch, 0.05)
+    exchange_note = None
+    if world > 1 and args.exchange == 'fused':
+        # symmetric-memory rendezvous must succeed on EVERY rank, else all ranks use NCCL
+        ok = torch.ones(1, device=dev)
+        try:
+            gen.eval_lattice(c, tips=tips_arg, group=group, exchange='fused')
+        except Exception as e:  # noqa: BLE001 - report and fall back to the NCCL plumbing
+            ok.zero_()
+            exchange_note = 'fused exchange unavailable (%s); NCCL all-gather used' % type(e).__name__
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if ok.item() == 0:
+            args.exchange = 'nccl'
+            gen._fused = None
+            exchange_note = exchange_note or 'fused exchange unavailable on a peer; NCCL all-gather used' 
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
 
     def device_step():
@@ -403,6 +417,8 @@ def run_ours(args, rank, local_rank, world):
             'mesh': {'vertices': V, 'faces': F},
             'clocks': clocks.summary(), 'wall_s_timed_region': wall,
         }
+        if world > 1:
+            line['exchange'] = args.exchange if exchange_note is None else exchange_note
         if world == 1 and not args.no_cpu_baseline:
             ref = CpuReference(nx, args.cpu_sample)
             ref.run()

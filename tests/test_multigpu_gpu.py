@@ -48,7 +48,7 @@ def _worker(rank, world, port, nx, q, exchange='nccl'):
         v, f = gen.extract_mesh(grid, keys)
         v, f = v.clone(), f.clone()
         single, skeys = gen.eval_lattice(c, group=False)   # this rank alone, whole lattice
-        single = single.clone()
+        single, skeys = single.clone(), skeys.clone()   # the generator re-uses these buffers
         from vtaco_b200.mcubes import keys_to_level
         lvl = keys_to_level(keys)
         grid2, _ = gen.eval_lattice(c, group=dist.group.WORLD, exchange=exchange)
