@@ -314,11 +314,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) decoder_tc_kernel(const __grid_
     bool valid;
     if (DENSE) {
       long long t = tile;
-      const int bz = (int)(t % P.t_nbz); t /= P.t_nbz;   // bricks: 4 (x) x 4 (y) x 8 (z)
-      const int by = (int)(t % P.t_nby); t /= P.t_nby;
+      const int bz = (int)(t % P.t_nbz); t /= P.t_nbz;   // bricks: 2 (x) x 2 (y) x 32 (z): a warp = one z-run,
+      const int by = (int)(t % P.t_nby); t /= P.t_nby;   // its 32 logits are one 128-byte store per destination
       const int bx = (int)(t % P.t_nbx);
       const int b = (int)(t / P.t_nbx);
-      const int ix = P.x0 + bx * 4 + (tg >> 5), iy = by * 4 + ((tg >> 3) & 3), iz = bz * 8 + (tg & 7);
+      const int ix = P.x0 + bx * 2 + (tg >> 6), iy = by * 2 + ((tg >> 5) & 1), iz = bz * 32 + (tg & 31);
       valid = (ix < P.t_xend) && (iy < nx) && (iz < nx);
       px = __ldg(P.axis + min(ix, nx - 1));
       py = __ldg(P.axis + min(iy, nx - 1));
@@ -506,9 +506,9 @@ int launch_decoder_tc(DecParams P, bool dense, const float* wtc, cudaStream_t st
   if (P.use_img && P.c_img) return VTACO_ERR_UNSUPPORTED;  // dense c_img tensor: SIMT kernel
   if (dense) {
     P.t_xend = P.x1;
-    P.t_nbz = (P.nx + 7) / 8;
-    P.t_nby = (P.nx + 3) / 4;
-    P.t_nbx = (P.x1 - P.x0 + 3) / 4;
+    P.t_nbz = (P.nx + 31) / 32;
+    P.t_nby = (P.nx + 1) / 2;
+    P.t_nbx = (P.x1 - P.x0 + 1) / 2;
     P.n_tiles = (long long)P.B * P.t_nbx * P.t_nby * P.t_nbz;
   } else {
     P.n_tiles = (P.total + kTcTile - 1) / kTcTile;

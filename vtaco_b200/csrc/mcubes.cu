@@ -95,10 +95,11 @@ __device__ __forceinline__ unsigned block_scan_excl(unsigned v, unsigned& total)
 
 // run -> lattice coordinates of its first point
 __device__ __forceinline__ void run_coords(const McParams& P, long long run, int& i, int& j, int& k0) {
-  const int kc = (int)(run % P.nzc);
-  const long long r = run / P.nzc;
-  j = (int)(r % P.ny);
-  i = (int)(r / P.ny);
+  const unsigned ru = (unsigned)run;           // nruns < 2^31 (checked by the host wrapper)
+  const unsigned r = ru / (unsigned)P.nzc;
+  const int kc = (int)(ru - r * (unsigned)P.nzc);
+  i = (int)(r / (unsigned)P.ny);
+  j = (int)(r - (unsigned)i * (unsigned)P.ny);
   k0 = kc * kMcRun;
 }
 
@@ -125,7 +126,7 @@ __device__ __forceinline__ unsigned row_bits(const McParams& P, int i, int j, in
 
 // codes of the 8 points of a run (see McParams::code); returns packed (ntris << 16 | nverts)
 __device__ __forceinline__ unsigned run_codes(const McParams& P, int i, int j, int k0, float level,
-                                               unsigned long long& codes) {
+                                               unsigned long long& codes, const uint8_t* __restrict__ tri_count) {
   const unsigned r00 = row_bits(P, i, j, k0, level), r01 = row_bits(P, i, j + 1, k0, level);
   const unsigned r10 = row_bits(P, i + 1, j, k0, level), r11 = row_bits(P, i + 1, j + 1, k0, level);
   const bool hx = i + 1 < P.nx, hy = j + 1 < P.ny;
@@ -143,7 +144,7 @@ __device__ __forceinline__ unsigned run_codes(const McParams& P, int i, int j, i
                         (((r01 >> (t + 1)) & 1u) << 6) | (((r11 >> (t + 1)) & 1u) << 7);
     const unsigned flags = (unsigned)(hx && (((cs >> 1) & 1u) != a0)) | ((unsigned)(hy && (((cs >> 2) & 1u) != a0)) << 1) |
                            ((unsigned)(hz && (((cs >> 4) & 1u) != a0)) << 2);
-    const unsigned nt = (hx && hy && hz) ? (unsigned)kMcTriCount[cs] : 0u;
+    const unsigned nt = (hx && hy && hz) ? (unsigned)tri_count[cs] : 0u;
     codes |= (unsigned long long)(flags | (nt << 3)) << (8 * t);
     packed += (nt << 16) | __popc(flags);
   }
@@ -151,13 +152,17 @@ __device__ __forceinline__ unsigned run_codes(const McParams& P, int i, int j, i
 }
 
 __global__ void __launch_bounds__(kMcThreads) mc_classify_kernel(const __grid_constant__ McParams P) {
+  // divergent look-ups: the case tables live in shared memory, not in the constant bank
+  __shared__ uint8_t s_count[256];
+  s_count[threadIdx.x] = (uint8_t)kMcTriCount[threadIdx.x];
+  __syncthreads();
   const long long run = (long long)blockIdx.x * kMcThreads + threadIdx.x;
   unsigned packed = 0;
   if (run < P.nruns) {
     int i, j, k0;
     run_coords(P, run, i, j, k0);
     unsigned long long codes;
-    packed = run_codes(P, i, j, k0, mc_level(P), codes);
+    packed = run_codes(P, i, j, k0, mc_level(P), codes, s_count);
     reinterpret_cast<unsigned long long*>(P.code)[run] = codes;
   }
   unsigned total;
@@ -249,6 +254,12 @@ __device__ __forceinline__ long long run_slot(const McParams& P, int i, int j, i
 
 __global__ void __launch_bounds__(kMcThreads) mc_faces_kernel(const __grid_constant__ McParams P) {
   if (P.block_sums[blockIdx.x].y == 0) return;
+  __shared__ int8_t s_tri[256][kMcMaxTris * 3 + 1];   // +1: odd row stride spreads the banks
+  __shared__ int8_t s_edge[12][4];
+  for (int t = threadIdx.x; t < 256 * kMcMaxTris * 3; t += kMcThreads)
+    s_tri[t / (kMcMaxTris * 3)][t % (kMcMaxTris * 3)] = kMcTriTable[t / (kMcMaxTris * 3)][t % (kMcMaxTris * 3)];
+  if (threadIdx.x < 48) s_edge[threadIdx.x >> 2][threadIdx.x & 3] = kMcEdge[threadIdx.x >> 2][threadIdx.x & 3];
+  __syncthreads();
   const long long run = (long long)blockIdx.x * kMcThreads + threadIdx.x;
   const bool fits = P.counts[0] <= P.vcap && P.counts[1] <= P.fcap && P.counts[0] < 0x7fffffffll;
   unsigned long long codes = 0;
@@ -276,9 +287,9 @@ __global__ void __launch_bounds__(kMcThreads) mc_faces_kernel(const __grid_const
       int32_t* o = P.faces + (tb + tr) * 3;
 #pragma unroll
       for (int corner = 0; corner < 3; ++corner) {
-        const int e = kMcTriTable[cs][3 * tr + corner];
-        const int a = kMcEdge[e][0];
-        const long long q = run_slot(P, i + kMcEdge[e][1], j + kMcEdge[e][2], k + kMcEdge[e][3]);
+        const int e = s_tri[cs][3 * tr + corner];
+        const int a = s_edge[e][0];
+        const long long q = run_slot(P, i + s_edge[e][1], j + s_edge[e][2], k + s_edge[e][3]);
         o[corner] = (int32_t)(P.vbase[q] + __popc((P.code[q] & 7u) & ((1u << a) - 1u)));
       }
     }
