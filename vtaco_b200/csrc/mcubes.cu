@@ -124,45 +124,52 @@ __device__ __forceinline__ unsigned row_bits(const McParams& P, int i, int j, in
   return bits;
 }
 
-// codes of the 8 points of a run (see McParams::code); returns packed (ntris << 16 | nverts)
+// codes of the 8 points of a run (see McParams::code); returns packed (ntris << 16 | nverts).
+// Bit-parallel over the run: own-edge masks are XORs of the "above" rows and a cell is cut iff
+// its 8 corner bits are neither all 0 nor all 1, so the ~95 % of runs that the surface does not
+// touch cost a handful of logic ops; only the set bits take the per-point path.
 __device__ __forceinline__ unsigned run_codes(const McParams& P, int i, int j, int k0, float level,
-                                               unsigned long long& codes, const uint8_t* __restrict__ tri_count) {
+                                               unsigned long long& codes) {
   const unsigned r00 = row_bits(P, i, j, k0, level), r01 = row_bits(P, i, j + 1, k0, level);
   const unsigned r10 = row_bits(P, i + 1, j, k0, level), r11 = row_bits(P, i + 1, j + 1, k0, level);
   const bool hx = i + 1 < P.nx, hy = j + 1 < P.ny;
-  unsigned packed = 0;
+  const int left = P.nz - k0;                                     // points of this run inside the lattice
+  const unsigned m8 = left >= kMcRun ? 0xffu : ((1u << left) - 1u);
+  const unsigned mz = left - 1 >= kMcRun ? 0xffu : ((1u << max(left - 1, 0)) - 1u);   // points with k+1 < nz
+  const unsigned fx = hx ? ((r00 ^ r10) & m8) : 0u;
+  const unsigned fy = hy ? ((r00 ^ r01) & m8) : 0u;
+  const unsigned fz = (r00 ^ (r00 >> 1)) & mz;
+  const unsigned any = r00 | r10 | r01 | r11, all = r00 & r10 & r01 & r11;
+  const unsigned cut = (hx && hy) ? (((any | (any >> 1)) & ~(all & (all >> 1))) & mz) : 0u;
   codes = 0;
-#pragma unroll
-  for (int t = 0; t < kMcRun; ++t) {
-    const int k = k0 + t;
-    if (k >= P.nz) break;
-    const bool hz = k + 1 < P.nz;
-    const unsigned a0 = (r00 >> t) & 1u;
-    // corner c = x | y<<1 | z<<2
-    const unsigned cs = a0 | (((r10 >> t) & 1u) << 1) | (((r01 >> t) & 1u) << 2) | (((r11 >> t) & 1u) << 3) |
-                        (((r00 >> (t + 1)) & 1u) << 4) | (((r10 >> (t + 1)) & 1u) << 5) |
-                        (((r01 >> (t + 1)) & 1u) << 6) | (((r11 >> (t + 1)) & 1u) << 7);
-    const unsigned flags = (unsigned)(hx && (((cs >> 1) & 1u) != a0)) | ((unsigned)(hy && (((cs >> 2) & 1u) != a0)) << 1) |
-                           ((unsigned)(hz && (((cs >> 4) & 1u) != a0)) << 2);
-    const unsigned nt = (hx && hy && hz) ? (unsigned)tri_count[cs] : 0u;
+  unsigned todo = fx | fy | fz | cut;
+  unsigned packed = __popc(fx) + __popc(fy) + __popc(fz);
+  while (todo) {
+    const int t = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const unsigned flags = ((fx >> t) & 1u) | (((fy >> t) & 1u) << 1) | (((fz >> t) & 1u) << 2);
+    unsigned nt = 0;
+    if ((cut >> t) & 1u) {
+      // corner c = x | y<<1 | z<<2
+      const unsigned cs = ((r00 >> t) & 1u) | (((r10 >> t) & 1u) << 1) | (((r01 >> t) & 1u) << 2) |
+                          (((r11 >> t) & 1u) << 3) | (((r00 >> (t + 1)) & 1u) << 4) | (((r10 >> (t + 1)) & 1u) << 5) |
+                          (((r01 >> (t + 1)) & 1u) << 6) | (((r11 >> (t + 1)) & 1u) << 7);
+      nt = (unsigned)kMcTriCount[cs];
+    }
     codes |= (unsigned long long)(flags | (nt << 3)) << (8 * t);
-    packed += (nt << 16) | __popc(flags);
+    packed += nt << 16;
   }
   return packed;
 }
 
 __global__ void __launch_bounds__(kMcThreads) mc_classify_kernel(const __grid_constant__ McParams P) {
-  // divergent look-ups: the case tables live in shared memory, not in the constant bank
-  __shared__ uint8_t s_count[256];
-  s_count[threadIdx.x] = (uint8_t)kMcTriCount[threadIdx.x];
-  __syncthreads();
   const long long run = (long long)blockIdx.x * kMcThreads + threadIdx.x;
   unsigned packed = 0;
   if (run < P.nruns) {
     int i, j, k0;
     run_coords(P, run, i, j, k0);
     unsigned long long codes;
-    packed = run_codes(P, i, j, k0, mc_level(P), codes, s_count);
+    packed = run_codes(P, i, j, k0, mc_level(P), codes);
     reinterpret_cast<unsigned long long*>(P.code)[run] = codes;
   }
   unsigned total;
@@ -254,12 +261,6 @@ __device__ __forceinline__ long long run_slot(const McParams& P, int i, int j, i
 
 __global__ void __launch_bounds__(kMcThreads) mc_faces_kernel(const __grid_constant__ McParams P) {
   if (P.block_sums[blockIdx.x].y == 0) return;
-  __shared__ int8_t s_tri[256][kMcMaxTris * 3 + 1];   // +1: odd row stride spreads the banks
-  __shared__ int8_t s_edge[12][4];
-  for (int t = threadIdx.x; t < 256 * kMcMaxTris * 3; t += kMcThreads)
-    s_tri[t / (kMcMaxTris * 3)][t % (kMcMaxTris * 3)] = kMcTriTable[t / (kMcMaxTris * 3)][t % (kMcMaxTris * 3)];
-  if (threadIdx.x < 48) s_edge[threadIdx.x >> 2][threadIdx.x & 3] = kMcEdge[threadIdx.x >> 2][threadIdx.x & 3];
-  __syncthreads();
   const long long run = (long long)blockIdx.x * kMcThreads + threadIdx.x;
   const bool fits = P.counts[0] <= P.vcap && P.counts[1] <= P.fcap && P.counts[0] < 0x7fffffffll;
   unsigned long long codes = 0;
@@ -287,9 +288,9 @@ __global__ void __launch_bounds__(kMcThreads) mc_faces_kernel(const __grid_const
       int32_t* o = P.faces + (tb + tr) * 3;
 #pragma unroll
       for (int corner = 0; corner < 3; ++corner) {
-        const int e = s_tri[cs][3 * tr + corner];
-        const int a = s_edge[e][0];
-        const long long q = run_slot(P, i + s_edge[e][1], j + s_edge[e][2], k + s_edge[e][3]);
+        const int e = kMcTriTable[cs][3 * tr + corner];
+        const int a = kMcEdge[e][0];
+        const long long q = run_slot(P, i + kMcEdge[e][1], j + kMcEdge[e][2], k + kMcEdge[e][3]);
         o[corner] = (int32_t)(P.vbase[q] + __popc((P.code[q] & 7u) & ((1u << a) - 1u)));
       }
     }
