@@ -22,7 +22,7 @@ c = {'grid': torch.randn(1, 32, 64, 64, 64, device='cuda')}
 tri = {k: torch.randn(1, 32, 64, 64, device='cuda') for k in ('xz', 'xy', 'yz')}
 out = torch.empty(nx, nx, nx, device='cuda')
 for name, feats in (('grid', c), ('tri', tri)):
-    for v in (0, 1, 2):
+    for v in (0, 1, 2, 3):
         dec.kernel_variant = v
         with torch.no_grad():
             for _ in range(2):

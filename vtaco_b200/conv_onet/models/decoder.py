@@ -235,7 +235,7 @@ class LocalDecoder(nn.Module):
         a.leaky = int(self.leaky)
         a.variant = int(self.kernel_variant)
         keep = [cl, w]
-        if a.variant == 2:
+        if a.variant in (2, 3):
             wtc = self._packed_weights_tc()
             a.weights_tc = wtc.data_ptr()
             keep.append(wtc)

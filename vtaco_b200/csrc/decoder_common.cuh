@@ -30,6 +30,7 @@ struct DecParams {
   int Rg, Rp, n_blocks, leaky, use_img, nearest, n_tips, wfloats, has_c;
   float* peers[8];   // dense multi-GPU: logit grids of all ranks (fused all-gather)
   int n_peers;
+  int tc_products;   // 3 = 3xTF32 (fp32 fidelity); 1 = single TF32 product (variant 3: timing experiments, ~1e-3 accuracy)
   int t_nbx, t_nby, t_nbz, t_xend;  // tcgen05 kernel, dense mode: 2x2x32 bricks and slab end row
   NormConst nc;
   double tips[VTACO_MAX_TIPS][3];

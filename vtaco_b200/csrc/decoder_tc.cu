@@ -10,7 +10,7 @@
 // product is evaluated as hi*hi + lo*hi + hi*lo (3xTF32, fp32 accumulation in TMEM); the
 // dropped lo*lo term and the truncation of lo are ~2^-22 relative.
 //
-// Structure (one persistent CTA per SM, 416 threads = 3 independent groups of 4 warps + 1 issuer warp):
+// Structure (one persistent CTA per SM, 384 threads = 3 independent groups of 4 warps):
 //   * a group owns a tile of 128 queries = the 128 TMEM lanes; thread t <-> query t <-> lane t;
 //   * all 3*n_blocks weight matrices (hi and lo, UMMA canonical K-major, no swizzle) stay in
 //     shared memory for the life of the CTA (120 KB); they are the B operands;
@@ -20,20 +20,17 @@
 //   * biases ride along as one more K-block: a constant (1,1,0,..) A block times a B block
 //     whose rows 0/1 hold the bias hi/lo; fc_c[i+1](c) accumulates into the same TMEM
 //     accumulator as fc_1 of block i, so a block costs 2 accumulator reads, not 3;
-//   * a 13th warp only issues MMAs: the 128 threads of a group arrive on the group's "ready"
-//     mbarrier once their operands are in TMEM; the issuer polls the three barriers, issues
-//     the step's tcgen05.mma (M128 N32 K8, kind::tf32) and commits to the group's "done"
-//     mbarrier.  The groups interleave on the tensor pipe, so one group's ALU phase overlaps
-//     the others' MMA phases and no compute warp spends issue slots on descriptors;
+//   * one elected thread per group (the role rotates over the 4 warps) issues the tcgen05.mma
+//     (M128 N32 K8, kind::tf32) of a step and commits to the group's mbarrier; the groups
+//     interleave on the tensor pipe, so one group's ALU phase overlaps the others' MMA phases;
 //   * the residual stream stays in registers; feature gather, fc_p, tips and fc_out run on the
 //     CUDA cores exactly as in the SIMT kernel.
 #include "decoder_common.cuh"
 
 namespace vtaco {
 
+constexpr int kTcThreads = 384;
 constexpr int kTcGroups = 3;
-constexpr int kTcComputeThreads = kTcGroups * 128;
-constexpr int kTcThreads = kTcComputeThreads + 32;   // + one MMA-issuer warp
 constexpr int kTcTile = 128;
 constexpr int kColsPerGroup = 168;   // C_hi 0, C_lo 32, X_hi 64, X_lo 96, ones 128 (8), D 136 (32)
 constexpr int kStageStride = 36;     // floats per staged query row (conflict-free LDS.128)
@@ -56,22 +53,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "DONE:\n"
       "}\n" ::"r"(bar), "r"(parity)
       : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -241,21 +222,25 @@ __host__ __device__ inline TcSmem tc_smem_layout(int n_blocks) {
   s.tips = s.small + (128 + 68) * 4;
   s.stage = s.tips + VTACO_MAX_TIPS * 32 * 4;
   s.stage = (s.stage + 15) / 16 * 16;
-  s.bars = s.stage + (kTcComputeThreads / 32) * 32 * kStageStride * 4;
+  s.bars = s.stage + (kTcThreads / 32) * 32 * kStageStride * 4;
   s.tmem_ptr = s.bars + 64;
   s.total = s.tmem_ptr + 16;
   return s;
 }
 
 // MMAs of one accumulation step, issued by one thread.  D = [A_x * W] + ones * Bias [+ C * Wc]
-__device__ __forceinline__ void issue_product(uint32_t d, uint32_t a_hi, uint32_t w_smem, uint32_t accumulate_first) {
+__device__ __forceinline__ void issue_product(uint32_t d, uint32_t a_hi, uint32_t w_smem, uint32_t accumulate_first,
+                                              int n_products = 3) {
   const uint32_t a_lo = a_hi + 32;
+  if (n_products >= 3) {
 #pragma unroll
-  for (int kk = 0; kk < 4; ++kk) tc_mma_ts(d, a_lo + 8 * kk, make_bdesc(w_smem + kk * 1024), kk > 0 ? 1u : accumulate_first);
+    for (int kk = 0; kk < 4; ++kk) tc_mma_ts(d, a_lo + 8 * kk, make_bdesc(w_smem + kk * 1024), kk > 0 ? 1u : accumulate_first);
 #pragma unroll
-  for (int kk = 0; kk < 4; ++kk) tc_mma_ts(d, a_hi + 8 * kk, make_bdesc(w_smem + 4096 + kk * 1024), 1);
+    for (int kk = 0; kk < 4; ++kk) tc_mma_ts(d, a_hi + 8 * kk, make_bdesc(w_smem + 4096 + kk * 1024), 1);
+    accumulate_first = 1;
+  }
 #pragma unroll
-  for (int kk = 0; kk < 4; ++kk) tc_mma_ts(d, a_hi + 8 * kk, make_bdesc(w_smem + kk * 1024), 1);
+  for (int kk = 0; kk < 4; ++kk) tc_mma_ts(d, a_hi + 8 * kk, make_bdesc(w_smem + kk * 1024), kk > 0 ? 1u : accumulate_first);
 }
 
 template <bool DENSE>
@@ -270,7 +255,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) decoder_tc_kernel(const __grid_
   uint64_t* sBars = reinterpret_cast<uint64_t*>(tsm + L.bars);
   uint32_t* sTmem = reinterpret_cast<uint32_t*>(tsm + L.tmem_ptr);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // warp index through a shuffle: the compiler can then prove g / wg and everything derived
+  // from them warp-uniform (uniform registers for the MMA descriptors, uniform branches)
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(kFull, tid >> 5, 0);
   const int g = warp >> 2, wg = warp & 3, tg = tid & 127;
   const int nb = P.n_blocks;
 
@@ -291,10 +279,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) decoder_tc_kernel(const __grid_
     }
   }
   if (tid == 0) {
-    for (int i = 0; i < kTcGroups; ++i) {
-      mbar_init(smem_u32(sBars + i), 1);                    // done[g]  : tcgen05.commit arrives
-      mbar_init(smem_u32(sBars + kTcGroups + i), 128);      // ready[g] : the group's 128 threads arrive
-    }
+    for (int i = 0; i < kTcGroups; ++i) mbar_init(smem_u32(sBars + i), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -305,65 +290,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) decoder_tc_kernel(const __grid_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *sTmem;
-  const uint32_t wsm = smem_u32(sWtc), bsm = smem_u32(tsm + L.bias);
-
-  if (warp == kTcGroups * 4) {
-    // ===== MMA issuer warp: serves whichever group has published its operands =====
-    if (lane == 0) {
-      long long tile[kTcGroups];
-      int st[kTcGroups];          // next step of the group's current tile: 0 .. 2*nb
-      uint32_t rph[kTcGroups];
-      int live = 0;
-      const int first = P.has_c ? 0 : 1;
-#pragma unroll
-      for (int gg = 0; gg < kTcGroups; ++gg) {
-        tile[gg] = (long long)blockIdx.x * kTcGroups + gg;
-        st[gg] = first;
-        rph[gg] = 0;
-        live += tile[gg] < P.n_tiles;
-      }
-      while (live > 0) {
-#pragma unroll
-        for (int gg = 0; gg < kTcGroups; ++gg) {
-          if (tile[gg] >= P.n_tiles) continue;
-          const uint32_t ready = smem_u32(sBars + kTcGroups + gg);
-          if (!mbar_test(ready, rph[gg])) continue;
-          rph[gg] ^= 1;
-          tc_fence_after();
-          const uint32_t mb = tmem_base + (uint32_t)(gg * kColsPerGroup);
-          const uint32_t mC = mb, mX = mb + 64, mOnes = mb + 128, mD = mb + 136;
-          const int sidx = st[gg];
-          if (sidx == 0) {                               // D = C*Wc_0 + ones*bc_0
-            issue_product(mD, mC, wsm, 0);
-            tc_mma_ts(mD, mOnes, make_bdesc(bsm), 1);
-          } else {
-            const int i = (sidx - 1) >> 1;
-            if (sidx & 1) {                              // D = relu(net)*W0_i + ones*b0_i
-              issue_product(mD, mX, wsm + (3 * i + 1) * 8192, 0);
-              tc_mma_ts(mD, mOnes, make_bdesc(bsm + sidx * 1024), 1);
-            } else {                                     // D = relu(h)*W1_i + ones*(b1_i + bc_{i+1}) [+ C*Wc_{i+1}]
-              issue_product(mD, mX, wsm + (3 * i + 2) * 8192, 0);
-              tc_mma_ts(mD, mOnes, make_bdesc(bsm + sidx * 1024), 1);
-              if (P.has_c && i + 1 < nb) issue_product(mD, mC, wsm + (3 * (i + 1)) * 8192, 1);
-            }
-          }
-          tc_commit(smem_u32(sBars + gg));
-          if (++st[gg] > 2 * nb) {
-            st[gg] = first;
-            tile[gg] += (long long)gridDim.x * kTcGroups;
-            live -= tile[gg] >= P.n_tiles;
-          }
-        }
-      }
-    }
-    __syncwarp();
-  } else {
-  // ===== compute warps =====
+  const uint32_t tmem_base = __shfl_sync(kFull, *sTmem, 0);
   // group columns: C_hi 0, C_lo 32, X_hi 64, X_lo 96, ones 128 (8), D 136 (32)
   const uint32_t tbase = tmem_base + ((uint32_t)(32 * wg) << 16) + (uint32_t)(g * kColsPerGroup);
   const uint32_t tC = tbase, tX = tbase + 64, tOnes = tbase + 128, tD = tbase + 136;
-  const uint32_t bar = smem_u32(sBars + g), ready = smem_u32(sBars + kTcGroups + g);
+  const uint32_t mbase = tmem_base + (uint32_t)(g * kColsPerGroup);
+  const uint32_t mC = mbase, mX = mbase + 64, mOnes = mbase + 128, mD = mbase + 136;
+  const uint32_t bar = smem_u32(sBars + g);
+  const uint32_t wsm = smem_u32(sWtc), bsm = smem_u32(tsm + L.bias);
   uint32_t ph = 0;
   {  // the constant A block that multiplies the bias rows: columns (1, 1, 0, 0, 0, 0, 0, 0)
     const uint32_t one = __float_as_uint(1.0f);
@@ -376,6 +310,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) decoder_tc_kernel(const __grid_
   const int grp = lane >> 3, sub = lane & 7;
   const int nx = P.nx;
   float vmin = CUDART_INF_F, vmax = -CUDART_INF_F;
+  int step = 0;  // accumulation steps issued so far by this group (rotates the issuing warp)
 
   for (long long tile = (long long)blockIdx.x * kTcGroups + g; tile < P.n_tiles;
        tile += (long long)gridDim.x * kTcGroups) {
@@ -450,7 +385,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) decoder_tc_kernel(const __grid_
       split_store(tC, cv);
       tc_wait_st();
       tc_fence_before();
-      mbar_arrive(ready);                         // step 0: D = C*Wc_0 + ones*bc_0 (issuer warp)
+      group_sync(g);
+      if (wg == (step & 3) && lane == 0) {       // step 0: D = C*Wc_0 + ones*bc_0
+        tc_fence_after();
+        issue_product(mD, mC, wsm, 0, P.tc_products);
+        tc_mma_ts(mD, mOnes, make_bdesc(bsm), 1);
+        tc_commit(bar);
+      }
+      ++step;
     }
 
     // ---------------- net = fc_p(p) | fc_p_img(p, tip feature) on the CUDA cores ----------------
@@ -494,7 +436,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) decoder_tc_kernel(const __grid_
       split_store(tX, x);
       tc_wait_st();
       tc_fence_before();
-      mbar_arrive(ready);                         // D = relu(net)*W0_i + ones*b0_i
+      group_sync(g);
+      if (wg == (step & 3) && lane == 0) {       // D = relu(net)*W0_i + ones*b0_i
+        tc_fence_after();
+        issue_product(mD, mX, wsm + (3 * i + 1) * 8192, 0, P.tc_products);
+        tc_mma_ts(mD, mOnes, make_bdesc(bsm + (2 * i + 1) * 1024), 1);
+        tc_commit(bar);
+      }
+      ++step;
       mbar_wait(bar, ph); ph ^= 1;
       tc_fence_after();
       tmem_ld32(tD, r);
@@ -504,7 +453,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) decoder_tc_kernel(const __grid_
       split_store(tX, x);
       tc_wait_st();
       tc_fence_before();
-      mbar_arrive(ready);                         // D = relu(h)*W1_i + ones*(b1_i + bc_{i+1}) [+ C*Wc_{i+1}]
+      group_sync(g);
+      if (wg == (step & 3) && lane == 0) {       // D = relu(h)*W1_i + ones*(b1_i + bc_{i+1}) [+ C*Wc_{i+1}]
+        tc_fence_after();
+        issue_product(mD, mX, wsm + (3 * i + 2) * 8192, 0, P.tc_products);
+        tc_mma_ts(mD, mOnes, make_bdesc(bsm + (2 * i + 2) * 1024), 1);
+        if (P.has_c && i + 1 < nb) issue_product(mD, mC, wsm + (3 * (i + 1)) * 8192, 1, P.tc_products);
+        tc_commit(bar);
+      }
+      ++step;
       mbar_wait(bar, ph); ph ^= 1;
       tc_fence_after();
       tmem_ld32(tD, r);
@@ -544,7 +501,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) decoder_tc_kernel(const __grid_
       atomicMax(P.minmax_key + 1, float_to_key(vmax));
     }
   }
-  }  // compute warps
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
