@@ -392,7 +392,7 @@ def run_ours(args, rank, local_rank, world):
                                                                                    bf16_peak, peak_tag),
                             tensor_flop_per_query=tensor_flop_per_query,
                             note='3xTF32 executes 3.36x the algorithmic FLOPs to keep fp32 accuracy; the kernel is '
-                                 'latency/issue-bound (tensor pipe ~26%% busy, issue slots ~43%%), see '
+                                 'latency/issue-bound (tensor pipe ~30% busy, issue slots ~45%), see '
                                  'profiles/decoder_tc_ncu_summary.json')
         else:
             roofline = dict(common, bound='fp32', kernel='decoder_kernel<dense> (SIMT)', achieved=achieved / 1e12,
