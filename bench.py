@@ -267,8 +267,7 @@ def run_ours(args, rank, local_rank, world):
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
 
     def device_step():
-        grid, keys = gen.eval_lattice(c, tips=tips_arg, group=group, exchange=args.exchange)
-        return gen.mc(grid, level_keys=keys, voffset=np.float32(nx / 2), vscale=np.float32(1.1 / nx), sync=False)
+        return gen.lattice_and_mesh(c, tips=tips_arg, group=group, exchange=args.exchange)
 
     def barrier():
         if world > 1:
@@ -293,6 +292,26 @@ def run_ours(args, rank, local_rank, world):
         gen.mc._ensure(0, int(V * 1.25) + 16, int(F * 1.25) + 16)
         device_step()
 
+    # ---- CUDA graph of the step (decode [+ peer stores, barriers] + marching cubes) ----
+    graph, graph_note = None, 'eager launches'
+    if not args.no_graph and (world == 1 or args.exchange == 'fused'):
+        ok = torch.ones(1, device=dev)
+        try:
+            graph, _ = gen.capture_step(c, tips=tips_arg, group=group, exchange=args.exchange)
+            graph.replay()
+            torch.cuda.synchronize(dev)
+        except Exception as e:  # noqa: BLE001
+            ok.zero_()
+            graph_note = 'eager launches (graph capture failed: %s)' % type(e).__name__
+        if world > 1:
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if ok.item() == 0:
+            graph = None
+        else:
+            graph_note = 'CUDA graph replay'
+    elif not args.no_graph:
+        graph_note = 'eager launches (NCCL exchange is not captured)'
+
     # ---- timed region: K steps, per-step CUDA events, L2 flushed in between ----
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
            torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -303,14 +322,21 @@ def run_ours(args, rank, local_rank, world):
             flush.fill_(float(s))
             e0, e_dec, e1 = ev[s]
             e0.record()
-            grid, keys = gen.eval_lattice(c, tips=tips_arg, group=None if world == 1 else group, exchange=args.exchange)
-            e_dec.record()
-            gen.mc(grid, level_keys=keys, voffset=np.float32(nx / 2), vscale=np.float32(1.1 / nx), sync=False)
+            if graph is not None:
+                graph.replay()
+                e_dec.record()
+            else:
+                grid, keys = gen.eval_lattice(c, tips=tips_arg, group=None if world == 1 else group,
+                                              exchange=args.exchange)
+                e_dec.record()
+                gen.mc(grid, level_keys=keys, voffset=np.float32(nx / 2), vscale=np.float32(1.1 / nx), sync=False)
             e1.record()
         barrier()
     wall = time.perf_counter() - wall0
     step_ms = [e0.elapsed_time(e1) for e0, _, e1 in ev]
     dec_ms = [e0.elapsed_time(ed) for e0, ed, _ in ev]
+    if graph is not None:   # stages are inside one graph launch: split by the separately timed decoder kernel below
+        dec_ms = None
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX, group=group)
@@ -412,8 +438,11 @@ def run_ours(args, rank, local_rank, world):
                     'path': 'Generator3D.generate_mesh: pinned cloud -> H2D -> LocalPoolPointnet+UNet3D -> '
                             'decode -> marching cubes -> mesh D2H'},
             'gpu_launches': args.steps * 5,  # per step: 1 fused decoder + 4 marching-cubes kernels
-            'stage_ms': {'decode_plus_exchange': float(np.mean(dec_ms)), 'marching_cubes':
-                         float(np.mean(step_ms)) - float(np.mean(dec_ms))},
+            'stage_ms': ({'decode_plus_exchange': float(np.mean(dec_ms)), 'marching_cubes':
+                          float(np.mean(step_ms)) - float(np.mean(dec_ms))} if dec_ms is not None else
+                         {'decoder_kernel_alone': k_ms, 'rest_of_step(exchange+marching_cubes)':
+                          float(np.mean(step_ms)) - k_ms}),
+            'launch_mode': graph_note,
             'mesh': {'vertices': V, 'faces': F},
             'clocks': clocks.summary(), 'wall_s_timed_region': wall,
         }
@@ -444,6 +473,7 @@ def main():
                     help='decoder kernel: 0 scalar-FFMA SIMT, 1 packed-FFMA2 SIMT, 2 tcgen05 3xTF32 (default)')
     ap.add_argument('--cpu-sample', type=int, default=4 * 256 * 256)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='launch the step eagerly instead of replaying a CUDA graph')
     ap.add_argument('--exchange', default='fused', choices=['fused', 'nccl'],
                     help='N>1: fused = decoder stores slabs into peer grids over NVLink; nccl = all-gather')
     args = ap.parse_args()

@@ -145,6 +145,31 @@ class Generator3D(object):
                            sync=sync)
         return self.mc(grid, level=level, level_keys=keys, sync=sync)
 
+    def lattice_and_mesh(self, c, tips=None, c_img_all=None, group=None, exchange=None):
+        """One device-resident pass: lattice logits (+ exchange) and marching cubes, no host
+        synchronisation.  Returns the extractor's (vertex buffer, face buffer, int64[2] counts)."""
+        nx = self.resolution0 * 4
+        grid, keys = self.eval_lattice(c, tips=tips, c_img_all=c_img_all, group=group, exchange=exchange)
+        return self.mc(grid, level_keys=keys, voffset=np.float32(nx / 2), vscale=np.float32((1 + self.padding) / nx),
+                       sync=False)
+
+    def capture_step(self, c, tips=None, c_img_all=None, group=None, exchange=None, warmup=2):
+        """Capture `lattice_and_mesh` into a CUDA graph (launch latency and Python overhead off
+        the critical path — it matters once a slab decodes in well under a millisecond).
+        Returns (graph, outputs); call graph.replay() per step.  The feature tensors, tips and
+        all buffers are baked into the graph: re-capture when they change."""
+        for _ in range(max(1, warmup)):          # allocations, attribute set-up, rendezvous
+            out = self.lattice_and_mesh(c, tips, c_img_all, group, exchange)
+        V, F = [int(x) for x in out[2].cpu()]
+        if V > out[0].shape[0] or F > out[1].shape[0]:
+            self.mc._ensure(0, int(V * 1.5) + 16, int(F * 1.5) + 16)
+            self.lattice_and_mesh(c, tips, c_img_all, group, exchange)
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = self.lattice_and_mesh(c, tips, c_img_all, group, exchange)
+        return graph, out
+
     def generate_mesh(self, inputs=None, c=None, tips=None, c_img_all=None, group=None, to_host=True, exchange=None):
         """inputs (1,T,3) point cloud -> encoder -> lattice logits -> mesh.
         tips = (positions (F,3) float64, features (F,c_dim) device tensor, touch (F,), radius)."""
