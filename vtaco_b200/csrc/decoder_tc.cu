@@ -26,6 +26,8 @@
 //   * the residual stream stays in registers; feature gather, fc_p, tips and fc_out run on the
 //     CUDA cores exactly as in the SIMT kernel.
 #include "decoder_common.cuh"
+#include <cstdio>
+#include <cstdlib>
 
 namespace vtaco {
 
@@ -53,6 +55,21 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "DONE:\n"
       "}\n" ::"r"(bar), "r"(parity)
       : "memory");
+}
+// exactly one lane of a converged warp; unlike `lane == 0` the compiler knows a single lane is
+// active, so tcgen05.mma sequences compile to back-to-back UTCHMMA without per-instruction
+// ELECT / retry loops (measured: ~45 -> ~16 cycles of issue per MMA)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .b32 rx;\n"
+      ".reg .pred px;\n"
+      "elect.sync rx|px, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, px;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -243,9 +260,18 @@ __device__ __forceinline__ void issue_product(uint32_t d, uint32_t a_hi, uint32_
   for (int kk = 0; kk < 4; ++kk) tc_mma_ts(d, a_hi + 8 * kk, make_bdesc(w_smem + kk * 1024), kk > 0 ? 1u : accumulate_first);
 }
 
+// Debug-only phase tracing (VTACO_TC_TRACE=1): clock64 stamps of one warp of block 0, group 0.
+#define TC_STAMP(slot)                                                            \
+  do {                                                                            \
+    if (trace && blockIdx.x == 0 && warp == 0 && lane == 0 && trace_n < 4096)     \
+      trace[trace_n++] = ((long long)(slot) << 56) | (clock64() & 0x00ffffffffffffffll); \
+  } while (0)
+
 template <bool DENSE>
 __global__ void __launch_bounds__(kTcThreads, 1) decoder_tc_kernel(const __grid_constant__ DecParams P,
-                                                                   const float* __restrict__ wtc) {
+                                                                   const float* __restrict__ wtc,
+                                                                   long long* __restrict__ trace) {
+  int trace_n = 0;
   extern __shared__ __align__(1024) unsigned char tsm[];
   const TcSmem L = tc_smem_layout(P.n_blocks);
   float* sWtc = reinterpret_cast<float*>(tsm + L.w);
@@ -386,7 +412,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) decoder_tc_kernel(const __grid_
       tc_wait_st();
       tc_fence_before();
       group_sync(g);
-      if (wg == (step & 3) && lane == 0) {       // step 0: D = C*Wc_0 + ones*bc_0
+      if (wg == (step & 3) && elect_one()) {     // step 0: D = C*Wc_0 + ones*bc_0
         tc_fence_after();
         issue_product(mD, mC, wsm, 0, P.tc_products);
         tc_mma_ts(mD, mOnes, make_bdesc(bsm), 1);
@@ -431,30 +457,37 @@ __global__ void __launch_bounds__(kTcThreads, 1) decoder_tc_kernel(const __grid_
 
     // ---------------- residual blocks: 2 accumulation steps each ----------------
     for (int i = 0; i < nb; ++i) {
+      TC_STAMP(1);   // ALU phase starts (accumulator already read)
 #pragma unroll
       for (int j = 0; j < 32; ++j) x[j] = fmaxf(net[j], 0.f);
       split_store(tX, x);
+      TC_STAMP(2);   // operands computed, tcgen05.st issued
       tc_wait_st();
       tc_fence_before();
+      TC_STAMP(3);   // stores complete
       group_sync(g);
-      if (wg == (step & 3) && lane == 0) {       // D = relu(net)*W0_i + ones*b0_i
+      TC_STAMP(4);   // group barrier passed
+      if (wg == (step & 3) && elect_one()) {     // D = relu(net)*W0_i + ones*b0_i
         tc_fence_after();
         issue_product(mD, mX, wsm + (3 * i + 1) * 8192, 0, P.tc_products);
         tc_mma_ts(mD, mOnes, make_bdesc(bsm + (2 * i + 1) * 1024), 1);
         tc_commit(bar);
       }
       ++step;
+      TC_STAMP(5);   // (issuing warp: MMAs issued)
       mbar_wait(bar, ph); ph ^= 1;
+      TC_STAMP(6);   // MMAs complete
       tc_fence_after();
       tmem_ld32(tD, r);
       tc_wait_ld();
+      TC_STAMP(7);   // accumulator in registers
 #pragma unroll
       for (int j = 0; j < 32; ++j) x[j] = fmaxf(__uint_as_float(r[j]), 0.f);
       split_store(tX, x);
       tc_wait_st();
       tc_fence_before();
       group_sync(g);
-      if (wg == (step & 3) && lane == 0) {       // D = relu(h)*W1_i + ones*(b1_i + bc_{i+1}) [+ C*Wc_{i+1}]
+      if (wg == (step & 3) && elect_one()) {     // D = relu(h)*W1_i + ones*(b1_i + bc_{i+1}) [+ C*Wc_{i+1}]
         tc_fence_after();
         issue_product(mD, mX, wsm + (3 * i + 2) * 8192, 0, P.tc_products);
         tc_mma_ts(mD, mOnes, make_bdesc(bsm + (2 * i + 2) * 1024), 1);
@@ -532,9 +565,31 @@ int launch_decoder_tc(DecParams P, bool dense, const float* wtc, cudaStream_t st
   }
   long long grid = (P.n_tiles + kTcGroups - 1) / kTcGroups;
   if (grid > num_sms()) grid = num_sms();
-  if (dense) decoder_tc_kernel<true><<<(unsigned)grid, kTcThreads, L.total, stream>>>(P, wtc);
-  else decoder_tc_kernel<false><<<(unsigned)grid, kTcThreads, L.total, stream>>>(P, wtc);
+  long long* trace = nullptr;
+  static const bool want_trace = getenv("VTACO_TC_TRACE") != nullptr;
+  if (want_trace) {
+    VTACO_CUDA_CHECK(cudaMalloc(&trace, 4096 * sizeof(long long)));
+    VTACO_CUDA_CHECK(cudaMemsetAsync(trace, 0, 4096 * sizeof(long long), stream));
+  }
+  if (dense) decoder_tc_kernel<true><<<(unsigned)grid, kTcThreads, L.total, stream>>>(P, wtc, trace);
+  else decoder_tc_kernel<false><<<(unsigned)grid, kTcThreads, L.total, stream>>>(P, wtc, trace);
   VTACO_LAUNCH_CHECK();
+  if (trace) {   // debug: average cycles between consecutive stamps, per (from -> to) slot pair
+    static long long h[4096];
+    VTACO_CUDA_CHECK(cudaStreamSynchronize(stream));
+    VTACO_CUDA_CHECK(cudaMemcpy(h, trace, sizeof(h), cudaMemcpyDeviceToHost));
+    cudaFree(trace);
+    double sum[8][8] = {{0}};
+    long long cnt[8][8] = {{0}};
+    for (int i = 1; i < 4096 && h[i]; ++i) {
+      const int a = (int)(h[i - 1] >> 56) & 7, b = (int)(h[i] >> 56) & 7;
+      const long long d = (h[i] & 0x00ffffffffffffffll) - (h[i - 1] & 0x00ffffffffffffffll);
+      if (d >= 0 && d < 1000000) { sum[a][b] += (double)d; cnt[a][b]++; }
+    }
+    for (int a = 0; a < 8; ++a)
+      for (int b = 0; b < 8; ++b)
+        if (cnt[a][b]) fprintf(stderr, "[vtaco tc trace] %d -> %d : %8.0f cycles (n=%lld)\n", a, b, sum[a][b] / cnt[a][b], cnt[a][b]);
+  }
   return VTACO_OK;
 }
 
