@@ -228,6 +228,7 @@ def run_ours(args, rank, local_rank, world):
     net = build_models(dev)
     net.decoder.kernel_variant = args.variant
     gen = Generator3D(net, device=dev, resolution0=nx // 4, with_img=True, padding=0.1, input_type='pointcloud')
+    gen.use_multicast = not args.no_multicast
     cloud_np, tips, tip_feat_np, touch = synthetic_scene(0)
     cloud_host = torch.from_numpy(cloud_np)[None].pin_memory()
     tip_feat_host = torch.from_numpy(tip_feat_np).pin_memory()
@@ -448,6 +449,8 @@ def run_ours(args, rank, local_rank, world):
         }
         if world > 1:
             line['exchange'] = args.exchange if exchange_note is None else exchange_note
+            if gen._fused is not None:
+                line['exchange'] += ' (NVLS multicast stores)' if gen._fused.grid_multicast else ' (unicast peer stores)'
         if world == 1 and not args.no_cpu_baseline:
             ref = CpuReference(nx, args.cpu_sample)
             ref.run()
@@ -473,6 +476,7 @@ def main():
                     help='decoder kernel: 0 scalar-FFMA SIMT, 1 packed-FFMA2 SIMT, 2 tcgen05 3xTF32 (default)')
     ap.add_argument('--cpu-sample', type=int, default=4 * 256 * 256)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-multicast', action='store_true', help='fused exchange with unicast peer stores only')
     ap.add_argument('--no-graph', action='store_true', help='launch the step eagerly instead of replaying a CUDA graph')
     ap.add_argument('--exchange', default='fused', choices=['fused', 'nccl'],
                     help='N>1: fused = decoder stores slabs into peer grids over NVLink; nccl = all-gather')

@@ -154,6 +154,10 @@ typedef struct vtaco_decoder_args {
    * all-gather of the logit slabs into the decoder epilogue: no separate collective. */
   float* logits_peers[8];
   int32_t n_peers;
+  /* optional NVLS multicast address of the same grids (all ranks bound to one multicast object):
+   * when non-NULL (and n_peers > 0) each logit is written ONCE with multimem.st and the NVSwitch
+   * replicates it to every rank, instead of n_peers unicast stores. */
+  float* logits_multicast;
 } vtaco_decoder_args;
 
 int vtaco_decoder_forward(const vtaco_decoder_args* args, void* stream);

@@ -39,7 +39,7 @@ class DecoderArgs(C.Structure):
         ('tip_radius', C.c_double), ('tip_feat', C.c_void_p),
         ('logits', C.c_void_p), ('contact', C.c_void_p), ('minmax_key', C.c_void_p),
         ('variant', C.c_int32), ('weights_tc', C.c_void_p),
-        ('logits_peers', C.c_void_p * 8), ('n_peers', C.c_int32),
+        ('logits_peers', C.c_void_p * 8), ('n_peers', C.c_int32), ('logits_multicast', C.c_void_p),
     ]
 
 

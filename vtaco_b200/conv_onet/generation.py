@@ -61,6 +61,7 @@ class Generator3D(object):
         self._keys_init = None
         self._pin = None
         self._fused = None
+        self.use_multicast = True   # NVLS multimem.st for the fused exchange when the fabric supports it
 
     @property
     def mc(self):
@@ -116,13 +117,14 @@ class Generator3D(object):
         x0, x1 = vdist.slab(nx, rank, world)
         if world > 1 and (exchange or 'fused') == 'fused':
             if self._fused is None or self._fused.grid.shape[0] != nx:
-                self._fused = vdist.FusedExchange(nx, dev, group)
+                self._fused = vdist.FusedExchange(nx, dev, group, use_multicast=self.use_multicast)
             ex = self._fused
             with torch.no_grad():
                 ex.barrier()                       # every rank is done reading the previous grid
                 if x1 > x0:
                     dec.forward_dense(c, nx, x0=x0, x1=x1, use_img=self.with_img, c_img=c_img_all, tips=tips,
-                                      out=ex.grid, minmax_key=keys, axis=self._axis, peers=ex.grid_ptrs)
+                                      out=ex.grid, minmax_key=keys, axis=self._axis, peers=ex.grid_ptrs,
+                                      multicast=ex.grid_multicast)
                 ex.publish(keys)                   # (min,max) -> slot `rank` of every table; resets keys
                 ex.barrier()                       # all slabs and key pairs have landed
             return ex.grid, ex.table

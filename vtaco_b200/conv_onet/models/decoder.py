@@ -310,7 +310,7 @@ class LocalDecoder(nn.Module):
 
     # ------------------------------------------------------------------ dense lattice (Generator3D fast path)
     def forward_dense(self, c_plane, nx, x0=0, x1=None, use_img=False, c_img=None, tips=None,
-                      out=None, minmax_key=None, axis=None, peers=None):
+                      out=None, minmax_key=None, axis=None, peers=None, multicast=None):
         """Evaluate the extraction lattice (1+padding)*make_3d_grid(nx^3) (reference
         generation.py:155-157) for rows x in [x0,x1) directly into `out` (nx,nx,nx).
 
@@ -360,6 +360,8 @@ class LocalDecoder(nn.Module):
             a.n_peers = len(peers)
             for r, ptr_ in enumerate(peers):
                 a.logits_peers[r] = int(ptr_)
+            if multicast:
+                a.logits_multicast = int(multicast)
         if minmax_key is not None:
             a.minmax_key = minmax_key.data_ptr()
         self._run(a, dev)

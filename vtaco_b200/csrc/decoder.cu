@@ -466,6 +466,7 @@ extern "C" int vtaco_decoder_forward(const vtaco_decoder_args* a, void* stream) 
   cudaStream_t st = (cudaStream_t)stream;
   P.t_nbx = P.t_nby = P.t_nbz = P.t_xend = 0;
   P.n_peers = 0;
+  P.mcast = nullptr;
   if (a->n_peers < 0 || a->n_peers > 8) return VTACO_ERR_INVALID_ARG;
   if (a->n_peers > 0) {
     if (!dense) return VTACO_ERR_UNSUPPORTED;
@@ -474,6 +475,7 @@ extern "C" int vtaco_decoder_forward(const vtaco_decoder_args* a, void* stream) 
       if (!a->logits_peers[r]) return VTACO_ERR_INVALID_ARG;
       P.peers[r] = a->logits_peers[r];
     }
+    P.mcast = a->logits_multicast;
   }
   P.tc_products = (a->variant == 3) ? 1 : 3;
   if (a->variant == 2 || a->variant == 3) return launch_decoder_tc(P, dense, a->weights_tc, st);

@@ -29,6 +29,7 @@ struct DecParams {
   int B, nx, x0, x1, nbx, nby;  // dense: bricks along x (slab) and along y/z
   int Rg, Rp, n_blocks, leaky, use_img, nearest, n_tips, wfloats, has_c;
   float* peers[8];   // dense multi-GPU: logit grids of all ranks (fused all-gather)
+  float* mcast;      // NVLS multicast alias of those grids (one multimem.st reaches every rank) or NULL
   int n_peers;
   int tc_products;   // 3 = 3xTF32 (fp32 fidelity); 1 = single TF32 product (variant 3: timing experiments, ~1e-3 accuracy)
   int t_nbx, t_nby, t_nbz, t_xend;  // tcgen05 kernel, dense mode: 2x2x32 bricks and slab end row
@@ -40,7 +41,9 @@ struct DecParams {
 };
 
 __device__ __forceinline__ void store_logit(const DecParams& P, long long idx, float v) {
-  if (P.n_peers > 0) {
+  if (P.mcast) {
+    asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(P.mcast + idx), "f"(v) : "memory");
+  } else if (P.n_peers > 0) {
 #pragma unroll 1
     for (int r = 0; r < P.n_peers; ++r) P.peers[r][idx] = v;
   } else {

@@ -66,7 +66,7 @@ class FusedExchange(object):
     peer's table by a one-thread kernel.  Two symmetric-memory barriers per step order the
     writers against the marching-cubes readers.  No NCCL collective is on the data path."""
 
-    def __init__(self, nx, device, group):
+    def __init__(self, nx, device, group, use_multicast=True):
         import ctypes as C
         import torch.distributed._symmetric_memory as symm
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
@@ -79,6 +79,8 @@ class FusedExchange(object):
         self.grid_ptrs = [int(p) + int(getattr(self.h_grid, 'offset', 0)) for p in self.h_grid.buffer_ptrs]
         self.table_ptrs = [int(p) + int(getattr(self.h_table, 'offset', 0)) for p in self.h_table.buffer_ptrs]
         assert self.grid_ptrs[self.rank] == self.grid.data_ptr(), 'symmetric buffer pointer mismatch'
+        mc = int(getattr(self.h_grid, 'multicast_ptr', 0) or 0)
+        self.grid_multicast = (mc + int(getattr(self.h_grid, 'offset', 0))) if (mc and use_multicast) else 0
         self._tabs = (C.c_void_p * self.world)(*self.table_ptrs)
         self.device = device
 
