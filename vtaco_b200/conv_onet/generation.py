@@ -172,6 +172,47 @@ class Generator3D(object):
             out = self.lattice_and_mesh(c, tips, c_img_all, group, exchange)
         return graph, out
 
+    def capture_generate(self, inputs_host, tips=None, warmup=2):
+        """CUDA graph of the whole single-GPU extraction for a fixed input shape:
+        H2D copy of the (pinned) host cloud -> encoder (PointNet kernels + UNet/UNet3D) ->
+        lattice decode -> marching cubes.  Usage:
+            run = gen.capture_generate(pinned_cloud, tips)      # once per shape
+            pinned_cloud.copy_(new_cloud); v, f = run()         # per scene (host arrays)
+        The tip positions / touch mask are baked in; tip features are read from the tensor
+        passed in `tips` at replay time (update it in place)."""
+        if not inputs_host.is_pinned():
+            raise ValueError('inputs_host must be a pinned host tensor (it is re-read at every replay)')
+        dev = self.device
+        static_in = torch.empty(inputs_host.shape, dtype=torch.float32, device=dev)
+        self.model.eval()
+
+        def body():
+            static_in.copy_(inputs_host, non_blocking=True)
+            c = self.model.encode_inputs(static_in)
+            return self.lattice_and_mesh(c, tips=tips)
+
+        with torch.no_grad():
+            for _ in range(max(1, warmup)):
+                out = body()
+            V, F = [int(x) for x in out[2].cpu()]
+            if V > out[0].shape[0] or F > out[1].shape[0]:
+                self.mc._ensure(0, int(V * 1.5) + 16, int(F * 1.5) + 16)
+                body()
+            torch.cuda.synchronize(dev)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = body()
+
+        def run():
+            graph.replay()
+            V, F = [int(x) for x in out[2].cpu()]           # D2H of the two counters (synchronises)
+            if V > out[0].shape[0] or F > out[1].shape[0]:
+                raise RuntimeError('mesh larger than the captured buffers (%d vertices, %d faces): re-capture' % (V, F))
+            return self._to_host(out[0][:V], out[1][:F])
+
+        run.graph = graph
+        return run
+
     def generate_mesh(self, inputs=None, c=None, tips=None, c_img_all=None, group=None, to_host=True, exchange=None):
         """inputs (1,T,3) point cloud -> encoder -> lattice logits -> mesh.
         tips = (positions (F,3) float64, features (F,c_dim) device tensor, touch (F,), radius)."""
