@@ -80,3 +80,39 @@ def test_generator_mesh_pipeline_256_properties():
     sv, sf = marching_cubes(sub, level)
     rv, rf, _ = omc.marching_cubes(sub.cpu().numpy(), level)
     assert np.array_equal(sf.cpu().numpy(), rf) and np.abs(sv.cpu().numpy() - rv).max() <= 1e-4
+
+
+def test_cuda_graph_paths_match_eager():
+    """capture_step / capture_generate replay == eager launches (same grid, same mesh)."""
+    from vtaco_b200.encoder import encoder_dict
+    from vtaco_b200.conv_onet.models import decoder_dict, ConvolutionalOccupancyNetwork
+    from vtaco_b200.conv_onet.generation import Generator3D
+    torch.manual_seed(0)
+    enc = encoder_dict['pointnet_local_pool'](dim=3, c_dim=32, padding=0.1, hidden_dim=32, plane_type='grid',
+                                              grid_resolution=32)
+    dec = decoder_dict['simple_local'](dim=3, c_dim=32, hidden_size=32)
+    with torch.no_grad():
+        for m in (enc, dec):
+            for b in m.blocks:
+                b.fc_1.weight.normal_(0, 0.1)
+    net = ConvolutionalOccupancyNetwork(dec, enc, device='cuda').eval()
+    gen = Generator3D(net, device='cuda', resolution0=16, with_img=True, padding=0.1, input_type='pointcloud')
+    rs = np.random.RandomState(3)
+    cloud = torch.from_numpy(rs.uniform(-0.5, 0.5, size=(1, 1500, 3)).astype(np.float32)).pin_memory()
+    tips = (rs.uniform(-0.3, 0.3, size=(3, 3)), torch.randn(3, 32, device='cuda'), [True, False, True], 0.05)
+    v0, f0 = gen.generate_mesh(inputs=cloud, tips=tips)
+    v0, f0 = v0.copy(), f0.copy()
+    with torch.no_grad():
+        c = net.encode_inputs(cloud.cuda())
+    graph, out = gen.capture_step(c, tips=tips)
+    graph.replay()
+    V, F = [int(x) for x in out[2].cpu()]
+    assert F == f0.shape[0] and np.array_equal(out[1][:F].cpu().numpy(), f0)
+    assert np.abs(out[0][:V].cpu().numpy() - v0).max() <= 1e-6
+    run = gen.capture_generate(cloud, tips=tips)
+    v1, f1 = run()
+    assert np.array_equal(f1, f0) and np.abs(v1 - v0).max() <= 1e-6
+    cloud.copy_(torch.from_numpy(rs.uniform(-0.4, 0.4, size=(1, 1500, 3)).astype(np.float32)))   # new scene, same graph
+    v2, f2 = run()
+    v3, f3 = gen.generate_mesh(inputs=cloud, tips=tips)
+    assert np.array_equal(f2, f3) and np.abs(v2 - v3).max() <= 1e-6 and not np.array_equal(f2.shape, ()) 
