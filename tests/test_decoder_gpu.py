@@ -119,7 +119,10 @@ def test_dense_matches_flat_and_golden(variant):
         flat = dec(pts[None], c)[0]
         key = torch.tensor([2 ** 31 - 1, -2 ** 31], dtype=torch.int32, device='cuda')
         dense = dec.forward_dense(c, nx, minmax_key=key)
-        assert torch.equal(dense.reshape(-1), flat)
+        if variant == 2:   # the tcgen05 kernel's dense mode interpolates separably (bilinear in x,y then z)
+            assert close(dense.reshape(-1).cpu().numpy(), flat.cpu().numpy()) < 1e-5
+        else:
+            assert torch.equal(dense.reshape(-1), flat)
         assert close(dense.reshape(-1).cpu().numpy(), g['logits']) < TOL
         from vtaco_b200 import _abi
         lo, hi = [_abi.lib().vtaco_key_to_float_host(int(k)) for k in key.cpu()]

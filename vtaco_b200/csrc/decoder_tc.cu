@@ -346,11 +346,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) decoder_tc_kernel(const __grid_
     int qb;
     bool valid;
     if (DENSE) {
-      long long t = tile;
-      const int bz = (int)(t % P.t_nbz); t /= P.t_nbz;   // bricks: 2 (x) x 2 (y) x 32 (z): a warp = one z-run,
-      const int by = (int)(t % P.t_nby); t /= P.t_nby;   // its 32 logits are one 128-byte store per destination
-      const int bx = (int)(t % P.t_nbx);
-      const int b = (int)(t / P.t_nbx);
+      unsigned t = (unsigned)tile;                        // n_tiles < 2^31 (checked at launch)
+      const int bz = (int)(t % (unsigned)P.t_nbz); t /= (unsigned)P.t_nbz;   // bricks: 2 (x) x 2 (y) x 32 (z): a warp = one
+      const int by = (int)(t % (unsigned)P.t_nby); t /= (unsigned)P.t_nby;   // z-run, its 32 logits are one 128-byte store
+      const int bx = (int)(t % (unsigned)P.t_nbx);
+      const int b = (int)(t / (unsigned)P.t_nbx);
       const int ix = P.x0 + bx * 2 + (tg >> 6), iy = by * 2 + ((tg >> 5) & 1), iz = bz * 32 + (tg & 31);
       valid = (ix < P.t_xend) && (iy < nx) && (iz < nx);
       px = __ldg(P.axis + min(ix, nx - 1));
@@ -369,9 +369,65 @@ __global__ void __launch_bounds__(kTcThreads, 1) decoder_tc_kernel(const __grid_
       oidx = nn;
     }
     if (!valid) oidx = 0;
+    TC_STAMP(13);  // tile start: coordinates loaded
 
-    // ---------------- gather: owner computes the taps, 8 lanes fetch them ----------------
+    // ---------------- gather ----------------
     if (P.has_c) {
+      float cv[32];
+      bool sep_done = false;
+      if (DENSE && P.grid && !P.nearest && !(P.plane[0] || P.plane[1] || P.plane[2])) {
+        // Separable dense gather: a warp is one z-run of 32 lattice points at fixed (x, y), so the
+        // (x,y)-bilinear part of the trilinear sample is shared by the whole run.  Reduce the 4
+        // (x,y) corners once per needed z-row into shared memory (4 z-rows x 8 channel quads per
+        // load step), then every thread lerps its two z-rows: ~40 tap loads per run instead of 256.
+        const int R = P.Rg;
+        const float tx = unnormalize(norm3d(px, P.nc), R), ty = unnormalize(norm3d(py, P.nc), R);
+        const float tz = unnormalize(norm3d(pz, P.nc), R);
+        const float flx = floorf(tx), fly = floorf(ty), flz = floorf(tz);
+        const int x0 = (int)flx, y0 = (int)fly, z0 = (int)flz;
+        const float fx1 = tx - flx, fx0 = (flx + 1.0f) - tx, fy1 = ty - fly, fy0 = (fly + 1.0f) - ty;
+        const float fz1 = tz - flz, fz0 = (flz + 1.0f) - tz;
+        const int zmin = __shfl_sync(kFull, z0, 0);
+        const int zmax = min(__shfl_sync(kFull, z0, 31) + 1, R - 1);
+        const int nz = zmax - zmin + 1;
+        if (nz <= 32) {   // warp-uniform
+          const int dx = (x0 + 1 < R) ? 8 : 0, dy = (y0 + 1 < R) ? R * 8 : 0;   // clamped corners carry weight 0
+          const float w00 = fx0 * fy0, w01 = fx1 * fy0, w10 = fx0 * fy1, w11 = fx1 * fy1;
+          const int zr = lane >> 3;
+          const float4* col = reinterpret_cast<const float4*>(P.grid) + (size_t)qb * R * R * R * 8 +
+                              ((size_t)y0 * R + x0) * 8 + sub;
+#pragma unroll 2
+          for (int zb = 0; zb < nz; zb += 4) {
+            const int zrow = zb + zr;
+            if (zrow < nz) {
+              const float4* p = col + (size_t)(zmin + zrow) * R * R * 8;
+              const float4 v00 = __ldg(p), v01 = __ldg(p + dx), v10 = __ldg(p + dy), v11 = __ldg(p + dy + dx);
+              float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+              a = f4_fma(w00, v00, a);
+              a = f4_fma(w01, v01, a);
+              a = f4_fma(w10, v10, a);
+              a = f4_fma(w11, v11, a);
+              *reinterpret_cast<float4*>(stage + zrow * kStageStride + 4 * sub) = a;
+            }
+          }
+          __syncwarp();
+          const float* r0 = stage + (z0 - zmin) * kStageStride;
+          const float* r1 = stage + (min(z0 + 1, R - 1) - zmin) * kStageStride;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 a = *reinterpret_cast<const float4*>(r0 + 4 * j);
+            const float4 b = *reinterpret_cast<const float4*>(r1 + 4 * j);
+            cv[4 * j + 0] = fmaf(b.x, fz1, a.x * fz0);
+            cv[4 * j + 1] = fmaf(b.y, fz1, a.y * fz0);
+            cv[4 * j + 2] = fmaf(b.z, fz1, a.z * fz0);
+            cv[4 * j + 3] = fmaf(b.w, fz1, a.w * fz0);
+          }
+          __syncwarp();
+          sep_done = true;
+        }
+      }
+      if (!sep_done) {
+      // generic gather: the owner computes the taps, 8 lanes fetch them
       TapInfo tv, tp0, tp1, tp2;
       if (P.grid) tv = tap_volume(norm3d(px, P.nc), norm3d(py, P.nc), norm3d(pz, P.nc), P.Rg, P.nearest);
       const bool planes = P.plane[0] || P.plane[1] || P.plane[2];
@@ -381,6 +437,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) decoder_tc_kernel(const __grid_
         if (P.plane[1]) tp1 = tap_plane(ux, uy, P.Rp, P.nearest);
         if (P.plane[2]) tp2 = tap_plane(uy, uz, P.Rp, P.nearest);
       }
+      TC_STAMP(14);  // taps computed
 #pragma unroll 2
       for (int it = 0; it < 8; ++it) {
         const int src = it * 4 + grp;
@@ -401,17 +458,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) decoder_tc_kernel(const __grid_
         *reinterpret_cast<float4*>(stage + src * kStageStride + 4 * sub) = c;
       }
       __syncwarp();
-      float cv[32];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float4 v = *reinterpret_cast<const float4*>(stage + lane * kStageStride + 4 * j);
         cv[4 * j] = v.x; cv[4 * j + 1] = v.y; cv[4 * j + 2] = v.z; cv[4 * j + 3] = v.w;
       }
       __syncwarp();
+      }  // generic gather
+      TC_STAMP(15);  // features of the thread's query in registers
       split_store(tC, cv);
       tc_wait_st();
       tc_fence_before();
       group_sync(g);
+      TC_STAMP(16);  // C in TMEM, group synced
       if (wg == (step & 3) && elect_one()) {     // step 0: D = C*Wc_0 + ones*bc_0
         tc_fence_after();
         issue_product(mD, mC, wsm, 0, P.tc_products);
@@ -444,6 +503,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) decoder_tc_kernel(const __grid_
         for (int j = 0; j < 32; ++j) net[j] += sTip[f * 32 + j];
       }
     }
+    TC_STAMP(17);    // fc_p / tips done
     uint32_t r[32];
     float x[32];
     if (P.has_c) {  // net += fc_c[0](c)
@@ -455,6 +515,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) decoder_tc_kernel(const __grid_
       for (int j = 0; j < 32; ++j) net[j] += __uint_as_float(r[j]);
     }
 
+    TC_STAMP(18);    // step 0 consumed
     // ---------------- residual blocks: 2 accumulation steps each ----------------
     for (int i = 0; i < nb; ++i) {
       TC_STAMP(1);   // ALU phase starts (accumulator already read)
@@ -484,9 +545,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) decoder_tc_kernel(const __grid_
 #pragma unroll
       for (int j = 0; j < 32; ++j) x[j] = fmaxf(__uint_as_float(r[j]), 0.f);
       split_store(tX, x);
+      TC_STAMP(8 + 16 * (i & 1));    // W1 step: operands computed (+16: warp 0 is this step's issuer)
       tc_wait_st();
       tc_fence_before();
       group_sync(g);
+      TC_STAMP(9 + 16 * (i & 1));
       if (wg == (step & 3) && elect_one()) {     // D = relu(h)*W1_i + ones*(b1_i + bc_{i+1}) [+ C*Wc_{i+1}]
         tc_fence_after();
         issue_product(mD, mX, wsm + (3 * i + 2) * 8192, 0, P.tc_products);
@@ -495,14 +558,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) decoder_tc_kernel(const __grid_
         tc_commit(bar);
       }
       ++step;
+      TC_STAMP(10 + 16 * (i & 1));
       mbar_wait(bar, ph); ph ^= 1;
+      TC_STAMP(11 + 16 * (i & 1));
       tc_fence_after();
       tmem_ld32(tD, r);
       tc_wait_ld();
+      TC_STAMP(12 + 16 * (i & 1));
 #pragma unroll
       for (int j = 0; j < 32; ++j) net[j] += __uint_as_float(r[j]);
     }
 
+    TC_STAMP(19);    // blocks done
     // ---------------- heads ----------------
     {
       const float* Wo = sSmall + 128;
@@ -555,6 +622,7 @@ int launch_decoder_tc(DecParams P, bool dense, const float* wtc, cudaStream_t st
   }
   const TcSmem L = tc_smem_layout(P.n_blocks);
   if (L.total > 227 * 1024) return VTACO_ERR_UNSUPPORTED;
+  if (P.n_tiles >= (1ll << 31)) return VTACO_ERR_UNSUPPORTED;
   static size_t configured[2][64] = {{0}};
   int dev = 0;
   VTACO_CUDA_CHECK(cudaGetDevice(&dev));
@@ -579,15 +647,16 @@ int launch_decoder_tc(DecParams P, bool dense, const float* wtc, cudaStream_t st
     VTACO_CUDA_CHECK(cudaStreamSynchronize(stream));
     VTACO_CUDA_CHECK(cudaMemcpy(h, trace, sizeof(h), cudaMemcpyDeviceToHost));
     cudaFree(trace);
-    double sum[8][8] = {{0}};
-    long long cnt[8][8] = {{0}};
+    static double sum[32][32];
+    static long long cnt[32][32];
+    for (int a = 0; a < 32; ++a) for (int b = 0; b < 32; ++b) { sum[a][b] = 0; cnt[a][b] = 0; }
     for (int i = 1; i < 4096 && h[i]; ++i) {
-      const int a = (int)(h[i - 1] >> 56) & 7, b = (int)(h[i] >> 56) & 7;
+      const int a = (int)(h[i - 1] >> 56) & 31, b = (int)(h[i] >> 56) & 31;
       const long long d = (h[i] & 0x00ffffffffffffffll) - (h[i - 1] & 0x00ffffffffffffffll);
       if (d >= 0 && d < 1000000) { sum[a][b] += (double)d; cnt[a][b]++; }
     }
-    for (int a = 0; a < 8; ++a)
-      for (int b = 0; b < 8; ++b)
+    for (int a = 0; a < 32; ++a)
+      for (int b = 0; b < 32; ++b)
         if (cnt[a][b]) fprintf(stderr, "[vtaco tc trace] %d -> %d : %8.0f cycles (n=%lld)\n", a, b, sum[a][b] / cnt[a][b], cnt[a][b]);
   }
   return VTACO_OK;
