@@ -435,7 +435,10 @@ extern "C" int vtaco_decoder_forward(const vtaco_decoder_args* a, void* stream) 
   if (P.n_tips > 0 && !a->tip_feat) return VTACO_ERR_INVALID_ARG;
   if (P.use_img && !a->c_img && P.n_tips == 0) { /* c_img == 0 everywhere */ }
   for (int f = 0; f < VTACO_MAX_TIPS; ++f) {
-    for (int d = 0; d < 3; ++d) P.tips[f][d] = f < P.n_tips ? a->tips[f][d] : 0.0;
+    for (int d = 0; d < 3; ++d) {
+      P.tips[f][d] = f < P.n_tips ? a->tips[f][d] : 0.0;
+      P.tipsf[f][d] = (float)P.tips[f][d];
+    }
     P.tip_touch[f] = f < P.n_tips ? a->tip_touch[f] : 0;
   }
   P.tip_radius = a->tip_radius;

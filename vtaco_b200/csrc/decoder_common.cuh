@@ -35,6 +35,7 @@ struct DecParams {
   int t_nbx, t_nby, t_nbz, t_xend;  // tcgen05 kernel, dense mode: 2x2x32 bricks and slab end row
   NormConst nc;
   double tips[VTACO_MAX_TIPS][3];
+  float tipsf[VTACO_MAX_TIPS][3];   // fp32 copies for the prefilter
   int tip_touch[VTACO_MAX_TIPS];
   double tip_radius;
   float tip_r2_hi;  // fp32 prefilter threshold (squared, padded)
@@ -134,7 +135,7 @@ __device__ __forceinline__ float4 sample_plane(const float4* __restrict__ pl, in
 __device__ __forceinline__ int tip_assign(const DecParams& P, float x, float y, float z) {
   bool near = false;
   for (int f = 0; f < P.n_tips; ++f) {
-    const float dx = x - (float)P.tips[f][0], dy = y - (float)P.tips[f][1], dz = z - (float)P.tips[f][2];
+    const float dx = x - P.tipsf[f][0], dy = y - P.tipsf[f][1], dz = z - P.tipsf[f][2];
     near |= (dx * dx + dy * dy + dz * dz) < P.tip_r2_hi;
   }
   if (!near) return -1;

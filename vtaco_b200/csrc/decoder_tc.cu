@@ -577,9 +577,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) decoder_tc_kernel(const __grid_
       float o = Wo[64], oc = Wo[65];
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        const float a = net[j] > 0.f ? net[j] : net[j] * slope;
-        o = fmaf(Wo[j], a, o);
-        oc = fmaf(Wo[32 + j], a, oc);
+        net[j] = net[j] > 0.f ? net[j] : net[j] * slope;
+        o = fmaf(Wo[j], net[j], o);
+      }
+      if (P.contact) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) oc = fmaf(Wo[32 + j], net[j], oc);
       }
       if (valid) {
         store_logit(P, oidx, o);
