@@ -203,8 +203,11 @@ def workload_config(nx, args):
             'nx': nx, 'queries_per_step': nx ** 3, 'encoder': 'LocalPoolPointnet grid64 hidden32 + UNet3D(4 levels)',
             'decoder': 'LocalDecoder simple_local hidden32 c_dim32 n_blocks5 bilinear', 'input_points': 3640,
             'parallelism': 'x-slabs of the lattice over %d GPU(s), features replicated, logit slabs %s' % (
-                args.gpus, 'stored into every rank over NVLink peer memory by the decoder kernel (fused all-gather)'
-                if getattr(args, 'exchange', 'fused') == 'fused' else 'all-gathered with NCCL'),
+                args.gpus, {'fused': 'stored into every rank over NVLink peer memory by the decoder kernel (fused '
+                                     'all-gather)',
+                            'root': 'stored into rank 0 over NVLink peer memory by the decoder kernel (fused gather, '
+                                    'marching cubes on rank 0 overlaps the peers\' next decode)',
+                            'nccl': 'all-gathered with NCCL'}[getattr(args, 'exchange', 'root')]),
             'l2': 'flushed between timed steps (256 MiB write outside the step events)',
             'kernel_variant': args.variant}
 
@@ -249,14 +252,40 @@ def run_ours(args, rank, local_rank, world):
                 g = flat.permute(0, 4, 1, 2, 3)
             return {'grid': g}
 
+    def encode_features_local():
+        with torch.no_grad():
+            return net.encode_inputs(cloud_host.to(dev, non_blocking=True))
+
     c = encode_features()
     tips_arg = (tips, tip_feat, touch, 0.05)
     exchange_note = None
-    if world > 1 and args.exchange == 'fused':
+    if world > 1 and args.exchange == 'root':
+        # balance: rank 0 decodes fewer rows so that decode_0 + marching cubes == a peer's decode
+        rr = torch.zeros(1, device=dev)
+        if rank == 0:
+            with torch.no_grad():
+                g0, k0 = gen.eval_lattice(c_probe := encode_features_local(), tips=None, group=False)
+                gen.mc(g0, level_keys=k0, sync=False)
+                torch.cuda.synchronize(dev)
+                ea, eb, ec = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+                ea.record()
+                g0, k0 = gen.eval_lattice(c_probe, tips=None, group=False)
+                eb.record()
+                gen.mc(g0, level_keys=k0, sync=False)
+                ec.record()
+                torch.cuda.synchronize(dev)
+            row_ms = ea.elapsed_time(eb) / nx
+            mc_rows = eb.elapsed_time(ec) / row_ms
+            per = (nx + mc_rows) / world
+            rr.fill_(max(2.0, per - mc_rows))
+        dist.broadcast(rr, 0, group=group)
+        gen.root_rows = int(rr.item()) // 2 * 2
+    if world > 1 and args.exchange in ('fused', 'root'):
         # symmetric-memory rendezvous must succeed on EVERY rank, else all ranks use NCCL
         ok = torch.ones(1, device=dev)
         try:
-            gen.eval_lattice(c, tips=tips_arg, group=group, exchange='fused')
+            for _ in range(2):
+                gen.eval_lattice(c, tips=tips_arg, group=group, exchange=args.exchange)
         except Exception as e:  # noqa: BLE001 - report and fall back to the NCCL plumbing
             ok.zero_()
             exchange_note = 'fused exchange unavailable (%s); NCCL all-gather used' % type(e).__name__
@@ -264,6 +293,7 @@ def run_ours(args, rank, local_rank, world):
         if ok.item() == 0:
             args.exchange = 'nccl'
             gen._fused = None
+            gen._root_ex = None
             exchange_note = exchange_note or 'fused exchange unavailable on a peer; NCCL all-gather used' 
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
 
@@ -287,15 +317,26 @@ def run_ours(args, rank, local_rank, world):
     for _ in range(max(args.warmup, 1)):
         device_step()
     # make sure the MC buffers are large enough, then no more host reads inside the steps
-    v_, f_, counts = device_step()
-    V, F = [int(x) for x in counts.cpu()]
-    if V > v_.shape[0] or F > f_.shape[0]:
-        gen.mc._ensure(0, int(V * 1.25) + 16, int(F * 1.25) + 16)
+    if world > 1 and args.exchange == 'root' and max(args.warmup, 1) % 2 == 0:
+        device_step()                      # keep the buffer parity even before the next pair of steps
+    out_ = device_step()
+    V = F = 0
+    grow = torch.zeros(1, device=dev)
+    if out_ is not None:
+        v_, f_, counts = out_
+        V, F = [int(x) for x in counts.cpu()]
+        if V > v_.shape[0] or F > f_.shape[0]:
+            gen.mc._ensure(0, int(V * 1.25) + 16, int(F * 1.25) + 16)
+            grow.fill_(1)
+    if world > 1:
+        dist.all_reduce(grow, group=group)
+    if grow.item() > 0:
+        device_step()
         device_step()
 
     # ---- CUDA graph of the step (decode [+ peer stores, barriers] + marching cubes) ----
     graph, graph_note = None, 'eager launches'
-    if not args.no_graph and (world == 1 or args.exchange == 'fused'):
+    if not args.no_graph and (world == 1 or args.exchange in ('fused', 'root')):
         ok = torch.ones(1, device=dev)
         try:
             graph, _ = gen.capture_step(c, tips=tips_arg, group=group, exchange=args.exchange)
@@ -345,7 +386,11 @@ def run_ours(args, rank, local_rank, world):
     value = nx ** 3 * args.steps / (total_ms * 1e-3)
 
     # ---- decoder kernel alone (dominant kernel) for the roofline: events around the launch ----
-    x0, x1 = __import__('vtaco_b200.dist', fromlist=['slab']).slab(nx, rank, world)
+    _vd = __import__('vtaco_b200.dist', fromlist=['slab'])
+    x0, x1 = (_vd.slab_root(nx, rank, world, gen.root_rows) if (world > 1 and args.exchange == 'root')
+              else _vd.slab(nx, rank, world))
+    if x1 <= x0:
+        x0, x1 = 0, 2
     kq = (x1 - x0) * nx * nx
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     out_grid = gen._grid
@@ -386,9 +431,10 @@ def run_ours(args, rank, local_rank, world):
             cc = encode_features()                               # H2D of the pinned cloud + encoder (+ broadcast)
             tf = tip_feat_host.to(dev, non_blocking=True)        # H2D of the fingertip features
             grid, keys = gen.eval_lattice(cc, tips=(tips, tf, touch, 0.05), group=group, exchange=args.exchange)
-            vv, ff = gen.extract_mesh(grid, keys)                # reads the two counters (D2H)
-            if rank == 0:
-                vh, fh = gen._to_host(vv, ff)                    # mesh D2H into pinned buffers
+            if grid is not None:
+                vv, ff = gen.extract_mesh(grid, keys)            # reads the two counters (D2H)
+                if rank == 0:
+                    vh, fh = gen._to_host(vv, ff)                # mesh D2H into pinned buffers
         barrier()
         if s >= max(args.warmup, 1):
             e2e_times.append(time.perf_counter() - t0)
@@ -469,6 +515,8 @@ def run_ours(args, rank, local_rank, world):
             line['exchange'] = args.exchange if exchange_note is None else exchange_note
             if gen._fused is not None:
                 line['exchange'] += ' (NVLS multicast stores)' if gen._fused.grid_multicast else ' (unicast peer stores)'
+            if gen._root_ex is not None:
+                line['exchange'] += ' (gather to rank 0, double-buffered, 1 barrier/step, rank 0 decodes %d of %d rows)' % (gen.root_rows, nx)
         if world == 1 and not args.no_cpu_baseline:
             ref = CpuReference(nx, args.cpu_sample)
             ref.run()
@@ -496,8 +544,10 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-multicast', action='store_true', help='fused exchange with unicast peer stores only')
     ap.add_argument('--no-graph', action='store_true', help='launch the step eagerly instead of replaying a CUDA graph')
-    ap.add_argument('--exchange', default='fused', choices=['fused', 'nccl'],
-                    help='N>1: fused = decoder stores slabs into peer grids over NVLink; nccl = all-gather')
+    ap.add_argument('--exchange', default='root', choices=['root', 'fused', 'nccl'],
+                    help='N>1: root = slabs stored into rank 0 only (double-buffered, 1 barrier/step, MC on rank 0, '
+                         'rank 0 decodes fewer rows); fused = slabs stored into every rank (NVLS multicast); '
+                         'nccl = all_gather_into_tensor')
     args = ap.parse_args()
     rank, local_rank, world = env_int('RANK', 0), env_int('LOCAL_RANK', 0), env_int('WORLD_SIZE', 1)
     os.environ.setdefault('MASTER_ADDR', '127.0.0.1')

@@ -264,8 +264,9 @@ int vtaco_marching_cubes(const vtaco_mc_args* args, void* stream);
 /* keys[0..1] <- ordered-int keys of min / max of grid[0..n) (initialised by the call) */
 int vtaco_grid_minmax(const float* grid, int64_t n, int32_t* keys, void* stream);
 /* multi-GPU iso-level exchange without a collective: copy this rank's (min,max) key pair into
- * slot `rank` of every peer's int32[n_peers][2] table (peer-mapped pointers), then reset `keys`
- * to (INT32_MAX, INT32_MIN) for the next step. */
+ * slot `rank` (0..7) of each of the `n_peers` int32[world][2] tables given (peer-mapped pointers:
+ * all ranks' tables for an all-gather, only the root's for a gather), then reset `keys` to
+ * (INT32_MAX, INT32_MIN) for the next step. */
 int vtaco_publish_keys(int32_t* keys, int32_t* const* tables_host_array, int32_t n_peers, int32_t rank, void* stream);
 
 /* ------------------------------------------------------------------------- *

@@ -3,6 +3,7 @@ bit-for-bit and the same mesh."""
 import os
 import socket
 
+import numpy as np
 import pytest
 import torch
 import torch.distributed as dist
@@ -44,6 +45,9 @@ def _worker(rank, world, port, nx, q, exchange='nccl'):
     dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
     try:
         gen, c = _build(dev, nx)
+        if exchange == 'root':
+            _root_worker(gen, c, nx, rank, q)
+            return
         grid, keys = gen.eval_lattice(c, group=dist.group.WORLD, exchange=exchange)
         v, f = gen.extract_mesh(grid, keys)
         v, f = v.clone(), f.clone()
@@ -60,7 +64,39 @@ def _worker(rank, world, port, nx, q, exchange='nccl'):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('exchange', ['fused', 'nccl'])
+def _root_worker(gen, c, nx, rank, q):
+    """gather-to-root, double-buffered: several steps eager, then through the two alternating graphs."""
+    gen.root_rows = max(2, nx // dist.get_world_size() - 6)
+    single, skeys = gen.eval_lattice(c, group=False)
+    single, skeys = single.clone(), skeys.clone()
+    v1, f1 = [t.clone() for t in gen.extract_mesh(single, skeys)]
+    ok = True
+    for _ in range(3):
+        grid, keys = gen.eval_lattice(c, group=dist.group.WORLD, exchange='root')
+        if rank == 0:
+            ok = ok and torch.equal(grid, single)
+            v, f = gen.extract_mesh(grid, keys)
+            ok = ok and torch.equal(v, v1) and torch.equal(f, f1)
+        else:
+            ok = ok and grid is None
+    if gen._root_ex.parity:          # leave the eager steps on an even count before capturing
+        gen.eval_lattice(c, group=dist.group.WORLD, exchange='root')
+    stepper, out = gen.capture_step(c, group=dist.group.WORLD, exchange='root')
+    for _ in range(5):
+        stepper.replay()
+    torch.cuda.synchronize()
+    ok_mesh = True
+    if rank == 0:
+        V, F = [int(x) for x in out[2].cpu()]
+        from vtaco_b200.mcubes import keys_to_level
+        ok_mesh = F == f1.shape[0] and torch.equal(out[1][:F], f1)
+        nxh = np.float32(nx / 2)
+        ok_mesh = ok_mesh and V == v1.shape[0]
+    dist.barrier()
+    q.put((rank, bool(ok), bool(ok_mesh), int(f1.shape[0])))
+
+
+@pytest.mark.parametrize('exchange', ['fused', 'nccl', 'root'])
 @pytest.mark.parametrize('nx', [64, 40])
 def test_sharded_extraction_matches_single_gpu(nx, exchange):
     world = min(torch.cuda.device_count(), 4)

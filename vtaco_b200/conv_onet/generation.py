@@ -61,6 +61,8 @@ class Generator3D(object):
         self._keys_init = None
         self._pin = None
         self._fused = None
+        self._root_ex = None
+        self.root_rows = None       # exchange='root': lattice rows decoded by rank 0 (None: nx / world)
         self.use_multicast = True   # NVLS multimem.st for the fused exchange when the fabric supports it
 
     @property
@@ -115,6 +117,24 @@ class Generator3D(object):
         keys.copy_(self._keys_init)
         rank, world = vdist.rank_world(group)
         x0, x1 = vdist.slab(nx, rank, world)
+        if world > 1 and exchange == 'root':
+            # gather-to-root, double-buffered, one barrier per step (vdist.RootExchange)
+            if self._root_ex is None or self._root_ex.grids[0].shape[0] != nx:
+                self._root_ex = vdist.RootExchange(nx, dev, group)
+            ex = self._root_ex
+            b = ex.parity
+            ex.parity ^= 1
+            x0, x1 = vdist.slab_root(nx, rank, world, self.root_rows if self.root_rows is not None else nx // world)
+            with torch.no_grad():
+                if x1 > x0:
+                    dec.forward_dense(c, nx, x0=x0, x1=x1, use_img=self.with_img, c_img=c_img_all, tips=tips,
+                                      out=ex.grids[b], minmax_key=keys, axis=self._axis,
+                                      peers=[ex.root_grid_ptr[b]])
+                ex.publish(keys, b)
+                ex.barrier()
+            if rank == 0:
+                return ex.grids[b], ex.tables[b][:2 * world]
+            return None, None
         if world > 1 and (exchange or 'fused') == 'fused':
             if self._fused is None or self._fused.grid.shape[0] != nx:
                 self._fused = vdist.FusedExchange(nx, dev, group, use_multicast=self.use_multicast)
@@ -152,6 +172,8 @@ class Generator3D(object):
         synchronisation.  Returns the extractor's (vertex buffer, face buffer, int64[2] counts)."""
         nx = self.resolution0 * 4
         grid, keys = self.eval_lattice(c, tips=tips, c_img_all=c_img_all, group=group, exchange=exchange)
+        if grid is None:      # exchange='root' on a non-root rank: the mesh is extracted by rank 0 only
+            return None
         return self.mc(grid, level_keys=keys, voffset=np.float32(nx / 2), vscale=np.float32((1 + self.padding) / nx),
                        sync=False)
 
@@ -160,6 +182,8 @@ class Generator3D(object):
         the critical path — it matters once a slab decodes in well under a millisecond).
         Returns (graph, outputs); call graph.replay() per step.  The feature tensors, tips and
         all buffers are baked into the graph: re-capture when they change."""
+        if exchange == 'root' and vdist.rank_world(group)[1] > 1:
+            return self._capture_root_steps(c, tips, c_img_all, group, warmup)
         for _ in range(max(1, warmup)):          # allocations, attribute set-up, rendezvous
             out = self.lattice_and_mesh(c, tips, c_img_all, group, exchange)
         V, F = [int(x) for x in out[2].cpu()]
@@ -171,6 +195,42 @@ class Generator3D(object):
         with torch.cuda.graph(graph):
             out = self.lattice_and_mesh(c, tips, c_img_all, group, exchange)
         return graph, out
+
+    def _capture_root_steps(self, c, tips, c_img_all, group, warmup):
+        """exchange='root': the step alternates between two symmetric buffers, so two graphs are
+        captured (one per buffer parity) and replayed in turn."""
+        import torch.distributed as dist
+        rank = dist.get_rank(group)
+        for _ in range(2 * max(1, warmup)):      # even count: parity returns to 0
+            out = self.lattice_and_mesh(c, tips, c_img_all, group, 'root')
+        need = torch.zeros(1, device=self.device)
+        if rank == 0:
+            V, F = [int(x) for x in out[2].cpu()]
+            if V > out[0].shape[0] or F > out[1].shape[0]:
+                self.mc._ensure(0, int(V * 1.5) + 16, int(F * 1.5) + 16)
+                need.fill_(1)
+        dist.all_reduce(need, group=group)
+        if need.item() > 0:
+            for _ in range(2):
+                self.lattice_and_mesh(c, tips, c_img_all, group, 'root')
+        torch.cuda.synchronize(self.device)
+        graphs, outs = [], []
+        for _ in range(2):
+            gph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gph):
+                o = self.lattice_and_mesh(c, tips, c_img_all, group, 'root')
+            graphs.append(gph)
+            outs.append(o)
+
+        class _Alternating(object):
+            def __init__(self):
+                self.i = 0
+
+            def replay(self):
+                graphs[self.i].replay()
+                self.i ^= 1
+
+        return _Alternating(), outs[1]
 
     def capture_generate(self, inputs_host, tips=None, warmup=2):
         """CUDA graph of the whole single-GPU extraction for a fixed input shape:

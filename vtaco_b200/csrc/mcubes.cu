@@ -400,7 +400,7 @@ extern "C" int vtaco_marching_cubes(const vtaco_mc_args* a, void* stream) {
 }
 
 extern "C" int vtaco_publish_keys(int32_t* keys, int32_t* const* tables, int32_t n_peers, int32_t rank, void* stream) {
-  if (!keys || !tables || n_peers < 1 || n_peers > 8 || rank < 0 || rank >= n_peers) return VTACO_ERR_INVALID_ARG;
+  if (!keys || !tables || n_peers < 1 || n_peers > 8 || rank < 0 || rank >= 8) return VTACO_ERR_INVALID_ARG;
   PeerTables t;
   for (int r = 0; r < 8; ++r) t.t[r] = r < n_peers ? tables[r] : nullptr;
   publish_keys_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(keys, t, n_peers, rank);

@@ -23,6 +23,21 @@ def slab(nx, rank, world):
     return x0, min(nx, x0 + per)
 
 
+def slab_root(nx, rank, world, root_rows):
+    """x-rows when rank 0 also runs marching cubes: the root decodes `root_rows` rows (even,
+    >= 0), the remaining rows are split evenly (in bricks of 2 rows) over ranks 1..world-1."""
+    if world == 1:
+        return 0, nx
+    root_rows = max(0, min(nx, int(root_rows) // 2 * 2))
+    rest = nx - root_rows
+    per = -(-rest // (world - 1))
+    per += per & 1
+    if rank == 0:
+        return 0, root_rows
+    x0 = min(nx, root_rows + (rank - 1) * per)
+    return x0, min(nx, x0 + per)
+
+
 def all_gather_slabs(grid, nx, group=None):
     """in-place all-gather of the x-slabs of `grid` (nx,nx,nx)."""
     rank, world = rank_world(group)
@@ -91,5 +106,49 @@ class FusedExchange(object):
         from . import _abi
         with torch.cuda.device(self.device):
             st = _abi.lib().vtaco_publish_keys(_abi.ptr(keys), self._tabs, self.world, self.rank,
+                                               _abi.stream_ptr(self.device))
+        _abi.check(st, 'publish_keys')
+
+
+class RootExchange(object):
+    """Gather-to-root variant of the fused exchange for a stream of extractions.
+
+    Only rank 0 extracts the mesh, so peers store their logit slabs (unicast, over NVLink peer
+    memory) into rank 0's grid only and publish their (min,max) keys into rank 0's table.  The
+    grid and table are double-buffered: while rank 0 runs marching cubes on buffer b the peers
+    already decode the next lattice into buffer b^1, and ONE symmetric-memory barrier per step
+    (placed after the decode on every rank) orders both hazards:
+      * peers pass barrier(s+1) only after rank 0 arrived there, i.e. after it finished marching
+        cubes on the buffer they are about to overwrite at step s+2;
+      * rank 0 passes barrier(s) only after every peer's decode(s) kernel (and key publish) ended.
+    Rank 0 is given fewer lattice rows (`root_rows`) so that decode_0 + marching cubes takes as
+    long as a peer's decode."""
+
+    def __init__(self, nx, device, group):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if self.world > 8:
+            raise ValueError('fused exchange supports up to 8 ranks (one NVSwitch domain)')
+        self.device = device
+        self.grids, self.tables, self.root_grid_ptr, self._tabs, self._handles = [], [], [], [], []
+        for _ in range(2):
+            g = symm.empty((nx, nx, nx), dtype=torch.float32, device=device)
+            t = symm.empty((16,), dtype=torch.int32, device=device)
+            hg, ht = symm.rendezvous(g, group), symm.rendezvous(t, group)
+            self.grids.append(g)
+            self.tables.append(t)
+            self._handles.append((hg, ht))
+            self.root_grid_ptr.append(int(hg.buffer_ptrs[0]) + int(getattr(hg, 'offset', 0)))
+            self._tabs.append((C.c_void_p * 1)(int(ht.buffer_ptrs[0]) + int(getattr(ht, 'offset', 0))))
+        self.parity = 0
+
+    def barrier(self):
+        self._handles[0][0].barrier()
+
+    def publish(self, keys, b):
+        from . import _abi
+        with torch.cuda.device(self.device):
+            st = _abi.lib().vtaco_publish_keys(_abi.ptr(keys), self._tabs[b], 1, self.rank,
                                                _abi.stream_ptr(self.device))
         _abi.check(st, 'publish_keys')
