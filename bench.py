@@ -205,8 +205,8 @@ def workload_config(nx, args):
             'parallelism': 'x-slabs of the lattice over %d GPU(s), features replicated, logit slabs %s' % (
                 args.gpus, {'fused': 'stored into every rank over NVLink peer memory by the decoder kernel (fused '
                                      'all-gather)',
-                            'root': 'stored into rank 0 over NVLink peer memory by the decoder kernel (fused gather, '
-                                    'marching cubes on rank 0 overlaps the peers\' next decode)',
+                            'root': 'pushed into rank 0 by one bulk NVLink peer copy per rank (double-buffered; marching '
+                                    'cubes on rank 0 overlaps the peers\' next decode)',
                             'nccl': 'all-gathered with NCCL'}[getattr(args, 'exchange', 'root')]),
             'l2': 'flushed between timed steps (256 MiB write outside the step events)',
             'kernel_variant': args.variant}
@@ -545,8 +545,8 @@ def main():
     ap.add_argument('--no-multicast', action='store_true', help='fused exchange with unicast peer stores only')
     ap.add_argument('--no-graph', action='store_true', help='launch the step eagerly instead of replaying a CUDA graph')
     ap.add_argument('--exchange', default='root', choices=['root', 'fused', 'nccl'],
-                    help='N>1: root = slabs stored into rank 0 only (double-buffered, 1 barrier/step, MC on rank 0, '
-                         'rank 0 decodes fewer rows); fused = slabs stored into every rank (NVLS multicast); '
+                    help='N>1: root = slabs pushed into rank 0 only by bulk peer copies (double-buffered, 1 barrier/step, MC on '
+                         'rank 0, rank 0 decodes fewer rows); fused = decoder stores slabs into every rank (NVLS multicast); '
                          'nccl = all_gather_into_tensor')
     args = ap.parse_args()
     rank, local_rank, world = env_int('RANK', 0), env_int('LOCAL_RANK', 0), env_int('WORLD_SIZE', 1)

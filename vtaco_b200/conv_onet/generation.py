@@ -127,9 +127,13 @@ class Generator3D(object):
             x0, x1 = vdist.slab_root(nx, rank, world, self.root_rows if self.root_rows is not None else nx // world)
             with torch.no_grad():
                 if x1 > x0:
+                    # rank 0 decodes straight into buffer b; a peer decodes into its local grid and
+                    # pushes the slab with one bulk P2P copy (same stream: ordered before the barrier)
+                    local = ex.grids[b] if rank == 0 else self._grid
                     dec.forward_dense(c, nx, x0=x0, x1=x1, use_img=self.with_img, c_img=c_img_all, tips=tips,
-                                      out=ex.grids[b], minmax_key=keys, axis=self._axis,
-                                      peers=[ex.root_grid_ptr[b]])
+                                      out=local, minmax_key=keys, axis=self._axis)
+                    if rank != 0:
+                        ex.root_view[b][x0:x1].copy_(local[x0:x1], non_blocking=True)
                 ex.publish(keys, b)
                 ex.barrier()
             if rank == 0:
