@@ -544,12 +544,15 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-multicast', action='store_true', help='fused exchange with unicast peer stores only')
     ap.add_argument('--no-graph', action='store_true', help='launch the step eagerly instead of replaying a CUDA graph')
-    ap.add_argument('--exchange', default='root', choices=['root', 'fused', 'nccl'],
-                    help='N>1: root = slabs pushed into rank 0 only by bulk peer copies (double-buffered, 1 barrier/step, MC on '
+    ap.add_argument('--exchange', default='auto', choices=['auto', 'root', 'fused', 'nccl'],
+                    help='N>1: auto = root for N <= 4, fused for N = 8 (measured best, profiles/r01_scaling_exchanges.json); '
+                         'root = slabs pushed into rank 0 only by bulk peer copies (double-buffered, 1 barrier/step, MC on '
                          'rank 0, rank 0 decodes fewer rows); fused = decoder stores slabs into every rank (NVLS multicast); '
                          'nccl = all_gather_into_tensor')
     args = ap.parse_args()
     rank, local_rank, world = env_int('RANK', 0), env_int('LOCAL_RANK', 0), env_int('WORLD_SIZE', 1)
+    if args.exchange == 'auto':
+        args.exchange = 'root' if world <= 4 else 'fused'
     os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
     if args.impl == 'reference':
         run_reference(args, rank, world)
