@@ -278,6 +278,10 @@ int vtaco_publish_keys(int32_t* keys, int32_t* const* tables_host_array, int32_t
  * ------------------------------------------------------------------------- */
 int vtaco_group_norm(const float* x, float* y, const float* gamma, const float* beta, int32_t N, int32_t C,
                      int32_t G, int64_t S, double eps, double* stats_ws, void* stream);
+/* same for channels-last storage [N][S][C] (torch channels_last_3d); returns VTACO_ERR_UNSUPPORTED
+ * unless C % 4 == 0, (C/G) % 4 == 0 and (C/4) divides 256 — callers then use vtaco_group_norm. */
+int vtaco_group_norm_cl(const float* x, float* y, const float* gamma, const float* beta, int32_t N, int32_t C,
+                        int32_t G, int64_t S, double eps, double* stats_ws, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * (4) self-measured FP32 FMA peak (roofline denominator of the decoder).

@@ -177,4 +177,7 @@ def test_group_norm_kernel(shape, groups):
         x = torch.randn(*shape, device='cuda') * 3 + 1.5
         ref = torch.nn.functional.group_norm(x, groups, gn.weight, gn.bias, gn.eps)
         got = gn(x)
+        xcl = x.contiguous(memory_format=torch.channels_last_3d)
+        got_cl = gn(xcl)                      # channels-last kernel where the shape allows it
     assert close(got.cpu().numpy(), ref.cpu().numpy()) < 1e-5
+    assert got_cl.shape == ref.shape and close(got_cl.contiguous().cpu().numpy(), ref.cpu().numpy()) < 1e-5

@@ -16,12 +16,22 @@ class GroupNorm(nn.GroupNorm):
         if (x.is_cuda and x.dtype == torch.float32 and x.dim() >= 3
                 and not (torch.is_grad_enabled() and (x.requires_grad or self.weight.requires_grad))):
             from .. import _abi
-            import ctypes as C
+            N, Cc = x.shape[0], x.shape[1]
+            S = x[0, 0].numel()
+            ws = torch.empty(2 * N * self.num_groups, dtype=torch.float64, device=x.device)
+            perm = (0,) + tuple(range(2, x.dim())) + (1,)
+            cpg = Cc // self.num_groups
+            if (x.dim() in (4, 5) and x.permute(*perm).is_contiguous() and Cc % 4 == 0 and cpg % 4 == 0
+                    and 256 % (Cc // 4) == 0 and self.num_groups <= 64):
+                y = torch.empty_like(x)          # keeps the channels-last strides
+                with torch.cuda.device(x.device):
+                    st = _abi.lib().vtaco_group_norm_cl(_abi.ptr(x), _abi.ptr(y), _abi.ptr(self.weight),
+                                                        _abi.ptr(self.bias), N, Cc, self.num_groups, S, float(self.eps),
+                                                        _abi.ptr(ws), _abi.stream_ptr(x.device))
+                _abi.check(st, 'group_norm_cl')
+                return y
             xc = x.contiguous()
             y = torch.empty_like(xc)
-            N, Cc = xc.shape[0], xc.shape[1]
-            S = xc[0, 0].numel()
-            ws = torch.empty(2 * N * self.num_groups, dtype=torch.float64, device=x.device)
             with torch.cuda.device(x.device):
                 st = _abi.lib().vtaco_group_norm(_abi.ptr(xc), _abi.ptr(y), _abi.ptr(self.weight), _abi.ptr(self.bias),
                                                  N, Cc, self.num_groups, S, float(self.eps), _abi.ptr(ws),
