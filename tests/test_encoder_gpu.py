@@ -178,6 +178,7 @@ def test_group_norm_kernel(shape, groups):
         ref = torch.nn.functional.group_norm(x, groups, gn.weight, gn.bias, gn.eps)
         got = gn(x)
         xcl = x.contiguous(memory_format=torch.channels_last_3d)
+        gn.prefer_channels_last = True
         got_cl = gn(xcl)                      # channels-last kernel where the shape allows it
     assert close(got.cpu().numpy(), ref.cpu().numpy()) < 1e-5
     assert got_cl.shape == ref.shape and close(got_cl.contiguous().cpu().numpy(), ref.cpu().numpy()) < 1e-5

@@ -111,7 +111,6 @@ class LocalPoolPointnet(nn.Module):
         self.division = 'cuda'
         self._pack_cache = None
         self._ws = None
-        self._unet3d_cl = False
 
     # ------------------------------------------------------------------ helpers
     def _keys_in(self):
@@ -229,11 +228,6 @@ class LocalPoolPointnet(nn.Module):
         out = {}
         for k, t in fea.items():
             if k == 'grid':
-                if self.unet3d is not None and t.is_cuda and not self._unet3d_cl:
-                    # run the 3-D U-Net in channels-last end to end: no cuDNN layout conversions,
-                    # and its output is already in the layout the decoder gathers from
-                    self.unet3d = self.unet3d.to(memory_format=torch.channels_last_3d)
-                    self._unet3d_cl = True
                 out[k] = self.unet3d(t) if self.unet3d is not None else t
             else:
                 out[k] = self.unet(t) if self.unet is not None else t

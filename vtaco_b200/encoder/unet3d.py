@@ -11,6 +11,7 @@ import torch.nn.functional as F
 class GroupNorm(nn.GroupNorm):
     """nn.GroupNorm with the same parameters / state_dict; on CUDA fp32 inference it runs
     vtaco_group_norm (chip-wide reduction) instead of ATen's one-block-per-group kernel."""
+    prefer_channels_last = False
 
     def forward(self, x):
         if (x.is_cuda and x.dtype == torch.float32 and x.dim() >= 3
@@ -21,7 +22,9 @@ class GroupNorm(nn.GroupNorm):
             ws = torch.empty(2 * N * self.num_groups, dtype=torch.float64, device=x.device)
             perm = (0,) + tuple(range(2, x.dim())) + (1,)
             cpg = Cc // self.num_groups
-            if (x.dim() in (4, 5) and x.permute(*perm).is_contiguous() and Cc % 4 == 0 and cpg % 4 == 0
+            # channels-last kernel only on request: measured on B200, cuDNN's fp32 Conv3d is not faster in
+            # channels_last_3d at these sizes (UNet3D 64^3 x 32: e2e 5.27 ms contiguous vs 5.48 ms channels-last)
+            if (self.prefer_channels_last and x.dim() in (4, 5) and x.permute(*perm).is_contiguous() and Cc % 4 == 0 and cpg % 4 == 0
                     and 256 % (Cc // 4) == 0 and self.num_groups <= 64):
                 y = torch.empty_like(x)          # keeps the channels-last strides
                 with torch.cuda.device(x.device):
