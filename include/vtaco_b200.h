@@ -165,6 +165,48 @@ int vtaco_decoder_forward(const vtaco_decoder_args* args, void* stream);
  * (decoder.py:55-68).  Uses the feature / padding / div_mode / sample_mode fields of
  * `args`; p: [B][N][3]; out: [B][32][N] (sum over the present keys). */
 int vtaco_sample_features(const vtaco_decoder_args* args, const float* p, int64_t N, float* out, void* stream);
+/* ------------------------------------------------------------------------- *
+ * (4b) Backward of LocalDecoder.forward / forward_img / forward_contact — what autograd
+ * computes when src/conv_onet/training.py:79,617 trains through decoder.py:71-161
+ * (SURVEY §8f-2).  Flat queries only.  The forward pass is recomputed in fp32 inside the
+ * kernel (the forward kernels save nothing).  Gradient w.r.t. the query points p is not
+ * produced (the reference never asks for it).
+ *
+ * d_params: flat fp32 buffer of VTACO_DEC_PACKED_FLOATS(n_blocks) floats, ACCUMULATED into
+ * (zero it first): same offsets as the packed forward weights, but each matrix in nn.Linear's
+ * native [out][in] orientation — fc_p.weight [32][3] at OFF_WP, fc_p.bias at OFF_BP,
+ * fc_p_img.weight[:, :3] [32][3] at OFF_WPI, fc_p_img.bias at OFF_BPI, fc_p_img.weight[:, 3:]
+ * [32][32] at OFF_WIMG; per block at OFF_BLOCKS + i*BLOCK_STRIDE: fc_c[i].weight, .bias (+1024),
+ * fc_0.weight (+1056), .bias (+2080), fc_1.weight (+2112), .bias (+3136); tail: fc_out.weight
+ * [32], fc_out_contact.weight [32] (+32), fc_out.bias (+64), fc_out_contact.bias (+65).
+ * d_grid / d_plane[k]: channels-last gradients [B][R..][32], ACCUMULATED into with vector
+ * atomics (NULL = not wanted).  d_c_img: [B][N][32], overwritten (NULL = not wanted).
+ * workspace: vtaco_decoder_backward_workspace_bytes(B*N, n_blocks) bytes of device memory. */
+typedef struct vtaco_decoder_bwd_args {
+  const float* p;          /* [B][N][3] */
+  int32_t B;
+  int64_t N;
+  const float* grid;       /* channels-last features as in vtaco_decoder_args, or NULL */
+  const float* plane[3];   /* xz, xy, yz */
+  int32_t reso_grid, reso_plane;
+  double padding;
+  int32_t div_mode, sample_mode;
+  const float* weights;    /* packed forward weights (VTACO_DEC_* layout) */
+  int32_t n_blocks, leaky;
+  int32_t use_img;         /* 1: net0 = fc_p_img(cat(p, c_img)) */
+  const float* c_img;      /* [B][N][32] or NULL */
+  const float* dlogits;    /* [B][N] dL/dlogits, or NULL (then dcontact must be given) */
+  const float* dcontact;   /* [B][N] dL/dcontact (forward_contact) or NULL */
+  void* workspace;
+  size_t workspace_bytes;
+  float* d_params;
+  float* d_grid;
+  float* d_plane[3];
+  float* d_c_img;
+} vtaco_decoder_bwd_args;
+size_t vtaco_decoder_backward_workspace_bytes(int64_t total_queries, int32_t n_blocks);
+int vtaco_decoder_backward(const vtaco_decoder_bwd_args* args, void* stream);
+
 /* decode an ordered-int key written by the decoder / encoder kernels back to float (host helper) */
 float vtaco_key_to_float_host(int32_t key);
 

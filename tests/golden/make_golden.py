@@ -260,10 +260,62 @@ def main():
     g.update(sd_np(u3, 'u3.'))
     np.savez_compressed(os.path.join(HERE, 'unets.npz'), **g)
 
+    make_grads(common, encoder_dict, models, generation)
     for f in sorted(os.listdir(HERE)):
         if f.endswith('.npz'):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, 'KiB')
 
 
+def make_grads(common, encoder_dict, models, generation):
+    """G6: gradients torch autograd produces through the reference LocalDecoder
+    (what training.py:79,617 back-propagates): loss = sum(logits * r) [+ sum(contact * r2)]."""
+    B, N, Rg, Rp = 2, 320, 8, 16
+    edge = np.array([[0.55, -0.55, 0.0], [0.7, -0.7, 0.55], [0.549999, -0.549999, 0.275]], dtype=np.float32)
+    p = rs_uniform(121, -0.6, 0.6, B, N, 3)
+    p[0, :edge.shape[0]] = edge
+    feats = {'grid': rs_randn(131, B, 32, Rg, Rg, Rg), 'xz': rs_randn(132, B, 32, Rp, Rp),
+             'xy': rs_randn(133, B, 32, Rp, Rp), 'yz': rs_randn(134, B, 32, Rp, Rp)}
+    c_img = rs_randn(135, B, N, 32)
+    c_img[:, ::3] = 0.0
+    r, r2 = rs_randn(136, B, N), rs_randn(137, B, N)
+    g = {'p': p, 'c_img': c_img, 'r': r, 'r2': r2, 'feat_seeds': np.array([131, 132, 133, 134]),
+         'feat_shapes': np.array([Rg, Rp])}
+    cases = (('img_grid_relu', False, ['grid'], 'img', 'bilinear'),
+             ('fwd_tri_leaky', True, ['xz', 'xy', 'yz'], 'fwd', 'bilinear'),
+             ('con_all_relu', False, ['grid', 'xz', 'xy', 'yz'], 'con', 'bilinear'),
+             ('img_all_nearest', False, ['grid', 'xz'], 'img', 'nearest'))
+    for tag, leaky, keys, mode, smode in cases:
+        dec = models.decoder_dict['simple_local'](dim=3, c_dim=32, padding=0.1, with_contact=(mode == 'con'),
+                                                  sample_mode=smode, hidden_size=32, leaky=leaky)
+        randomise(dec, 111)
+        dec.train()
+        cp = {k: torch.from_numpy(feats[k]).requires_grad_(True) for k in keys}
+        tci = torch.from_numpy(c_img).requires_grad_(True)
+        tp = torch.from_numpy(p)
+        if mode == 'img':
+            loss = (dec.forward_img(tp, cp, tci) * torch.from_numpy(r)).sum()
+        elif mode == 'con':
+            o, oc_ = dec.forward_contact(tp, cp)
+            loss = (o * torch.from_numpy(r)).sum() + (oc_ * torch.from_numpy(r2)).sum()
+        else:
+            loss = (dec(tp, cp) * torch.from_numpy(r)).sum()
+        loss.backward()
+        g[tag + '.loss'] = np.array(loss.item())
+        for k, v in sd_np(dec, tag + '.w.').items():
+            g[k] = v
+        for n, prm in dec.named_parameters():
+            if prm.grad is not None:
+                g['%s.dw.%s' % (tag, n)] = prm.grad.numpy()
+        for k in keys:
+            g['%s.dfeat.%s' % (tag, k)] = cp[k].grad.numpy()
+        if mode == 'img':
+            g[tag + '.dc_img'] = tci.grad.numpy()
+    np.savez_compressed(os.path.join(HERE, 'decoder_grads.npz'), **g)
+
+
 if __name__ == '__main__':
-    main()
+    if sys.argv[1:] == ['grads']:
+        torch.set_num_threads(4)
+        make_grads(*import_reference())
+    else:
+        main()

@@ -92,3 +92,51 @@ def test_cuda_division_flips_few_indices():
     a = oc.coordinate2index(oc.normalize_3d_coordinate(p, 0.1, False), 64, '3d')
     b = oc.coordinate2index(oc.normalize_3d_coordinate(p, 0.1, True), 64, '3d')
     assert (a != b).sum().item() < 50
+
+
+GRAD_CASES = (('img_grid_relu', False, ['grid'], 'img', 'bilinear'),
+              ('fwd_tri_leaky', True, ['xz', 'xy', 'yz'], 'forward', 'bilinear'),
+              ('con_all_relu', False, ['grid', 'xz', 'xy', 'yz'], 'contact', 'bilinear'),
+              ('img_all_nearest', False, ['grid', 'xz'], 'img', 'nearest'))
+
+
+def oracle_decoder_grads(g, tag, leaky, keys, mode, smode, device='cpu'):
+    """torch autograd through the oracle restatement: the checker for vtaco_decoder_backward."""
+    W = {k[len(tag) + 3:]: torch.from_numpy(v).to(device).requires_grad_(True)
+         for k, v in g.items() if k.startswith(tag + '.w.')}
+    feats = decoder_feats(g, device)
+    cp = {k: feats[k].clone().requires_grad_(True) for k in keys}
+    p = torch.from_numpy(g['p']).to(device)
+    c_img = torch.from_numpy(g['c_img']).to(device).requires_grad_(True)
+    r, r2 = torch.from_numpy(g['r']).to(device), torch.from_numpy(g['r2']).to(device)
+    if mode == 'contact':
+        o, c_ = oc.decoder_forward(p, cp, W, 'contact', leaky=leaky, sample_mode=smode)
+        loss = (o * r).sum() + (c_ * r2).sum()
+    else:
+        o = oc.decoder_forward(p, cp, W, mode, c_img=c_img if mode == 'img' else None, leaky=leaky, sample_mode=smode)
+        loss = (o * r).sum()
+    loss.backward()
+    out = {'dw.' + k: v.grad for k, v in W.items() if v.grad is not None}
+    out.update({'dfeat.' + k: v.grad for k, v in cp.items()})
+    if mode == 'img':
+        out['dc_img'] = c_img.grad
+    return loss.item(), out
+
+
+def rel_fro(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+@pytest.mark.parametrize('case', GRAD_CASES, ids=[c[0] for c in GRAD_CASES])
+def test_decoder_gradients_match_reference(case):
+    """autograd through the oracle == autograd through the reference modules (decoder_grads.npz)."""
+    tag, leaky, keys, mode, smode = case
+    g = load('decoder_grads.npz')
+    loss, grads = oracle_decoder_grads(g, tag, leaky, keys, mode, smode)
+    assert abs(loss - float(g[tag + '.loss'])) <= 1e-4 * max(1.0, abs(float(g[tag + '.loss'])))
+    n = 0
+    for k, v in grads.items():
+        assert rel_fro(v.numpy(), g['%s.%s' % (tag, k)]) < 1e-5, k
+        n += 1
+    assert n == sum(1 for k in g if k.startswith(tag + '.d'))

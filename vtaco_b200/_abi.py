@@ -43,6 +43,19 @@ class DecoderArgs(C.Structure):
     ]
 
 
+class DecoderBwdArgs(C.Structure):
+    _fields_ = [
+        ('p', C.c_void_p), ('B', C.c_int32), ('N', C.c_int64),
+        ('grid', C.c_void_p), ('plane', C.c_void_p * 3),
+        ('reso_grid', C.c_int32), ('reso_plane', C.c_int32),
+        ('padding', C.c_double), ('div_mode', C.c_int32), ('sample_mode', C.c_int32),
+        ('weights', C.c_void_p), ('n_blocks', C.c_int32), ('leaky', C.c_int32), ('use_img', C.c_int32),
+        ('c_img', C.c_void_p), ('dlogits', C.c_void_p), ('dcontact', C.c_void_p),
+        ('workspace', C.c_void_p), ('workspace_bytes', C.c_size_t),
+        ('d_params', C.c_void_p), ('d_grid', C.c_void_p), ('d_plane', C.c_void_p * 3), ('d_c_img', C.c_void_p),
+    ]
+
+
 class McArgs(C.Structure):
     _fields_ = [
         ('grid', C.c_void_p), ('nx', C.c_int32), ('ny', C.c_int32), ('nz', C.c_int32),
@@ -78,6 +91,9 @@ def lib():
     L.vtaco_relayout_cf.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p]
     L.vtaco_decoder_forward.argtypes = [C.POINTER(DecoderArgs), C.c_void_p]
     L.vtaco_sample_features.argtypes = [C.POINTER(DecoderArgs), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    L.vtaco_decoder_backward.argtypes = [C.POINTER(DecoderBwdArgs), C.c_void_p]
+    L.vtaco_decoder_backward_workspace_bytes.restype = C.c_size_t
+    L.vtaco_decoder_backward_workspace_bytes.argtypes = [C.c_int64, C.c_int32]
     L.vtaco_key_to_float_host.restype = C.c_float
     L.vtaco_key_to_float_host.argtypes = [C.c_int32]
     L.vtaco_fp32_peak.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double), C.c_void_p]
@@ -126,9 +142,13 @@ def require_cuda(t, name):
         raise TypeError('vtaco_b200: %s must be float32, got %s' % (name, t.dtype))
 
 
+def wants_grad(*tensors):
+    return torch.is_grad_enabled() and any(torch.is_tensor(t) and t.requires_grad for t in tensors)
+
+
 def forbid_autograd(*tensors):
-    """The kernels are forward-only (backward is SURVEY §8f 'next')."""
-    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
+    """For the entry points that have no backward kernel (SURVEY §8f-2 covers the decoder)."""
+    if wants_grad(*tensors):
         raise NotImplementedError(
-            'vtaco_b200 kernels are forward-only: call under torch.no_grad() '
-            '(backward kernels are not implemented yet)')
+            'vtaco_b200: this kernel is forward-only: call it under torch.no_grad() '
+            '(backward kernels exist for LocalDecoder.forward / forward_img / forward_contact)')

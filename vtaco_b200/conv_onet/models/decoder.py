@@ -3,7 +3,9 @@
 Same constructor arguments, parameter names / shapes (state_dict compatible) and
 method names.  All arithmetic runs in ONE fused CUDA kernel
 (vtaco_decoder_forward, vtaco_b200/csrc/decoder.cu); there is no PyTorch or CPU
-fallback.  Extra, non-reference entry point: `forward_dense` evaluates the
+fallback.  With grad enabled, forward / forward_img / forward_contact are autograd
+nodes whose backward is vtaco_decoder_backward (csrc/decoder_bwd.cu): gradients for
+all parameters, the c_plane feature tensors and c_img.  Extra, non-reference entry point: `forward_dense` evaluates the
 extraction lattice of Generator3D without materialising the query tensor.
 """
 import ctypes as C
@@ -36,6 +38,50 @@ def _as_channels_last(t):
         st = _abi.lib().vtaco_relayout_cl(_abi.ptr(src), _abi.ptr(dst), B, Cc, S, _abi.stream_ptr(t.device))
     _abi.check(st, 'relayout_cl')
     return dst
+
+
+class _DecodeFn(torch.autograd.Function):
+    """autograd bridge: forward = vtaco_decoder_forward, backward = vtaco_decoder_backward
+    (the role torch autograd plays for the reference decoder in training.py:79,617)."""
+
+    @staticmethod
+    def forward(ctx, mod, use_img, contact, keys, names, p, c_img, *tensors):
+        nk = len(keys)
+        feats = tensors[:nk]
+        out, out_c, keep = mod._decode_impl(p, dict(zip(keys, feats)), use_img, c_img, contact)
+        ctx.mod, ctx.use_img, ctx.contact, ctx.keys, ctx.names = mod, use_img, contact, keys, names
+        ctx.keep = keep  # channels-last feature copies and packed weights as the forward launch saw them
+        ctx.save_for_backward(p, c_img)
+        return (out, out_c) if contact else out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, *grads):
+        mod, keys, names = ctx.mod, ctx.keys, ctx.names
+        p, c_img = ctx.saved_tensors
+        nk = len(keys)
+        none_head = (None,) * 6   # mod, use_img, contact, keys, names, p
+        if ctx.keep is None:      # empty batch
+            return none_head + (None,) * (1 + nk + len(names))
+        cl, w = ctx.keep[0], ctx.keep[1]
+        dlogits = grads[0]
+        dcontact = grads[1] if ctx.contact and len(grads) > 1 else None
+        if dlogits is None and dcontact is None:
+            return none_head + (None,) * (1 + nk + len(names))
+        need = ctx.needs_input_grad
+        need_feat = {k: need[7 + i] for i, k in enumerate(keys)}
+        flat, d_feat, d_cimg = mod._decode_backward(p, c_img, cl, w, ctx.use_img, dlogits, dcontact,
+                                                    need_feat, need[6])
+        pg = mod._unpack_param_grads(flat, ctx.use_img, ctx.contact)
+        gfeat = []
+        for k in keys:
+            t = d_feat.get(k)
+            if t is None:
+                gfeat.append(None)
+            else:  # channels-last storage, channels-first shape
+                gfeat.append(t.permute(0, 4, 1, 2, 3) if k == 'grid' else t.permute(0, 3, 1, 2))
+        gpar = [pg.get(n) if need[7 + nk + i] else None for i, n in enumerate(names)]
+        return none_head + (d_cimg,) + tuple(gfeat) + tuple(gpar)
 
 
 class LocalDecoder(nn.Module):
@@ -245,13 +291,25 @@ class LocalDecoder(nn.Module):
         _abi.require_cuda(p, 'p')
         if p.dim() != 3 or p.size(2) != 3:
             raise ValueError('p must have shape (B, N, 3)')
-        _abi.forbid_autograd(p, c_img, *self.parameters(), *[t for t in c_plane.values() if torch.is_tensor(t)])
+        feats = {k: t for k, t in c_plane.items() if k in ('grid',) + _PLANES and torch.is_tensor(t)}
+        if _abi.wants_grad(p, c_img, *self.parameters(), *feats.values()):
+            if p.requires_grad:
+                raise NotImplementedError('vtaco_b200: no gradient w.r.t. the query points p '
+                                          '(the reference never differentiates through them); detach p')
+            names, params = zip(*self.named_parameters())
+            return _DecodeFn.apply(self, bool(use_img), bool(contact), tuple(feats.keys()), names, p, c_img,
+                                   *feats.values(), *params)
+        out, out_c, _ = self._decode_impl(p, c_plane, use_img, c_img, contact)
+        return (out, out_c) if contact else out
+
+    def _decode_impl(self, p, c_plane, use_img=False, c_img=None, contact=False):
+        """Launch the forward kernel; returns (logits, contact|None, tensors the launch reads)."""
         B, N = p.shape[0], p.shape[1]
         pc = p.contiguous()
         out = torch.empty((B, N), dtype=torch.float32, device=p.device)
         out_c = torch.empty((B, N), dtype=torch.float32, device=p.device) if contact else None
         if N == 0 or B == 0:
-            return (out, out_c) if contact else out
+            return out, out_c, None
         a, keep = self._base_args(c_plane, B)
         a.p = pc.data_ptr()
         a.N = N
@@ -272,7 +330,101 @@ class LocalDecoder(nn.Module):
                 raise AttributeError("'LocalDecoder' object has no attribute 'fc_out_contact'")
             a.contact = out_c.data_ptr()
         self._run(a, p.device)
-        return (out, out_c) if contact else out
+        return out, out_c, keep
+
+    # ------------------------------------------------------------------ backward
+    _BWD_MAX_QUERIES = 1 << 19   # per launch: 23 workspace rows of 128 B per query (1.5 GB)
+
+    def _decode_backward(self, p, c_img, cl, w, use_img, dlogits, dcontact, need_feat, need_cimg):
+        """vtaco_decoder_backward: returns (flat parameter gradients in the packed native layout,
+        dict of channels-last feature gradients, d_c_img | None)."""
+        dev = p.device
+        B, N = p.shape[0], p.shape[1]
+        nb = self.n_blocks
+        L = _abi.lib()
+        d_params = torch.zeros(_abi.dec_packed_floats(nb), dtype=torch.float32, device=dev)
+        d_feat = {k: torch.zeros_like(t) for k, t in cl.items() if need_feat.get(k)}
+        has_cimg = bool(use_img and self.c_dim and c_img is not None)
+        d_cimg = torch.empty((B, N, 32), dtype=torch.float32, device=dev) if (need_cimg and has_cimg) else None
+        pc = p.contiguous()
+        cic = c_img.contiguous() if has_cimg else None
+        dl = dlogits.contiguous() if dlogits is not None else None
+        dc = dcontact.contiguous() if dcontact is not None else None
+        if B * N <= self._BWD_MAX_QUERIES:
+            pieces = [(0, B, 0, N)]
+        else:
+            pieces = [(b, 1, n0, min(self._BWD_MAX_QUERIES, N - n0))
+                      for b in range(B) for n0 in range(0, N, self._BWD_MAX_QUERIES)]
+        qmax = max(nbatch * n for _, nbatch, _, n in pieces)
+        ws_bytes = L.vtaco_decoder_backward_workspace_bytes(qmax, nb)
+        ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev)
+        for b0, nbatch, n0, n in pieces:
+            a = _abi.DecoderBwdArgs()
+            whole = (nbatch == B and n == N)
+            # a piece inside one sample is passed as B=1 with every per-sample pointer advanced
+            psl = pc if whole else pc[b0, n0:n0 + n]
+            a.p = psl.data_ptr()
+            a.B, a.N = nbatch, n
+            if 'grid' in cl:
+                a.grid = cl['grid'][b0].data_ptr()
+                a.reso_grid = cl['grid'].size(1)
+                if 'grid' in d_feat:
+                    a.d_grid = d_feat['grid'][b0].data_ptr()
+            for i, k in enumerate(_PLANES):
+                if k in cl:
+                    a.plane[i] = cl[k][b0].data_ptr()
+                    a.reso_plane = cl[k].size(1)
+                    if k in d_feat:
+                        a.d_plane[i] = d_feat[k][b0].data_ptr()
+            a.padding = float(self.padding)
+            a.div_mode = _div_mode(self.division)
+            a.sample_mode = _abi.SAMPLE[self.sample_mode]
+            a.weights = w.data_ptr()
+            a.n_blocks, a.leaky, a.use_img = nb, int(self.leaky), int(use_img)
+            if has_cimg:
+                a.c_img = (cic if whole else cic[b0, n0:n0 + n]).data_ptr()
+                if d_cimg is not None:
+                    a.d_c_img = (d_cimg if whole else d_cimg[b0, n0:n0 + n]).data_ptr()
+            if dl is not None:
+                a.dlogits = (dl if whole else dl[b0, n0:n0 + n]).data_ptr()
+            if dc is not None:
+                a.dcontact = (dc if whole else dc[b0, n0:n0 + n]).data_ptr()
+            a.workspace, a.workspace_bytes = ws.data_ptr(), ws_bytes
+            a.d_params = d_params.data_ptr()
+            with torch.cuda.device(dev):
+                st = L.vtaco_decoder_backward(C.byref(a), _abi.stream_ptr(dev))
+            _abi.check(st, 'decoder_backward')
+        return d_params, d_feat, d_cimg
+
+    def _unpack_param_grads(self, flat, use_img, contact):
+        """name -> gradient views of the flat buffer written by vtaco_decoder_backward."""
+        g = {}
+        nb = self.n_blocks
+        if use_img:
+            parts = [flat[_abi.DEC_OFF_WPI:_abi.DEC_OFF_WPI + 96].view(32, 3)]
+            if self.c_dim:
+                parts.append(flat[_abi.DEC_OFF_WIMG:_abi.DEC_OFF_WIMG + 1024].view(32, 32))
+            g['fc_p_img.weight'] = torch.cat(parts, 1)
+            g['fc_p_img.bias'] = flat[_abi.DEC_OFF_BPI:_abi.DEC_OFF_BPI + 32]
+        else:
+            g['fc_p.weight'] = flat[0:96].view(32, 3)
+            g['fc_p.bias'] = flat[_abi.DEC_OFF_BP:_abi.DEC_OFF_BP + 32]
+        for i in range(nb):
+            o = _abi.DEC_OFF_BLOCKS + i * _abi.DEC_BLOCK_STRIDE
+            if self.c_dim:
+                g['fc_c.%d.weight' % i] = flat[o:o + 1024].view(32, 32)
+                g['fc_c.%d.bias' % i] = flat[o + 1024:o + 1056]
+            g['blocks.%d.fc_0.weight' % i] = flat[o + 1056:o + 2080].view(32, 32)
+            g['blocks.%d.fc_0.bias' % i] = flat[o + 2080:o + 2112]
+            g['blocks.%d.fc_1.weight' % i] = flat[o + 2112:o + 3136].view(32, 32)
+            g['blocks.%d.fc_1.bias' % i] = flat[o + 3136:o + 3168]
+        o = _abi.DEC_OFF_BLOCKS + nb * _abi.DEC_BLOCK_STRIDE
+        g['fc_out.weight'] = flat[o:o + 32].view(1, 32)
+        g['fc_out.bias'] = flat[o + 64:o + 65]
+        if contact:
+            g['fc_out_contact.weight'] = flat[o + 32:o + 64].view(1, 32)
+            g['fc_out_contact.bias'] = flat[o + 65:o + 66]
+        return g
 
     # ------------------------------------------------------------------ reference API
     def forward(self, p, c_plane, **kwargs):
