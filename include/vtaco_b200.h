@@ -256,6 +256,38 @@ typedef struct vtaco_encoder_args {
 int64_t vtaco_encoder_workspace_bytes(int32_t B, int64_t T, int32_t n_keys, const int32_t* kind, const int32_t* reso);
 int vtaco_encoder_pointnet(const vtaco_encoder_args* args, void* stream);
 
+/* (5b) Backward of the PointNet part: what autograd computes through
+ * src/encoder/pointnet.py:135-172 when training.py trains the encoder.  Given the gradients of
+ * the scatter_mean feature tensors (channels-last, [B][cells][32] per key, NULL = no gradient
+ * for that key; same key order as vtaco_encoder_args) it ACCUMULATES parameter gradients into
+ * d_params (zero it first): the packed layout of the forward weights with every matrix in
+ * nn.Linear's native [out][in] orientation — fc_pos.weight [64][3] at 0, fc_pos.bias at 192;
+ * block i at 256 + 5184*i: fc_0.weight [32][64] (+0), fc_0.bias (+2048), fc_1.weight [32][32]
+ * (+2080), fc_1.bias (+3104), shortcut.weight [32][64] (+3136); fc_c.weight [32][32] at
+ * 256 + 5184*n_blocks, fc_c.bias (+1024).  The forward is recomputed inside (nothing is saved
+ * by vtaco_encoder_pointnet).  scatter_max routes a cell's gradient to the lowest-index point
+ * among exact ties (torch_scatter: one arg-max point, unspecified which). */
+typedef struct vtaco_encoder_bwd_args {
+  const float* p;          /* [B][T][3] */
+  int32_t B;
+  int64_t T;
+  double padding;
+  int32_t div_mode;
+  int32_t n_keys;
+  int32_t kind[4];
+  int32_t reso[4];
+  int32_t pool_mean;
+  int32_t n_blocks;
+  const float* weights;    /* packed forward weights */
+  void* workspace;
+  int64_t workspace_bytes; /* >= vtaco_encoder_backward_workspace_bytes(...) */
+  const float* d_out_cl[4];
+  float* d_params;
+} vtaco_encoder_bwd_args;
+int64_t vtaco_encoder_backward_workspace_bytes(int32_t B, int64_t T, int32_t n_keys, const int32_t* kind,
+                                               const int32_t* reso, int32_t n_blocks);
+int vtaco_encoder_backward(const vtaco_encoder_bwd_args* args, void* stream);
+
 /* pool_local stand-alone (src/encoder/pointnet.py:116-132): feat [B][T][32] row-major,
  * idx32_host_array[k] = device pointer to key k's [B*T] int32 cell indices, cells[k] = R^2 | R^3;
  * out [B][T][32] = sum over keys of (per-cell max | mean gathered back to the points). */

@@ -261,6 +261,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, 'unets.npz'), **g)
 
     make_grads(common, encoder_dict, models, generation)
+    make_encoder_grads(common, encoder_dict, models, generation)
     for f in sorted(os.listdir(HERE)):
         if f.endswith('.npz'):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, 'KiB')
@@ -313,9 +314,44 @@ def make_grads(common, encoder_dict, models, generation):
     np.savez_compressed(os.path.join(HERE, 'decoder_grads.npz'), **g)
 
 
+ENC_GRAD_CASES = (('grid_max', dict(plane_type='grid', grid_resolution=16)),
+                  ('tri_max', dict(plane_type=['xz', 'xy', 'yz'], plane_resolution=16)),
+                  ('all_mean', dict(plane_type=['xz', 'xy', 'yz', 'grid'], plane_resolution=8, grid_resolution=8,
+                                    scatter_type='mean')))
+
+
+def make_encoder_grads(common, encoder_dict, models, generation):
+    """G7: parameter gradients torch autograd produces through the reference LocalPoolPointnet
+    (PointNet part, no UNet): loss = sum_key sum(fea[key] * r_key).  torch_scatter is shimmed by
+    the oracle's restatement (see install_shims), everything else is the reference's code."""
+    cloud0, _ = synthetic_cloud(151, 260, 20)
+    cloud1, _ = synthetic_cloud(152, 260, 20)
+    p = np.stack([cloud0, cloud1])
+    g = {'p': p}
+    for tag, kw in ENC_GRAD_CASES:
+        enc = encoder_dict['pointnet_local_pool'](dim=3, c_dim=32, padding=0.1, hidden_dim=32, **kw)
+        randomise(enc, 141)
+        enc.train()
+        fea = enc(torch.from_numpy(p))
+        loss = 0
+        for i, (k, v) in enumerate(fea.items()):
+            r = rs_randn(160 + i, *v.shape)
+            loss = loss + (v * torch.from_numpy(r)).sum()
+        loss.backward()
+        g[tag + '.loss'] = np.array(loss.item())
+        g[tag + '.keys'] = np.array(list(fea.keys()))
+        for k, v in sd_np(enc, tag + '.w.').items():
+            g[k] = v
+        for n, prm in enc.named_parameters():
+            g['%s.dw.%s' % (tag, n)] = prm.grad.numpy()
+    np.savez_compressed(os.path.join(HERE, 'encoder_grads.npz'), **g)
+
+
 if __name__ == '__main__':
     if sys.argv[1:] == ['grads']:
         torch.set_num_threads(4)
-        make_grads(*import_reference())
+        ref = import_reference()
+        make_grads(*ref)
+        make_encoder_grads(*ref)
     else:
         main()

@@ -140,3 +140,31 @@ def test_decoder_gradients_match_reference(case):
         assert rel_fro(v.numpy(), g['%s.%s' % (tag, k)]) < 1e-5, k
         n += 1
     assert n == sum(1 for k in g if k.startswith(tag + '.d'))
+
+
+ENC_GRAD_CASES = (('grid_max', dict(plane_type='grid', reso_grid=16)),
+                  ('tri_max', dict(plane_type=['xz', 'xy', 'yz'], reso_plane=16)),
+                  ('all_mean', dict(plane_type=['xz', 'xy', 'yz', 'grid'], reso_plane=8, reso_grid=8,
+                                    scatter_type='mean')))
+
+
+def oracle_encoder_grads(g, tag, kw):
+    """torch autograd through the oracle's PointNet restatement: the checker for vtaco_encoder_backward."""
+    W = {k[len(tag) + 3:]: torch.from_numpy(v).requires_grad_(True) for k, v in g.items() if k.startswith(tag + '.w.')}
+    fea = oc.encoder_pointnet(torch.from_numpy(g['p']), W, **kw)
+    loss = 0
+    for i, (k, v) in enumerate(fea.items()):
+        loss = loss + (v * torch.from_numpy(rs_randn(160 + i, *v.shape))).sum()
+    loss.backward()
+    return loss.item(), list(fea.keys()), {k: v.grad for k, v in W.items()}
+
+
+@pytest.mark.parametrize('case', ENC_GRAD_CASES, ids=[c[0] for c in ENC_GRAD_CASES])
+def test_encoder_gradients_match_reference(case):
+    tag, kw = case
+    g = load('encoder_grads.npz')
+    loss, keys, grads = oracle_encoder_grads(g, tag, kw)
+    assert keys == [str(k) for k in g[tag + '.keys']]
+    assert abs(loss - float(g[tag + '.loss'])) <= 1e-4 * max(1.0, abs(float(g[tag + '.loss'])))
+    for k, v in grads.items():
+        assert rel_fro(v.numpy(), g['%s.dw.%s' % (tag, k)]) < 1e-5, k

@@ -52,6 +52,32 @@ def main():
             t_fb = timeit(step)
             res[mode] = {'fwd_ms': t_f, 'fwd_bwd_ms': t_fb, 'Mqueries_per_s_fwd_bwd': B * N / t_fb / 1e3}
         out[tag] = res
+    # PointNet part of the encoder (no UNet): B clouds of 3640 points into a 64^3 grid
+    from vtaco_b200.encoder import encoder_dict
+    for B, T, tag in ((8, 3640, 'pointnet_B8_T3640_grid64'), (32, 3000, 'pointnet_B32_T3000_tri32')):
+        kw = dict(plane_type='grid', grid_resolution=64) if 'grid' in tag else \
+            dict(plane_type=['xz', 'xy', 'yz'], plane_resolution=32)
+        enc = encoder_dict['pointnet_local_pool'](dim=3, c_dim=32, padding=0.1, hidden_dim=32, **kw).cuda().train()
+        with torch.no_grad():
+            for n, prm in enc.named_parameters():
+                if n.endswith('fc_1.weight'):
+                    prm.normal_(0, 0.1)
+        cloud = torch.rand(B, T, 3, device='cuda') - 0.5
+        with torch.no_grad():
+            fea = enc(cloud)
+        rs = {k: torch.randn_like(v) for k, v in fea.items()}
+
+        def efwd():
+            return enc(cloud)
+
+        def estep():
+            enc.zero_grad(set_to_none=True)
+            torch.autograd.backward(list(efwd().values()), list(rs.values()))
+
+        with torch.no_grad():
+            t_f = timeit(efwd)
+        t_fb = timeit(estep)
+        out[tag] = {'fwd_ms': t_f, 'fwd_bwd_ms': t_fb, 'Mpoints_per_s_fwd_bwd': B * T / t_fb / 1e3}
     print(json.dumps(out, indent=1))
     with open('gpurun_out/bwd_probe.json', 'w') as f:
         json.dump(out, f, indent=1)

@@ -19,10 +19,11 @@
 // as 32-bit masks.  Per-layer activations A and output gradients G are written as
 // [slot][query][32] rows (128-byte rows, STG.128) for kernel 2; dc is scattered into the
 // channels-last feature gradients with 16-byte vector atomics (red.global.add.v4.f32).
-// Kernel 2 (decoder_bwd_weights_kernel): dW = G^T A, one CTA per (matrix, query chunk),
+// Kernel 2 (linear_wgrad_kernel, wgrad.cuh): dW = G^T A, one CTA per (matrix, query chunk),
 // 128-query tiles staged in shared memory, 32x32 outer-product accumulators spread over 256
 // threads (4 per thread), one atomicAdd per element and CTA; db = column sums of G.
 #include "decoder_common.cuh"
+#include "wgrad.cuh"
 #include <algorithm>
 
 namespace vtaco {
@@ -341,70 +342,6 @@ __global__ void __launch_bounds__(kBT, 1) decoder_bwd_query_kernel(const __grid_
   }
 }
 
-// ---------------------------------------------------------------------------------------
-// dW[o][k] += sum_q G[q][o] * A[q][k];  db[o] += sum_q G[q][o]
-// ---------------------------------------------------------------------------------------
-constexpr int kMaxProd = 3 * kMaxBlocks + 5;
-constexpr int kWTile = 128;
-
-struct WProd {
-  const float* G;   // rows of g_ld floats, n_out used
-  const float* A;   // rows of a_ld floats, n_in used
-  float* dW;        // [n_out][w_ld] (+ column offset applied by the host)
-  float* db;        // [n_out] or NULL
-  int g_ld, n_out, a_ld, n_in, w_ld;
-};
-struct WParams {
-  WProd prod[kMaxProd];
-  long long Q;
-  int q_per_cta;
-};
-
-__global__ void __launch_bounds__(256) decoder_bwd_weights_kernel(const __grid_constant__ WParams P) {
-  __shared__ __align__(16) float sG[kWTile][32];
-  __shared__ __align__(16) float sA[kWTile][32];
-  const WProd& pr = P.prod[blockIdx.y];
-  const long long q_begin = (long long)blockIdx.x * P.q_per_cta;
-  const long long q_end = min(P.Q, q_begin + P.q_per_cta);
-  const int o = threadIdx.x >> 3, k4 = threadIdx.x & 7;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  float bsum = 0.f;
-  for (long long q0 = q_begin; q0 < q_end; q0 += kWTile) {
-    const int nq = (int)min((long long)kWTile, q_end - q0);
-    __syncthreads();
-#pragma unroll 4
-    for (int idx = threadIdx.x; idx < kWTile * 32; idx += 256) {
-      const int r = idx >> 5, c = idx & 31;
-      float g = 0.f, a = 0.f;
-      if (r < nq) {
-        if (c < pr.n_out) g = __ldg(pr.G + (size_t)(q0 + r) * pr.g_ld + c);
-        if (c < pr.n_in) a = __ldg(pr.A + (size_t)(q0 + r) * pr.a_ld + c);
-      }
-      sG[r][c] = g;
-      sA[r][c] = a;
-    }
-    __syncthreads();
-#pragma unroll 8
-    for (int r = 0; r < kWTile; ++r) {   // rows beyond nq are zero
-      const float g = sG[r][o];
-      const float4 a = *reinterpret_cast<const float4*>(&sA[r][4 * k4]);
-      acc[0] = fmaf(g, a.x, acc[0]);
-      acc[1] = fmaf(g, a.y, acc[1]);
-      acc[2] = fmaf(g, a.z, acc[2]);
-      acc[3] = fmaf(g, a.w, acc[3]);
-      bsum += g;
-    }
-  }
-  if (o < pr.n_out) {
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int k = 4 * k4 + e;
-      if (k < pr.n_in) atomicAdd(pr.dW + (size_t)o * pr.w_ld + k, acc[e]);
-    }
-    if (pr.db && k4 == 0) atomicAdd(pr.db + o, bsum);
-  }
-}
-
 }  // namespace vtaco
 
 using namespace vtaco;
@@ -469,6 +406,7 @@ extern "C" int vtaco_decoder_backward(const vtaco_decoder_bwd_args* a, void* str
                  float* db) {
     WProd& r = W.prod[np++];
     r.G = G; r.g_ld = g_ld; r.n_out = n_out; r.A = A; r.a_ld = a_ld; r.n_in = n_in; r.dW = dW; r.w_ld = w_ld; r.db = db;
+    r.a_relu = 0;
   };
   const float* g0 = slot(slot_gm(nb, 0));
   if (a->use_img) {
@@ -486,14 +424,5 @@ extern "C" int vtaco_decoder_backward(const vtaco_decoder_bwd_args* a, void* str
   float* dt = dp + VTACO_DEC_OFF_BLOCKS + nb * VTACO_DEC_BLOCK_STRIDE;
   if (a->dlogits) add(a->dlogits, 1, 1, slot(slot_aout(nb)), 32, 32, dt, 32, dt + 64);
   if (a->dcontact) add(a->dcontact, 1, 1, slot(slot_aout(nb)), 32, 32, dt + 32, 32, dt + 65);
-  const long long want = (long long)num_sms() * 8 / np + 1;           // ~8 CTAs per SM over all products
-  long long chunks = std::min<long long>((Q + kWTile - 1) / kWTile, want);
-  if (chunks < 1) chunks = 1;
-  long long per = (Q + chunks - 1) / chunks;
-  per = (per + kWTile - 1) / kWTile * kWTile;
-  W.q_per_cta = (int)per;
-  chunks = (Q + per - 1) / per;
-  decoder_bwd_weights_kernel<<<dim3((unsigned)chunks, (unsigned)np), 256, 0, stream>>>(W);
-  VTACO_LAUNCH_CHECK();
-  return VTACO_OK;
+  return launch_wgrad(W, np, stream);
 }

@@ -19,6 +19,7 @@
 //    (order not fixed -> tolerance), divided by the cell count, written once per occupied
 //    cell into a zero-filled channels-last tensor.
 #include "common.cuh"
+#include "wgrad.cuh"
 #include <math_constants.h>
 #include <cmath>
 
@@ -557,6 +558,8 @@ extern "C" int vtaco_scatter_mean(const float* c, const int32_t* idx32, int32_t 
   VTACO_LAUNCH_CHECK();
   return VTACO_OK;
 }
+
+#include "encoder_bwd.inl"
 
 // ---------------------------------------------------------------------------------------
 // GroupNorm over contiguous NC[D]HW fp32 tensors (the 'g' of UNet3D's 'gcr' layers, reference

@@ -10,6 +10,9 @@ The returned tensors are in torch's channels_last / channels_last_3d memory
 format: same shape and values as the reference's, and the layout the fused
 decoder gathers from without a copy.
 
+With grad enabled the PointNet part is an autograd node whose backward is
+vtaco_encoder_backward (csrc/encoder_bwd.inl); the UNets train through torch autograd.
+
 Out of scope (raises): the MANO hand head (`out_mano=True`), reference
 pointnet.py:175-198 — a different model.
 """
@@ -39,9 +42,24 @@ class EncoderArgs(C.Structure):
     ]
 
 
+class EncoderBwdArgs(C.Structure):
+    _fields_ = [
+        ('p', C.c_void_p), ('B', C.c_int32), ('T', C.c_int64),
+        ('padding', C.c_double), ('div_mode', C.c_int32),
+        ('n_keys', C.c_int32), ('kind', C.c_int32 * 4), ('reso', C.c_int32 * 4),
+        ('pool_mean', C.c_int32), ('n_blocks', C.c_int32),
+        ('weights', C.c_void_p), ('workspace', C.c_void_p), ('workspace_bytes', C.c_int64),
+        ('d_out_cl', C.c_void_p * 4), ('d_params', C.c_void_p),
+    ]
+
+
 def _bind(L):
     if getattr(L, '_enc_bound', False):
         return
+    L.vtaco_encoder_backward_workspace_bytes.restype = C.c_int64
+    L.vtaco_encoder_backward_workspace_bytes.argtypes = [C.c_int32, C.c_int64, C.c_int32, C.POINTER(C.c_int32),
+                                                         C.POINTER(C.c_int32), C.c_int32]
+    L.vtaco_encoder_backward.argtypes = [C.POINTER(EncoderBwdArgs), C.c_void_p]
     L.vtaco_encoder_workspace_bytes.restype = C.c_int64
     L.vtaco_encoder_workspace_bytes.argtypes = [C.c_int32, C.c_int64, C.c_int32, C.POINTER(C.c_int32),
                                                 C.POINTER(C.c_int32)]
@@ -59,6 +77,32 @@ def _lib():
     L = _abi.lib()
     _bind(L)
     return L
+
+
+class _PointnetFn(torch.autograd.Function):
+    """autograd bridge of the PointNet part: forward = vtaco_encoder_pointnet, backward =
+    vtaco_encoder_backward (what torch autograd does for the reference when training.py trains
+    the encoder through pointnet.py:135-172)."""
+
+    @staticmethod
+    def forward(ctx, mod, p, names, *params):
+        fea = mod._pointnet_impl(p)
+        ctx.mod, ctx.names, ctx.keys = mod, names, tuple(fea.keys())
+        ctx.w = mod._packed_weights()   # the weights this forward saw
+        ctx.save_for_backward(p)
+        return tuple(fea[k] for k in ctx.keys)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, *grads):
+        (p,) = ctx.saved_tensors
+        mod = ctx.mod
+        if all(g is None for g in grads) or p.numel() == 0:
+            return (None, None, None) + (None,) * len(ctx.names)
+        flat = mod._pointnet_backward(p, ctx.w, dict(zip(ctx.keys, grads)))
+        pg = mod._unpack_param_grads(flat)
+        need = ctx.needs_input_grad
+        return (None, None, None) + tuple(pg.get(n) if need[3 + i] else None for i, n in enumerate(ctx.names))
 
 
 class LocalPoolPointnet(nn.Module):
@@ -167,7 +211,22 @@ class LocalPoolPointnet(nn.Module):
         _abi.require_cuda(p, 'p')
         if p.dim() != 3 or p.size(2) != 3:
             raise ValueError('p must have shape (B, T, 3)')
-        _abi.forbid_autograd(p, *self.parameters())
+        own = self._pointnet_params()
+        if _abi.wants_grad(p, *[t for _, t in own]):
+            if p.requires_grad:
+                raise NotImplementedError('vtaco_b200: no gradient w.r.t. the input points p; detach p')
+            if return_code or return_index:
+                raise NotImplementedError('vtaco_b200: return_code / return_index are inference-only outputs; '
+                                          'call under torch.no_grad()')
+            names, params = zip(*own)
+            outs = _PointnetFn.apply(self, p, names, *params)
+            return dict(zip([k for k in _KEY_ORDER_OUT if k in self._keys_in()], outs))
+        return self._pointnet_impl(p, return_code, return_index)
+
+    def _pointnet_params(self):
+        return [(n, t) for n, t in self.named_parameters() if not n.startswith(('unet.', 'unet3d.'))]
+
+    def _pointnet_impl(self, p, return_code=False, return_index=False):
         L = _lib()
         B, T = p.shape[0], p.shape[1]
         keys = self._keys_in()
@@ -220,6 +279,56 @@ class LocalPoolPointnet(nn.Module):
         if return_index:
             res += (idxs,)
         return res if len(res) > 1 else fea
+
+    # ------------------------------------------------------------------ backward
+    def _pointnet_backward(self, p, w, grads):
+        """vtaco_encoder_backward: `grads` maps key -> gradient of the (B,32,R,R[,R]) feature tensor
+        (or None); returns the flat parameter-gradient buffer (native layout, include/vtaco_b200.h)."""
+        L = _lib()
+        B, T = p.shape[0], p.shape[1]
+        dev = p.device
+        keys = self._keys_in()
+        pc = p.contiguous()
+        a = EncoderBwdArgs()
+        a.p, a.B, a.T = pc.data_ptr(), B, T
+        a.padding, a.div_mode = float(self.padding), _div_mode(self.division)
+        a.n_keys = len(keys)
+        keep = []
+        for i, k in enumerate(keys):
+            a.kind[i], a.reso[i] = _abi.KIND[k], self._reso(k)
+            g = grads.get(k)
+            if g is not None:
+                gcl = (g.permute(0, 2, 3, 4, 1) if k == 'grid' else g.permute(0, 2, 3, 1)).contiguous().float()
+                keep.append(gcl)
+                a.d_out_cl[i] = gcl.data_ptr()
+        a.pool_mean = int(self.scatter_type == 'mean')
+        a.n_blocks = self.n_blocks
+        a.weights = w.data_ptr()
+        flat = torch.zeros(256 + 5184 * self.n_blocks + 1056, dtype=torch.float32, device=dev)
+        a.d_params = flat.data_ptr()
+        nbytes = L.vtaco_encoder_backward_workspace_bytes(B, T, a.n_keys, a.kind, a.reso, self.n_blocks)
+        if nbytes < 0:
+            _abi.check(int(nbytes), 'encoder_backward_workspace_bytes')
+        ws = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        with torch.cuda.device(dev):
+            st = L.vtaco_encoder_backward(C.byref(a), _abi.stream_ptr(dev))
+        _abi.check(st, 'encoder_backward')
+        return flat
+
+    def _unpack_param_grads(self, flat):
+        g = {'fc_pos.weight': flat[0:192].view(64, 3), 'fc_pos.bias': flat[192:256]}
+        for i in range(self.n_blocks):
+            o = 256 + 5184 * i
+            g['blocks.%d.fc_0.weight' % i] = flat[o:o + 2048].view(32, 64)
+            g['blocks.%d.fc_0.bias' % i] = flat[o + 2048:o + 2080]
+            g['blocks.%d.fc_1.weight' % i] = flat[o + 2080:o + 3104].view(32, 32)
+            g['blocks.%d.fc_1.bias' % i] = flat[o + 3104:o + 3136]
+            g['blocks.%d.shortcut.weight' % i] = flat[o + 3136:o + 5184].view(32, 64)
+        o = 256 + 5184 * self.n_blocks
+        g['fc_c.weight'] = flat[o:o + 1024].view(32, 32)
+        g['fc_c.bias'] = flat[o + 1024:o + 1056]
+        return g
 
     # ------------------------------------------------------------------ reference API
     def forward(self, p):
