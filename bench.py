@@ -167,6 +167,24 @@ class CpuReference(object):
         self.oc.eval_points(self.p, self.feats, self.W, self.c_img, points_batch_size=100000)
         return time.perf_counter() - t0
 
+    def run_torch_eager_gpu(self):
+        """The same algorithm the way the reference runs it on a GPU (generation.py:352-383): host chunk ->
+        .to(device) -> decode_img through torch eager ATen kernels -> .cpu().  SURVEY §8d's "GPU bar"."""
+        dev = torch.device('cuda', torch.cuda.current_device())
+        if not hasattr(self, 'feats_g'):
+            self.feats_g = {k: v.to(dev) for k, v in self.feats.items()}
+            self.W_g = {k: v.to(dev) for k, v in self.W.items()}
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        occ = []
+        with torch.no_grad():
+            for pi, ci in zip(torch.split(self.p, 100000), torch.split(self.c_img, 100000)):
+                o = self.oc.decoder_forward(pi.unsqueeze(0).to(dev), self.feats_g, self.W_g, mode='img',
+                                            c_img=ci.unsqueeze(0).to(dev))
+                occ.append(o.squeeze(0).cpu())
+        torch.cat(occ, dim=0)
+        return time.perf_counter() - t0
+
 
 def run_reference(args, rank, world):
     if rank != 0:
@@ -526,6 +544,15 @@ def run_ours(args, rank, local_rank, world):
                 'sample': '%d consecutive lattice points of the %d^3 lattice, best of 3 after 1 warm-up, oracle port '
                           'of Generator3D.eval_points + LocalDecoder.forward_img (torch CPU ops, 100k chunks)'
                           % (ref.n, nx)}
+            refg = CpuReference(nx, 16 * args.cpu_sample)
+            refg.run_torch_eager_gpu()
+            secg = min(refg.run_torch_eager_gpu() for _ in range(3))
+            line['torch_eager_gpu_baseline'] = {
+                'value': refg.n / secg, 'unit': UNIT, 'kind': 'port',
+                'sample': '%d lattice points, best of 3 after 1 warm-up: the oracle port (the same ATen ops the '
+                          'reference executes) on this GPU under torch %s eager, with the chunking and host<->device '
+                          'copies of Generator3D.eval_points (generation.py:352-383) - compare with e2e, not value'
+                          % (refg.n, torch.__version__)}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -539,7 +566,8 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--nx', type=int, default=256)
     ap.add_argument('--variant', type=int, default=2,
-                    help='decoder kernel: 0 scalar-FFMA SIMT, 1 packed-FFMA2 SIMT, 2 tcgen05 3xTF32 (default)')
+                    help='decoder kernel: 0 scalar-FFMA SIMT, 1 packed-FFMA2 SIMT, 2 tcgen05 3xTF32 (default), '
+                         '4 tcgen05 TF32 + BF16 corrections')
     ap.add_argument('--cpu-sample', type=int, default=4 * 256 * 256)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-multicast', action='store_true', help='fused exchange with unicast peer stores only')

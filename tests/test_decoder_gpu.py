@@ -23,7 +23,7 @@ def make_decoder(W, leaky=False, contact=None, mode='bilinear', division='true')
     return dec
 
 
-@pytest.mark.parametrize('variant', [0, 1, 2])
+@pytest.mark.parametrize('variant', [0, 1, 2, 4])
 @pytest.mark.parametrize('tag', ['relu', 'leaky'])
 def test_decoder_golden(tag, variant):
     g = load('decoder_%s.npz' % tag)

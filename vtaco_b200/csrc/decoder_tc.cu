@@ -26,6 +26,7 @@
 //   * the residual stream stays in registers; feature gather, fc_p, tips and fc_out run on the
 //     CUDA cores exactly as in the SIMT kernel.
 #include "decoder_common.cuh"
+#include <cuda_bf16.h>
 #include <cstdio>
 #include <cstdlib>
 
@@ -37,6 +38,7 @@ constexpr int kTcTile = 128;
 constexpr int kColsPerGroup = 168;   // C_hi 0, C_lo 32, X_hi 64, X_lo 96, ones 128 (8), D 136 (32)
 constexpr int kStageStride = 36;     // floats per staged query row (conflict-free LDS.128)
 constexpr uint32_t kIdescTf32 = (1u << 4) | (2u << 7) | (2u << 10) | (4u << 17) | (8u << 24);  // F32 acc, TF32 x TF32, K-major, N=32, M=128
+constexpr uint32_t kIdescBf16 = (1u << 4) | (1u << 7) | (1u << 10) | (4u << 17) | (8u << 24);  // F32 acc, BF16 x BF16 (kind::f16, K=16)
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -90,6 +92,16 @@ __device__ __forceinline__ void tc_mma_ts(uint32_t d, uint32_t a, uint64_t bdesc
       "}\n" ::"r"(d), "r"(a), "l"(bdesc), "r"(kIdescTf32), "r"(accumulate)
       : "memory");
 }
+// same with BF16 operands (two per 32-bit TMEM column, K = 16 per instruction)
+__device__ __forceinline__ void tc_mma_ts_bf16(uint32_t d, uint32_t a, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(d), "r"(a), "l"(bdesc), "r"(kIdescBf16), "r"(accumulate)
+      : "memory");
+}
 // K-major, no swizzle: 8 rows x 16 B core matrices; K-chunk stride 512 B, 8-row-group stride 128 B
 __device__ __forceinline__ uint64_t make_bdesc(uint32_t saddr) {
   uint64_t d = 0;
@@ -130,13 +142,29 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
 // truncation to TF32 is a 2^-21 relative error — far inside the 1e-4 parity bar.
 __device__ __forceinline__ uint32_t trunc_tf32(float x) { return __float_as_uint(x) & 0xffffe000u; }
 
-// x[32] (fp32) -> hi/lo TF32 operands stored to TMEM columns [col, col+32) and [col+32, col+64)
-__device__ __forceinline__ void split_store(uint32_t taddr, const float (&x)[32]) {
+__device__ __forceinline__ uint32_t pack_bf16(float k_even, float k_odd) {   // element 2c in the low half
+  const __nv_bfloat162 v = __floats2bfloat162_rn(k_even, k_odd);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+
+// x[32] (fp32) -> operands stored to TMEM columns [col, col+32) and [col+32, col+64):
+//   3xTF32 : hi | lo (both TF32 in fp32 containers)
+//   mixed  : hi (TF32) | correction operand in BF16, K = 64: bf16(lo[0..31]) then bf16(hi[0..31]),
+//            two elements per column.  The main product hi*W_hi stays TF32; lo*W and hi*W_lo are
+//            ~2^-11 of it, so BF16's 2^-9 relative rounding leaves a ~2^-19 relative error.
+__device__ __forceinline__ void split_store(uint32_t taddr, const float (&x)[32], bool mixed) {
   uint32_t hi[32], lo[32];
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    hi[j] = trunc_tf32(x[j]);
-    lo[j] = __float_as_uint(x[j] - __uint_as_float(hi[j]));
+  for (int j = 0; j < 32; ++j) hi[j] = trunc_tf32(x[j]);
+  if (mixed) {
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      lo[c] = pack_bf16(x[2 * c] - __uint_as_float(hi[2 * c]), x[2 * c + 1] - __uint_as_float(hi[2 * c + 1]));
+      lo[16 + c] = pack_bf16(__uint_as_float(hi[2 * c]), __uint_as_float(hi[2 * c + 1]));
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) lo[j] = __float_as_uint(x[j] - __uint_as_float(hi[j]));
   }
   tmem_st32(taddr, hi);
   tmem_st32(taddr + 32, lo);
@@ -249,6 +277,11 @@ __host__ __device__ inline TcSmem tc_smem_layout(int n_blocks) {
 __device__ __forceinline__ void issue_product(uint32_t d, uint32_t a_hi, uint32_t w_smem, uint32_t accumulate_first,
                                               int n_products = 3) {
   const uint32_t a_lo = a_hi + 32;
+  if (n_products == 2) {   // mixed: BF16 correction (K = 64) then the TF32 main product
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) tc_mma_ts_bf16(d, a_lo + 8 * kk, make_bdesc(w_smem + 4096 + kk * 1024), kk > 0 ? 1u : accumulate_first);
+    accumulate_first = 1;
+  }
   if (n_products >= 3) {
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) tc_mma_ts(d, a_lo + 8 * kk, make_bdesc(w_smem + kk * 1024), kk > 0 ? 1u : accumulate_first);
@@ -337,6 +370,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) decoder_tc_kernel(const __grid_
   const int nx = P.nx;
   float vmin = CUDART_INF_F, vmax = -CUDART_INF_F;
   int step = 0;  // accumulation steps issued so far by this group (rotates the issuing warp)
+  const bool mixed = (P.tc_products == 2);
 
   for (long long tile = (long long)blockIdx.x * kTcGroups + g; tile < P.n_tiles;
        tile += (long long)gridDim.x * kTcGroups) {
@@ -466,7 +500,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) decoder_tc_kernel(const __grid_
       __syncwarp();
       }  // generic gather
       TC_STAMP(15);  // features of the thread's query in registers
-      split_store(tC, cv);
+      split_store(tC, cv, mixed);
       tc_wait_st();
       tc_fence_before();
       group_sync(g);
@@ -521,7 +555,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) decoder_tc_kernel(const __grid_
       TC_STAMP(1);   // ALU phase starts (accumulator already read)
 #pragma unroll
       for (int j = 0; j < 32; ++j) x[j] = fmaxf(net[j], 0.f);
-      split_store(tX, x);
+      split_store(tX, x, mixed);
       TC_STAMP(2);   // operands computed, tcgen05.st issued
       tc_wait_st();
       tc_fence_before();
@@ -544,7 +578,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) decoder_tc_kernel(const __grid_
       TC_STAMP(7);   // accumulator in registers
 #pragma unroll
       for (int j = 0; j < 32; ++j) x[j] = fmaxf(__uint_as_float(r[j]), 0.f);
-      split_store(tX, x);
+      split_store(tX, x, mixed);
       TC_STAMP(8 + 16 * (i & 1));    // W1 step: operands computed (+16: warp 0 is this step's issuer)
       tc_wait_st();
       tc_fence_before();
