@@ -368,6 +368,17 @@ int vtaco_group_norm_cl(const float* x, float* y, const float* gamma, const floa
  * ------------------------------------------------------------------------- */
 int vtaco_fp32_peak(int variant, int iters, double* flops_per_s_host, void* stream);
 
+/* ------------------------------------------------------------------------- *
+ * (9) Chamfer distance — the metric computed right after mesh extraction
+ * (src/common.py:54-137 chamfer_distance{,_naive,_kdtree}, called by
+ * generation.py:281 on 2048 mesh vertices vs 2048 ground-truth points).
+ * p1 [B][T1][3], p2 [B][T2][3].  dist12[b][i] = min_j |p1_i - p2_j|^2 (fp32, (dx^2+dy^2)+dz^2),
+ * idx12 = the arg-min (first minimum), dist21 / idx21 the other direction; idx* optional.
+ * chamfer1[b] = mean_i dist12, chamfer2[b] = mean_j dist21 (optional).  The reference's
+ * value is chamfer1 + chamfer2. */
+int vtaco_chamfer(const float* p1, const float* p2, int32_t B, int64_t T1, int64_t T2, float* dist12, int32_t* idx12,
+                  float* dist21, int32_t* idx21, float* chamfer1, float* chamfer2, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -293,3 +293,30 @@ def fingertip_c_img(p, tips, tip_feat, touch, radius=0.05):
             sel = np.where((dmin < radius) & (amin == f))[0]
             out[sel] = tip_feat[f]
     return out
+
+
+# --------------------------------------------------------------------------- #
+# src/common.py:54-137 — Chamfer distance (the metric after mesh extraction)
+# --------------------------------------------------------------------------- #
+def chamfer_distance_naive(points1, points2):
+    """src/common.py:69-91."""
+    if points2.size()[1] < 2048:
+        points1 = points1[:, :points2.size()[1], :]
+    assert points1.size() == points2.size()
+    B, T, _ = points1.size()
+    d = (points1.view(B, T, 1, 3) - points2.view(B, 1, T, 3)).pow(2).sum(-1)
+    return d.min(dim=1)[0].mean(dim=1) + d.min(dim=2)[0].mean(dim=1)
+
+
+def chamfer_distance_kdtree(points1, points2, give_id=False):
+    """src/common.py:94-137 with the kd-tree query (pykdtree, un-vendored) restated as an exact
+    nearest-neighbour search in float64."""
+    d = torch.cdist(points1.double(), points2.double())
+    i12, i21 = d.argmin(2), d.argmin(1)
+    p12 = torch.gather(points2, 1, i12[:, :, None].expand_as(points1))
+    p21 = torch.gather(points1, 1, i21[:, :, None].expand_as(points2))
+    c1 = (points1 - p12).pow(2).sum(2).mean(1)
+    c2 = (points2 - p21).pow(2).sum(2).mean(1)
+    if give_id:
+        return c1, c2, i12, i21
+    return c1 + c2

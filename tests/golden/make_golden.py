@@ -43,7 +43,11 @@ def install_shims():
 
     mod('torch_scatter', scatter_mean=_scatter_mean, scatter_max=_scatter_max)
     k = mod('pykdtree')
-    k.kdtree = mod('pykdtree.kdtree', KDTree=object)
+    try:   # same query API (tree.query(x, k) -> (dist, idx)); exact nearest neighbours either way
+        from scipy.spatial import cKDTree as _KD
+    except Exception:
+        _KD = object
+    k.kdtree = mod('pykdtree.kdtree', KDTree=_KD)
     mod('pybullet')
     mod('trimesh', Trimesh=object)
     mod('igl')
@@ -262,6 +266,7 @@ def main():
 
     make_grads(common, encoder_dict, models, generation)
     make_encoder_grads(common, encoder_dict, models, generation)
+    make_chamfer(common)
     for f in sorted(os.listdir(HERE)):
         if f.endswith('.npz'):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, 'KiB')
@@ -347,8 +352,25 @@ def make_encoder_grads(common, encoder_dict, models, generation):
     np.savez_compressed(os.path.join(HERE, 'encoder_grads.npz'), **g)
 
 
+def make_chamfer(common):
+    """G8: src/common.py chamfer_distance on mesh-vertex-like sets (generation.py:281 uses 2048 points)."""
+    g = {}
+    for tag, B, T in (('t2048', 2, 2048), ('t300', 3, 300)):
+        a = rs_uniform(171, -0.5, 0.5, B, T, 3)
+        b = (a + rs_randn(172, B, T, 3, scale=0.02))[:, ::-1].copy()
+        g[tag + '.p1'], g[tag + '.p2'] = a, b
+        ta, tb = torch.from_numpy(a), torch.from_numpy(b)
+        g[tag + '.naive'] = common.chamfer_distance(ta, tb, use_kdtree=False).numpy()
+        c1, c2, i12, i21 = common.chamfer_distance(ta, tb, use_kdtree=True, give_id=True)
+        g[tag + '.kd_c1'], g[tag + '.kd_c2'] = c1.numpy(), c2.numpy()
+        g[tag + '.kd_i12'], g[tag + '.kd_i21'] = i12.numpy().astype(np.int32), i21.numpy().astype(np.int32)
+    np.savez_compressed(os.path.join(HERE, 'chamfer.npz'), **g)
+
+
 if __name__ == '__main__':
-    if sys.argv[1:] == ['grads']:
+    if sys.argv[1:] == ['chamfer']:
+        make_chamfer(import_reference()[0])
+    elif sys.argv[1:] == ['grads']:
         torch.set_num_threads(4)
         ref = import_reference()
         make_grads(*ref)

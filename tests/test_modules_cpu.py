@@ -114,3 +114,24 @@ def test_make_3d_grid_matches_reference():
     assert np.array_equal(make_3d_grid((-0.5,) * 3, (0.5,) * 3, (4, 3, 2)).numpy(), g['grid3_4'])
     for nx in (8, 32, 128, 256):
         assert np.array_equal(dense_axis(nx).numpy(), g['axis_%d' % nx])
+
+
+def test_off_roundtrip(tmp_path):
+    """export_off writes what read_off (reference src/utils/io.py:27-80 semantics) reads back."""
+    import numpy as np
+    from vtaco_b200.io import export_off, read_off
+    rs = np.random.RandomState(0)
+    v = rs.uniform(-0.55, 0.55, size=(50, 3)).astype(np.float32)
+    f = rs.randint(0, 50, size=(80, 3)).astype(np.int32)
+    path = str(tmp_path / 'm.off')
+    export_off(path, torch.from_numpy(v), torch.from_numpy(f))
+    v2, f2 = read_off(path)
+    assert np.array_equal(f2, f) and np.allclose(v2, v, rtol=0, atol=1e-7)
+    with open(path) as fp:
+        assert fp.readline().strip() == 'OFF' and fp.readline().split() == ['50', '80', '0']
+    with open(path, 'w') as fp:          # ModelNet variant: counts on the OFF line
+        fp.write('OFF3 1 0\n0 0 0\n1 0 0\n0 1 0\n3 0 1 2\n')
+    v3, f3 = read_off(path)
+    assert v3.shape == (3, 3) and f3.tolist() == [[0, 1, 2]]
+    with pytest.raises(ValueError):
+        export_off(path, v, np.array([[0, 1, 50]]))

@@ -168,3 +168,13 @@ def test_encoder_gradients_match_reference(case):
     assert abs(loss - float(g[tag + '.loss'])) <= 1e-4 * max(1.0, abs(float(g[tag + '.loss'])))
     for k, v in grads.items():
         assert rel_fro(v.numpy(), g['%s.dw.%s' % (tag, k)]) < 1e-5, k
+
+
+@pytest.mark.parametrize('tag', ['t2048', 't300'])
+def test_chamfer_matches_reference(tag):
+    g = load('chamfer.npz')
+    a, b = torch.from_numpy(g[tag + '.p1']), torch.from_numpy(g[tag + '.p2'])
+    assert close(oc.chamfer_distance_naive(a, b).numpy(), g[tag + '.naive'], 1e-6) < 1e-6
+    c1, c2, i12, i21 = oc.chamfer_distance_kdtree(a, b, give_id=True)
+    assert np.array_equal(i12.numpy(), g[tag + '.kd_i12']) and np.array_equal(i21.numpy(), g[tag + '.kd_i21'])
+    assert close(c1.numpy(), g[tag + '.kd_c1'], 1e-6) < 1e-6 and close(c2.numpy(), g[tag + '.kd_c2'], 1e-6) < 1e-6

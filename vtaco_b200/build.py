@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'lib', 'libvtaco_b200.so')
-SOURCES = ['core.cu', 'decoder.cu', 'decoder_tc.cu', 'decoder_bwd.cu', 'encoder.cu', 'mcubes.cu', 'tc_microbench.cu']
+SOURCES = ['core.cu', 'decoder.cu', 'decoder_tc.cu', 'decoder_bwd.cu', 'encoder.cu', 'mcubes.cu', 'metrics.cu', 'tc_microbench.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '--use_fast_math=false', '-Xcompiler', '-fPIC', '-Xcompiler', '-O2',
               '--fmad=true', '-Xptxas', '-v']

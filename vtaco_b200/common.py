@@ -84,3 +84,59 @@ def dense_axis(nx, padding=0.1, device=None):
     reference's host tensor: computed with the same torch ops on the host."""
     ax = (1 + padding) * torch.linspace(-0.5, 0.5, nx)
     return ax.to(device) if device is not None else ax
+
+
+# --------------------------------------------------------------------------- #
+# Chamfer distance (reference src/common.py:54-137) — the metric Generator3D
+# computes right after mesh extraction (generation.py:281); SURVEY §8f-4.
+# --------------------------------------------------------------------------- #
+def _chamfer(points1, points2, want_idx):
+    import ctypes as C
+    _abi.require_cuda(points1, 'points1')
+    _abi.require_cuda(points2, 'points2')
+    if points1.dim() != 3 or points2.dim() != 3 or points1.size(2) != 3 or points2.size(2) != 3:
+        raise ValueError('points must have shape (B, T, 3)')
+    if points1.size(0) != points2.size(0):
+        raise ValueError('batch sizes differ')
+    _abi.forbid_autograd(points1, points2)
+    B, T1, T2 = points1.size(0), points1.size(1), points2.size(1)
+    dev = points1.device
+    p1, p2 = points1.contiguous(), points2.contiguous()
+    d12 = torch.empty((B, T1), dtype=torch.float32, device=dev)
+    d21 = torch.empty((B, T2), dtype=torch.float32, device=dev)
+    i12 = torch.empty((B, T1), dtype=torch.int32, device=dev) if want_idx else None
+    i21 = torch.empty((B, T2), dtype=torch.int32, device=dev) if want_idx else None
+    c1 = torch.empty(B, dtype=torch.float32, device=dev)
+    c2 = torch.empty(B, dtype=torch.float32, device=dev)
+    L = _abi.lib()
+    L.vtaco_chamfer.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int64] + [C.c_void_p] * 7
+    with torch.cuda.device(dev):
+        st = L.vtaco_chamfer(_abi.ptr(p1), _abi.ptr(p2), B, T1, T2, _abi.ptr(d12), _abi.ptr(i12), _abi.ptr(d21),
+                             _abi.ptr(i21), _abi.ptr(c1), _abi.ptr(c2), _abi.stream_ptr(dev))
+    _abi.check(st, 'chamfer')
+    return c1, c2, i12, i21
+
+
+def chamfer_distance_naive(points1, points2):
+    """reference src/common.py:69-91: sum of the two directed mean squared nearest-neighbour
+    distances; points1 is cut to points2's length when that is < 2048, sizes must then agree."""
+    if points2.size()[1] < 2048:
+        points1 = points1[:, :points2.size()[1], :]
+    assert points1.size() == points2.size()
+    c1, c2, _, _ = _chamfer(points1, points2, False)
+    return c1 + c2
+
+
+def chamfer_distance_kdtree(points1, points2, give_id=False):
+    """reference src/common.py:94-137; the exact neighbours a kd-tree returns, by brute force on the GPU."""
+    c1, c2, i12, i21 = _chamfer(points1, points2, give_id)
+    if give_id:
+        return c1, c2, i12.long(), i21.long()
+    return c1 + c2
+
+
+def chamfer_distance(points1, points2, use_kdtree=True, give_id=False):
+    """reference src/common.py:54-66."""
+    if use_kdtree:
+        return chamfer_distance_kdtree(points1, points2, give_id=give_id)
+    return chamfer_distance_naive(points1, points2)

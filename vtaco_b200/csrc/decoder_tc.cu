@@ -300,7 +300,7 @@ __device__ __forceinline__ void issue_product(uint32_t d, uint32_t a_hi, uint32_
       trace[trace_n++] = ((long long)(slot) << 56) | (clock64() & 0x00ffffffffffffffll); \
   } while (0)
 
-template <bool DENSE>
+template <bool DENSE, bool MIXED>
 __global__ void __launch_bounds__(kTcThreads, 1) decoder_tc_kernel(const __grid_constant__ DecParams P,
                                                                    const float* __restrict__ wtc,
                                                                    long long* __restrict__ trace) {
@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) decoder_tc_kernel(const __grid_
   const int nx = P.nx;
   float vmin = CUDART_INF_F, vmax = -CUDART_INF_F;
   int step = 0;  // accumulation steps issued so far by this group (rotates the issuing warp)
-  const bool mixed = (P.tc_products == 2);
+  constexpr bool mixed = MIXED;   // compile-time: the 3xTF32 kernel keeps its register budget
 
   for (long long tile = (long long)blockIdx.x * kTcGroups + g; tile < P.n_tiles;
        tile += (long long)gridDim.x * kTcGroups) {
@@ -660,13 +660,17 @@ int launch_decoder_tc(DecParams P, bool dense, const float* wtc, cudaStream_t st
   const TcSmem L = tc_smem_layout(P.n_blocks);
   if (L.total > 227 * 1024) return VTACO_ERR_UNSUPPORTED;
   if (P.n_tiles >= (1ll << 31)) return VTACO_ERR_UNSUPPORTED;
-  static size_t configured[2][64] = {{0}};
+  const bool mixed = (P.tc_products == 2);
+  using Kernel = void (*)(DecParams, const float*, long long*);
+  const Kernel kernel = dense ? (mixed ? (Kernel)decoder_tc_kernel<true, true> : (Kernel)decoder_tc_kernel<true, false>)
+                              : (mixed ? (Kernel)decoder_tc_kernel<false, true> : (Kernel)decoder_tc_kernel<false, false>);
+  static size_t configured[4][64] = {{0}};
   int dev = 0;
   VTACO_CUDA_CHECK(cudaGetDevice(&dev));
-  if (configured[dense][dev & 63] < (size_t)L.total) {
-    if (dense) VTACO_CUDA_CHECK(cudaFuncSetAttribute(decoder_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-    else VTACO_CUDA_CHECK(cudaFuncSetAttribute(decoder_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-    configured[dense][dev & 63] = L.total;
+  const int ki = (dense ? 2 : 0) + (mixed ? 1 : 0);
+  if (configured[ki][dev & 63] < (size_t)L.total) {
+    VTACO_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+    configured[ki][dev & 63] = L.total;
   }
   long long grid = (P.n_tiles + kTcGroups - 1) / kTcGroups;
   if (grid > num_sms()) grid = num_sms();
@@ -676,8 +680,7 @@ int launch_decoder_tc(DecParams P, bool dense, const float* wtc, cudaStream_t st
     VTACO_CUDA_CHECK(cudaMalloc(&trace, 4096 * sizeof(long long)));
     VTACO_CUDA_CHECK(cudaMemsetAsync(trace, 0, 4096 * sizeof(long long), stream));
   }
-  if (dense) decoder_tc_kernel<true><<<(unsigned)grid, kTcThreads, L.total, stream>>>(P, wtc, trace);
-  else decoder_tc_kernel<false><<<(unsigned)grid, kTcThreads, L.total, stream>>>(P, wtc, trace);
+  kernel<<<(unsigned)grid, kTcThreads, L.total, stream>>>(P, wtc, trace);
   VTACO_LAUNCH_CHECK();
   if (trace) {   // debug: average cycles between consecutive stamps, per (from -> to) slot pair
     static long long h[4096];
