@@ -55,3 +55,7 @@ def test_mesh_to_chamfer_end_to_end(tmp_path):
     sel = torch.from_numpy(rs.permutation(len(v))[:2048]).cuda()
     cd = chamfer_distance(gt, v[sel][None].contiguous(), use_kdtree=False)
     assert cd.item() < 2 * (0.03 ** 2)      # both sets lie on the same sphere (spacing ~0.02)
+    from vtaco_b200.conv_onet.generation import Generator3D
+    gen = Generator3D(torch.nn.Identity(), device='cuda', resolution0=16, padding=0.1)
+    cd2 = gen.mesh_chamfer(v, gt, generator=torch.Generator(device='cuda').manual_seed(0))
+    assert cd2.shape == (1,) and cd2.item() < 2 * (0.03 ** 2)

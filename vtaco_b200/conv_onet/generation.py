@@ -291,6 +291,17 @@ class Generator3D(object):
             return self._to_host(v, f)
         return v, f
 
+    def mesh_chamfer(self, vertices, points_obj, n_sample=2048, generator=None):
+        """The Chamfer metric of generate_obj_mesh_wnf (reference generation.py:275-281): shuffle the
+        mesh vertices, keep `n_sample`, chamfer_distance(points_obj, vertices, use_kdtree=False).
+        vertices (V,3) device tensor (extract_mesh output), points_obj (1,T,3).  Stays on the device;
+        the shuffle uses torch's generator instead of numpy's global one.  (The reference also reports
+        an Earth-Mover distance through scipy's Hungarian solver — not built)"""
+        from ..common import chamfer_distance
+        v = torch.as_tensor(vertices, device=self.device, dtype=torch.float32)
+        perm = torch.randperm(v.shape[0], device=self.device, generator=generator)[:n_sample]
+        return chamfer_distance(points_obj.to(self.device), v[perm][None].contiguous(), use_kdtree=False)
+
     def _to_host(self, v, f):
         """mesh D2H through cached pinned staging buffers (one synchronisation)."""
         if self._pin is None or self._pin[0].shape[0] < v.shape[0] or self._pin[1].shape[0] < f.shape[0]:
