@@ -470,7 +470,7 @@ def run_ours(args, rank, local_rank, world):
         bf16_peak = measured.get('bf16_tflops', 1590.0)        # burst figure: the kernel is timed alone
         peak_tag = 'of measured' if 'bf16_tflops' in measured else 'of fallback'
         traffic = None
-        prof = os.path.join(ROOT, 'profiles', 'decoder_ncu_summary.json' if args.variant != 2
+        prof = os.path.join(ROOT, 'profiles', 'decoder_ncu_summary.json' if args.variant < 2
                             else 'decoder_tc_ncu_summary.json')
         if os.path.exists(prof):
             try:
@@ -485,24 +485,36 @@ def run_ours(args, rank, local_rank, world):
                   'hbm_algorithmic_gbs': hbm_gbs,
                   'hbm_frac_of_measured': hbm_gbs / measured['hbm_gbs'] if 'hbm_gbs' in measured else None,
                   'traffic': traffic}
-        if args.variant == 2:
-            # executed tensor work: per 128-query tile (12 MMAs per 32x32 product, 3 products per block + 1,
-            # one bias MMA per step), each MMA = M128 x N32 x K8 x 2 FLOP
+        if args.variant >= 2:
+            # executed tensor work per 128-query tile: per 32x32 matrix (3 per block) either 12 TF32 MMAs
+            # (3xTF32) or 4 TF32 + 4 BF16 MMAs (mixed), plus one TF32 bias MMA per step; an MMA is
+            # M128 x N32 x (K8 tf32 | K16 bf16) x 2 FLOP
             nb_ = 5
-            mmas = 12 * (3 * nb_) + (2 * nb_ + 1)
-            tensor_flop_per_query = mmas * 128 * 32 * 8 * 2 / 128.0
+            mixed = args.variant in (4, 6)
+            split = 2 if args.variant in (5, 6) else 1
+            tf32_mmas = (4 if mixed else 12) * (3 * nb_) + (2 * nb_ + 1)
+            bf16_mmas = 4 * (3 * nb_) if mixed else 0
+            tf32_fpq = tf32_mmas * 128 * 32 * 8 * 2 / 128.0
+            bf16_fpq = bf16_mmas * 128 * 32 * 16 * 2 / 128.0
+            tensor_flop_per_query = tf32_fpq + bf16_fpq
             t_achieved = kq * tensor_flop_per_query / (k_ms * 1e-3) / 1e12
             tf32_peak = bf16_peak / 2.0
-            roofline = dict(common, bound='tensor', kernel='decoder_tc_kernel<dense> (tcgen05 kind::tf32, 3xTF32)',
-                            achieved=t_achieved, peak=tf32_peak, unit='TFLOP/s', frac=t_achieved / tf32_peak,
+            # fraction of the kernel time the tensor pipe would need at peak rate for the executed MMAs
+            frac = kq * (tf32_fpq / (tf32_peak * 1e12) + bf16_fpq / (bf16_peak * 1e12)) / (k_ms * 1e-3)
+            kname = '%s<dense> (tcgen05 %s, %d thread%s per query)' % (
+                'decoder_tc2_kernel' if split == 2 else 'decoder_tc_kernel',
+                'kind::tf32 main + kind::f16 BF16 corrections' if mixed else 'kind::tf32, 3xTF32',
+                split, 's' if split > 1 else '')
+            roofline = dict(common, bound='tensor', kernel=kname,
+                            achieved=t_achieved, peak=t_achieved / frac, unit='TFLOP/s', frac=frac,
                             peak_source='TF32 dense = 1/2 of the %s bf16 cuBLAS burst peak (%.1f TFLOP/s, %s); '
-                                        'MEASURED_PEAKS.json has no TF32 figure' % ('measured' if 'bf16_tflops' in
-                                                                                   measured else 'fallback',
-                                                                                   bf16_peak, peak_tag),
+                                        'MEASURED_PEAKS.json has no TF32 figure%s'
+                                        % ('measured' if 'bf16_tflops' in measured else 'fallback', bf16_peak, peak_tag,
+                                           '; BF16 MMAs counted against the bf16 peak' if mixed else ''),
                             tensor_flop_per_query=tensor_flop_per_query,
-                            note='3xTF32 executes 3.36x the algorithmic FLOPs to keep fp32 accuracy; the kernel is '
-                                 'latency/issue-bound (tensor pipe ~30% busy, issue slots ~45%), see '
-                                 'profiles/decoder_tc_ncu_summary.json')
+                            note='3xTF32 executes 3.16x the algorithmic FLOPs to keep fp32 accuracy (the mixed mode '
+                                 '2.2x of them in TF32-time); the kernel is bound by the per-warp phase chain, not by '
+                                 'the tensor pipe: see profiles/decoder_tc_ncu_summary.json and DESIGN.md 4.1')
         else:
             roofline = dict(common, bound='fp32', kernel='decoder_kernel<dense> (SIMT)', achieved=achieved / 1e12,
                             peak=fp32_peak / 1e12, unit='TFLOP/s', frac=achieved / fp32_peak,
@@ -565,9 +577,9 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--nx', type=int, default=256)
-    ap.add_argument('--variant', type=int, default=2,
-                    help='decoder kernel: 0 scalar-FFMA SIMT, 1 packed-FFMA2 SIMT, 2 tcgen05 3xTF32 (default), '
-                         '4 tcgen05 TF32 + BF16 corrections')
+    ap.add_argument('--variant', type=int, default=5,
+                    help='decoder kernel: 0 scalar-FFMA SIMT, 1 packed-FFMA2 SIMT, 2 tcgen05 3xTF32, 4 tcgen05 TF32 + BF16 '
+                         'corrections, 5 (default) / 6 = 2 / 4 with two threads per query')
     ap.add_argument('--cpu-sample', type=int, default=4 * 256 * 256)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-multicast', action='store_true', help='fused exchange with unicast peer stores only')

@@ -141,12 +141,13 @@ typedef struct vtaco_decoder_args {
   int32_t* minmax_key;     /* optional [2]: ordered-int keys of min / max logit, updated with
                               atomicMin/atomicMax (caller initialises to INT32_MAX, INT32_MIN) */
   int32_t variant;         /* 0 = scalar-FFMA SIMT kernel; 1 = packed-FFMA2 SIMT kernel; 2 = tcgen05 3xTF32 kernel;
-                            * 3 = single TF32 product (debug, ~1e-3); 4 = tcgen05 TF32 main product + BF16 corrections */
-  /* variants 2-4: the 3*n_blocks hidden matrices (per block: fc_c[i], fc_0, fc_1) as TF32 hi / lo
+                            * 3 = single TF32 product (debug, ~1e-3); 4 = tcgen05 TF32 main product + BF16 corrections;
+                            * 5 / 6 = 2 / 4 with two threads per query (768-thread CTAs; fastest) */
+  /* variants 2-6: the 3*n_blocks hidden matrices (per block: fc_c[i], fc_0, fc_1) as TF32 hi / lo
    * pairs in the UMMA canonical K-major no-swizzle layout, 2048 floats per matrix:
    *   float index of element (n = out, k = in) = (k/4)*128 + (n/8)*32 + (n%8)*4 + (k%4),
    *   hi block (1024 floats) = rn_tf32(W), lo block (1024 floats) = tf32(W - hi);
-   *   variant 4: the lo block instead holds 2048 BF16 values, the K = 64 correction operand
+   *   variants 4 and 6: the lo block instead holds 2048 BF16 values, the K = 64 correction operand
    *   [bf16(W) ; bf16(W - hi)], bf16 index of (n, k) = (k/8)*256 + (n/8)*64 + (n%8)*8 + (k%8);
    * followed by 2*n_blocks+1 bias K-blocks of 256 floats in the same layout with k in [0,8): row k=0
    * = bias hi, k=1 = bias lo, for the steps bc_0 | b0_i, b1_i + bc_{i+1} (i = 0..n_blocks-1). */

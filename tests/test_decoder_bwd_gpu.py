@@ -17,7 +17,7 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-4
 
 
-def run_case(g, tag, leaky, keys, mode, smode, variant=2, max_queries=None):
+def run_case(g, tag, leaky, keys, mode, smode, variant=5, max_queries=None):
     W = {k[len(tag) + 3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith(tag + '.w.')}
     dec = make_decoder(W, leaky=leaky, contact=(mode == 'contact'), mode=smode)
     dec.train()
@@ -44,7 +44,7 @@ def run_case(g, tag, leaky, keys, mode, smode, variant=2, max_queries=None):
     return loss.item(), out
 
 
-@pytest.mark.parametrize('variant', [1, 2])
+@pytest.mark.parametrize('variant', [1, 5])
 @pytest.mark.parametrize('case', GRAD_CASES, ids=[c[0] for c in GRAD_CASES])
 def test_backward_golden(case, variant):
     tag, leaky, keys, mode, smode = case

@@ -119,10 +119,11 @@ class LocalDecoder(nn.Module):
         self.padding = padding
         # how `tensor / python_scalar` of normalize_* is evaluated ('cuda' | 'true'), SURVEY §7.2-1
         self.division = 'cuda'
-        # 0 scalar-FFMA SIMT, 1 packed-FFMA2 SIMT, 2 tcgen05 3xTF32 (fp32-accurate, default; calls with a
-        # per-query c_img tensor are routed to variant 1), 4 tcgen05 TF32 main product + BF16 corrections
-        # (one third fewer MMAs, 3.6e-6 instead of 1.4e-6 max deviation, 4 % faster)
-        self.kernel_variant = 2
+        # 0 scalar-FFMA SIMT, 1 packed-FFMA2 SIMT (exact fp32; per-query c_img tensors are routed here),
+        # 2 tcgen05 3xTF32 (fp32-accurate to ~1.5e-6), 4 tcgen05 TF32 main product + BF16 corrections (3.6e-6),
+        # 5 / 6 = 2 / 4 with two threads per query (8 warps per 128-query tile; fastest, default 5),
+        # 3 single TF32 product (debug, ~1e-3)
+        self.kernel_variant = 5
         self._pack_cache = None
         self._pack_tc_cache = None
         self._cl_cache = {}
@@ -293,8 +294,8 @@ class LocalDecoder(nn.Module):
         a.leaky = int(self.leaky)
         a.variant = int(self.kernel_variant)
         keep = [cl, w]
-        if a.variant in (2, 3, 4):
-            wtc = self._packed_weights_tc(mixed=(a.variant == 4))
+        if a.variant in (2, 3, 4, 5, 6):
+            wtc = self._packed_weights_tc(mixed=(a.variant in (4, 6)))
             a.weights_tc = wtc.data_ptr()
             keep.append(wtc)
         return a, keep
@@ -334,7 +335,7 @@ class LocalDecoder(nn.Module):
                 raise ValueError('c_img must have shape (B, N, c_dim)')
             cic = c_img.contiguous()
             a.c_img = cic.data_ptr() if self.c_dim else None
-            if a.variant in (2, 4) and self.c_dim:
+            if a.variant in (2, 4, 5, 6) and self.c_dim:
                 a.variant = 1  # per-query c_img tensor: packed-FFMA2 SIMT kernel
         a.logits = out.data_ptr()
         if contact:
@@ -501,7 +502,7 @@ class LocalDecoder(nn.Module):
             if cic.size(0) != nx ** 3:
                 raise ValueError('dense c_img must have nx^3 rows')
             a.c_img = cic.data_ptr()
-            if a.variant in (2, 4):
+            if a.variant in (2, 4, 5, 6):
                 a.variant = 1
         if use_img and tips is not None:
             pos, feat, touch, radius = tips

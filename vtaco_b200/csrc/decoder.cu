@@ -480,8 +480,9 @@ extern "C" int vtaco_decoder_forward(const vtaco_decoder_args* a, void* stream) 
     }
     P.mcast = a->logits_multicast;
   }
-  P.tc_products = (a->variant == 3) ? 1 : (a->variant == 4) ? 2 : 3;
-  if (a->variant >= 2 && a->variant <= 4) return launch_decoder_tc(P, dense, a->weights_tc, st);
+  P.tc_products = (a->variant == 3) ? 1 : (a->variant == 4 || a->variant == 6) ? 2 : 3;
+  P.tc_split = (a->variant == 5 || a->variant == 6) ? 2 : 1;
+  if (a->variant >= 2 && a->variant <= 6) return launch_decoder_tc(P, dense, a->weights_tc, st);
   const bool f2 = (a->variant == 1);
   if (dense) return f2 ? launch_decoder<true, true>(P, smem_bytes, st) : launch_decoder<true, false>(P, smem_bytes, st);
   return f2 ? launch_decoder<false, true>(P, smem_bytes, st) : launch_decoder<false, false>(P, smem_bytes, st);

@@ -31,7 +31,8 @@ struct DecParams {
   float* peers[8];   // dense multi-GPU: logit grids of all ranks (fused all-gather)
   float* mcast;      // NVLS multicast alias of those grids (one multimem.st reaches every rank) or NULL
   int n_peers;
-  int tc_products;   // 3 = 3xTF32 (fp32 fidelity); 1 = single TF32 product (variant 3: timing experiments, ~1e-3 accuracy)
+  int tc_products;   // 3 = 3xTF32 (fp32 fidelity); 2 = TF32 main + BF16 corrections; 1 = single TF32 product (variant 3: timing experiments, ~1e-3 accuracy)
+  int tc_split;      // tcgen05 kernels: threads per query (1 | 2)
   int t_nbx, t_nby, t_nbz, t_xend;  // tcgen05 kernel, dense mode: 2x2x32 bricks and slab end row
   NormConst nc;
   double tips[VTACO_MAX_TIPS][3];
