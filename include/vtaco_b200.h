@@ -361,6 +361,13 @@ int vtaco_group_norm(const float* x, float* y, const float* gamma, const float* 
 int vtaco_group_norm_cl(const float* x, float* y, const float* gamma, const float* beta, int32_t N, int32_t C,
                         int32_t G, int64_t S, double eps, double* stats_ws, void* stream);
 
+/* UNet3D decoder input in one pass (src/encoder/unet3d.py Decoder.forward):
+ * out [N][C1+C2][Do][Ho][Wo] = cat(skip [N][C1][Do][Ho][Wo], nearest-upsample(x [N][C2][Di][Hi][Wi]), dim=1),
+ * contiguous NCDHW fp32, ATen's nearest source index min(floor(dst * in/out), in-1).
+ * Wo % 4 != 0 -> VTACO_ERR_UNSUPPORTED. */
+int vtaco_upsample_concat3d(const float* skip, const float* x, float* out, int32_t N, int32_t C1, int32_t C2,
+                            int32_t Do, int32_t Ho, int32_t Wo, int32_t Di, int32_t Hi, int32_t Wi, void* stream);
+
 /* ------------------------------------------------------------------------- *
  * (4) self-measured FP32 FMA peak (roofline denominator of the decoder).
  * Runs a register-resident FMA loop on every SM and returns achieved FLOP/s in

@@ -182,3 +182,21 @@ def test_group_norm_kernel(shape, groups):
         got_cl = gn(xcl)                      # channels-last kernel where the shape allows it
     assert close(got.cpu().numpy(), ref.cpu().numpy()) < 1e-5
     assert got_cl.shape == ref.shape and close(got_cl.contiguous().cpu().numpy(), ref.cpu().numpy()) < 1e-5
+
+
+@pytest.mark.parametrize('shape', [((2, 8, 16, 16, 16), (2, 16, 8, 8, 8)), ((1, 3, 12, 8, 16), (1, 5, 5, 3, 7)),
+                                   ((1, 32, 64, 64, 64), (1, 64, 32, 32, 32))])
+def test_upsample_concat_bit_exact(shape):
+    """fused UNet3D decoder input == cat(skip, F.interpolate(x, size, 'nearest')) bit for bit."""
+    import torch.nn.functional as F
+    from vtaco_b200.encoder.unet3d import _upsample_concat
+    s_shape, x_shape = shape
+    skip = torch.from_numpy(rs_randn(1, *s_shape)).cuda()
+    x = torch.from_numpy(rs_randn(2, *x_shape)).cuda()
+    ref = torch.cat((skip, F.interpolate(x, size=skip.shape[2:], mode='nearest')), dim=1)
+    with torch.no_grad():
+        got = _upsample_concat(skip, x)
+    assert got.shape == ref.shape and torch.equal(got, ref)
+    xs = x.clone().requires_grad_(True)          # autograd path: the two ATen ops
+    out = _upsample_concat(skip, xs)
+    assert out.requires_grad and torch.equal(out.detach(), ref)

@@ -738,3 +738,61 @@ extern "C" int vtaco_group_norm_cl(const float* x, float* y, const float* gamma,
   VTACO_LAUNCH_CHECK();
   return VTACO_OK;
 }
+
+// ---------------------------------------------------------------------------------------
+// UNet3D decoder input (reference src/encoder/unet3d.py Decoder.forward / _joining):
+//   out = cat(skip, interpolate(x, size = skip.shape[2:], mode='nearest'), dim=1)
+// in one pass over the output instead of ATen's upsample (writes C2 x S) + cat (reads and
+// writes (C1 + C2) x S).  Contiguous NCDHW fp32; source index as ATen's
+// nearest_neighbor_compute_source_index: min(floor(dst * (float)in / out), in - 1).
+// ---------------------------------------------------------------------------------------
+namespace vtaco {
+
+__global__ void __launch_bounds__(256) upsample_concat3d_kernel(const float* __restrict__ skip, const float* __restrict__ x,
+                                                                float* __restrict__ out, int C1, int C2, int Do, int Ho,
+                                                                int Wo, int Di, int Hi, int Wi, float sd, float sh,
+                                                                float sw, long long quads) {
+  const long long So = (long long)Do * Ho * Wo, Si = (long long)Di * Hi * Wi;
+  const int Wq = Wo >> 2;
+  for (long long q = (long long)blockIdx.x * 256 + threadIdx.x; q < quads; q += (long long)gridDim.x * 256) {
+    long long t = q;
+    const int xq = (int)(t % Wq); t /= Wq;
+    const int y = (int)(t % Ho); t /= Ho;
+    const int z = (int)(t % Do); t /= Do;
+    const int c = (int)(t % (C1 + C2));
+    const long long n = t / (C1 + C2);
+    const long long o = ((n * (C1 + C2) + c) * So + ((long long)z * Ho + y) * Wo) + 4 * xq;
+    float4 v;
+    if (c < C1) {
+      v = __ldg(reinterpret_cast<const float4*>(skip + (n * C1 + c) * So + ((long long)z * Ho + y) * Wo + 4 * xq));
+    } else {
+      const int zi = min((int)floorf(z * sd), Di - 1), yi = min((int)floorf(y * sh), Hi - 1);
+      const float* row = x + (n * C2 + (c - C1)) * Si + ((long long)zi * Hi + yi) * Wi;
+      const int x0 = 4 * xq;
+      v.x = __ldg(row + min((int)floorf(x0 * sw), Wi - 1));
+      v.y = __ldg(row + min((int)floorf((x0 + 1) * sw), Wi - 1));
+      v.z = __ldg(row + min((int)floorf((x0 + 2) * sw), Wi - 1));
+      v.w = __ldg(row + min((int)floorf((x0 + 3) * sw), Wi - 1));
+    }
+    *reinterpret_cast<float4*>(out + o) = v;
+  }
+}
+
+}  // namespace vtaco
+
+extern "C" int vtaco_upsample_concat3d(const float* skip, const float* x, float* out, int32_t N, int32_t C1, int32_t C2,
+                                       int32_t Do, int32_t Ho, int32_t Wo, int32_t Di, int32_t Hi, int32_t Wi,
+                                       void* stream) {
+  if (!skip || !x || !out || N <= 0 || C1 <= 0 || C2 <= 0 || Do <= 0 || Ho <= 0 || Wo <= 0 || Di <= 0 || Hi <= 0 || Wi <= 0)
+    return VTACO_ERR_INVALID_ARG;
+  if (Wo % 4) return VTACO_ERR_UNSUPPORTED;   // float4 rows; callers fall back to two ATen ops
+  const long long quads = (long long)N * (C1 + C2) * Do * Ho * (Wo / 4);
+  long long blocks = (quads + 255) / 256;
+  const long long cap = (long long)vtaco::num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  vtaco::upsample_concat3d_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      skip, x, out, C1, C2, Do, Ho, Wo, Di, Hi, Wi, (float)Di / (float)Do, (float)Hi / (float)Ho, (float)Wi / (float)Wo,
+      quads);
+  VTACO_LAUNCH_CHECK();
+  return VTACO_OK;
+}
