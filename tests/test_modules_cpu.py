@@ -135,3 +135,41 @@ def test_off_roundtrip(tmp_path):
     assert v3.shape == (3, 3) and f3.tolist() == [[0, 1, 2]]
     with pytest.raises(ValueError):
         export_off(path, v, np.array([[0, 1, 50]]))
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """sizeof / offsetof of every argument struct of include/vtaco_b200.h as a C compiler lays it
+    out == the ctypes mirror the Python side passes through the ABI."""
+    import ctypes as C
+    import os
+    import shutil
+    import subprocess
+    from vtaco_b200 import _abi
+    from vtaco_b200.encoder.pointnet import EncoderArgs, EncoderBwdArgs
+    if shutil.which('gcc') is None:
+        pytest.skip('no C compiler')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    structs = {'vtaco_decoder_args': _abi.DecoderArgs, 'vtaco_decoder_bwd_args': _abi.DecoderBwdArgs,
+               'vtaco_encoder_args': EncoderArgs, 'vtaco_encoder_bwd_args': EncoderBwdArgs,
+               'vtaco_mc_args': _abi.McArgs}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "vtaco_b200.h"', 'int main(void) {']
+    for cname, cls in structs.items():
+        lines.append('  printf("%s sizeof %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('  printf("%s %s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines += ['  return 0;', '}']
+    src = tmp_path / 'layout.c'
+    src.write_text('\n'.join(lines))
+    exe = str(tmp_path / 'layout')
+    subprocess.run(['gcc', '-std=c99', '-I', os.path.join(root, 'include'), str(src), '-o', exe], check=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout.split('\n')
+    seen = 0
+    for ln in out:
+        if not ln:
+            continue
+        cname, field, val = ln.split()
+        cls = structs[cname]
+        want = C.sizeof(cls) if field == 'sizeof' else getattr(cls, field).offset
+        assert int(val) == want, (cname, field, int(val), want)
+        seen += 1
+    assert seen == sum(len(c._fields_) + 1 for c in structs.values())

@@ -115,6 +115,8 @@ _OPTIONAL = {
                             C.c_double, C.c_void_p, C.c_void_p],
     'vtaco_group_norm': [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64,
                          C.c_double, C.c_void_p, C.c_void_p],
+    'vtaco_upsample_concat3d': [C.c_void_p] * 3 + [C.c_int32] * 9 + [C.c_void_p],
+    'vtaco_chamfer': [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int64] + [C.c_void_p] * 7,
 }
 
 

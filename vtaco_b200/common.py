@@ -91,7 +91,6 @@ def dense_axis(nx, padding=0.1, device=None):
 # computes right after mesh extraction (generation.py:281); SURVEY §8f-4.
 # --------------------------------------------------------------------------- #
 def _chamfer(points1, points2, want_idx):
-    import ctypes as C
     _abi.require_cuda(points1, 'points1')
     _abi.require_cuda(points2, 'points2')
     if points1.dim() != 3 or points2.dim() != 3 or points1.size(2) != 3 or points2.size(2) != 3:
@@ -109,7 +108,6 @@ def _chamfer(points1, points2, want_idx):
     c1 = torch.empty(B, dtype=torch.float32, device=dev)
     c2 = torch.empty(B, dtype=torch.float32, device=dev)
     L = _abi.lib()
-    L.vtaco_chamfer.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int64] + [C.c_void_p] * 7
     with torch.cuda.device(dev):
         st = L.vtaco_chamfer(_abi.ptr(p1), _abi.ptr(p2), B, T1, T2, _abi.ptr(d12), _abi.ptr(i12), _abi.ptr(d21),
                              _abi.ptr(i21), _abi.ptr(c1), _abi.ptr(c2), _abi.stream_ptr(dev))

@@ -50,13 +50,11 @@ def _upsample_concat(skip, x):
     if (skip.is_cuda and x.is_cuda and skip.dtype == torch.float32 and x.dtype == torch.float32 and skip.dim() == 5
             and skip.size(4) % 4 == 0 and skip.is_contiguous() and x.is_contiguous()
             and not (torch.is_grad_enabled() and (skip.requires_grad or x.requires_grad))):
-        import ctypes as C
         from .. import _abi
         N, C1, Do, Ho, Wo = skip.shape
         C2, Di, Hi, Wi = x.shape[1:]
         out = torch.empty((N, C1 + C2, Do, Ho, Wo), dtype=torch.float32, device=skip.device)
         L = _abi.lib()
-        L.vtaco_upsample_concat3d.argtypes = [C.c_void_p] * 3 + [C.c_int32] * 9 + [C.c_void_p]
         with torch.cuda.device(skip.device):
             st = L.vtaco_upsample_concat3d(_abi.ptr(skip), _abi.ptr(x), _abi.ptr(out), N, C1, C2, Do, Ho, Wo, Di, Hi, Wi,
                                            _abi.stream_ptr(skip.device))
