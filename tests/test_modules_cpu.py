@@ -173,3 +173,22 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
         assert int(val) == want, (cname, field, int(val), want)
         seen += 1
     assert seen == sum(len(c._fields_) + 1 for c in structs.values())
+
+
+def test_c_example_compiles_and_links(tmp_path):
+    """examples/dense_extract.c (the ABI used from plain C) builds against the header and the library."""
+    import os
+    import shutil
+    import subprocess
+    from vtaco_b200 import _abi
+    if shutil.which('gcc') is None or not os.path.exists(_abi.LIB_PATH):
+        pytest.skip('needs gcc and the built library')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cuda_lib = '/usr/local/cuda/lib64'
+    if not os.path.exists(os.path.join(cuda_lib, 'libcudart.so')):
+        pytest.skip('no libcudart to link against')
+    exe = str(tmp_path / 'dense_extract')
+    r = subprocess.run(['gcc', '-std=c99', '-Wall', '-Werror', '-I', os.path.join(root, 'include'),
+                        os.path.join(root, 'examples', 'dense_extract.c'), '-L', os.path.dirname(_abi.LIB_PATH),
+                        '-lvtaco_b200', '-L', cuda_lib, '-lcudart', '-lm', '-o', exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
