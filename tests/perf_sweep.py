@@ -1,6 +1,10 @@
 """BASELINE.json configs[1], [2], [4]: shape sweep of the hot-path kernels on one B200
 (device-resident inputs, CUDA-event timing, median of 5 after 2 warm-ups) with the reference CPU
-path (oracle port) timed on bounded sizes.  Writes gpurun_out/sweep.json."""
+path (oracle port) timed on bounded sizes.  Writes gpurun_out/sweep.json.
+
+Lives under tests/ (not tools/) because it times the oracle as the CPU baseline, and only tests/,
+smoke() and bench.py's baseline legs may execute oracle/.  Not collected by pytest; run it as
+`python tests/perf_sweep.py` on the GPU box."""
 import json
 import os
 import sys
