@@ -10,7 +10,11 @@
  *
  * Conventions
  *  - plain pointers + sizes only; every pointer is a DEVICE pointer unless the
- *    name ends in _host.  No torch types, no allocation, no global state.
+ *    name ends in _host.  No torch types, no allocation.  Process-wide state is limited to
+ *    idempotent caches held in atomics (SM count per device, the one-time opt-in of each
+ *    kernel to its dynamic shared-memory size per device) and a THREAD-LOCAL copy of the last
+ *    CUDA error for vtaco_last_cuda_error(): entry points may be called from several host
+ *    threads; calls that share a stream are ordered by that stream as usual.
  *  - `stream` is a cudaStream_t passed as void*; all work is enqueued on it and
  *    the call returns without synchronising.
  *  - return value: 0 on success, negative vtaco_status on error (never throws).
@@ -103,6 +107,9 @@ int vtaco_relayout_cf(const float* src, float* dst, int B, int C, int64_t S, voi
 #define VTACO_DEC_TAIL 68
 #define VTACO_DEC_PACKED_FLOATS(n_blocks) (VTACO_DEC_OFF_BLOCKS + VTACO_DEC_BLOCK_STRIDE * (n_blocks) + VTACO_DEC_TAIL)
 #define VTACO_MAX_TIPS 8
+#define VTACO_MAX_BLOCKS 8   /* n_blocks the shared-memory-resident kernels can hold */
+/* floats of the tcgen05 operand buffer `weights_tc` (layout below) */
+#define VTACO_DEC_TC_FLOATS(n_blocks) (3 * (n_blocks) * 2048 + (2 * (n_blocks) + 1) * 256 + 2048)
 
 typedef struct vtaco_decoder_args {
   /* ---- queries ---- */
@@ -150,7 +157,10 @@ typedef struct vtaco_decoder_args {
    *   variants 4 and 6: the lo block instead holds 2048 BF16 values, the K = 64 correction operand
    *   [bf16(W) ; bf16(W - hi)], bf16 index of (n, k) = (k/8)*256 + (n/8)*64 + (n%8)*8 + (k%8);
    * followed by 2*n_blocks+1 bias K-blocks of 256 floats in the same layout with k in [0,8): row k=0
-   * = bias hi, k=1 = bias lo, for the steps bc_0 | b0_i, b1_i + bc_{i+1} (i = 0..n_blocks-1). */
+   * = bias hi, k=1 = bias lo, for the steps bc_0 | b0_i, b1_i + bc_{i+1} (i = 0..n_blocks-1);
+   * followed by one more 2048-float matrix block in the matrix layout: fc_p_img.weight[:, 3:]
+   * (the product with a per-query c_img tensor, decoder.py:83-85).  VTACO_DEC_TC_FLOATS floats in
+   * total; vtaco_decoder_pack_tc builds the buffer from `weights`. */
   const float* weights_tc;
   /* dense mode, multi-GPU: when n_peers > 0 every logit of the slab is stored to
    * logits_peers[0..n_peers) instead of `logits` — the (nx,nx,nx) grids of all ranks (own one
@@ -210,6 +220,27 @@ typedef struct vtaco_decoder_bwd_args {
 } vtaco_decoder_bwd_args;
 size_t vtaco_decoder_backward_workspace_bytes(int64_t total_queries, int32_t n_blocks);
 int vtaco_decoder_backward(const vtaco_decoder_bwd_args* args, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * (4c) Weight packing, one launch each.  nn.Linear stores weight[out][in]; the kernels read
+ * K-major "[in][out]" blocks (layouts above / below).  A descriptor copies one parameter:
+ * element (n = out, k = in) = src[n*src_stride + src_col0 + k] -> dst[dst_off + k*out_dim + n]
+ * (bias vectors: in_dim = 1).  At most VTACO_PACK_MAX_DESCS descriptors per call; `dst` must be
+ * zero-initialised where no descriptor writes (padding, absent fc_c when c_dim = 0).
+ * vtaco_decoder_pack_tc derives the tcgen05 operand buffer (`weights_tc`, VTACO_DEC_TC_FLOATS
+ * floats, every float written) from the packed decoder buffer; mixed = 1 for variants 4 / 6.
+ * ------------------------------------------------------------------------- */
+#define VTACO_PACK_MAX_DESCS 64
+typedef struct vtaco_pack_desc {
+  const float* src;
+  int32_t out_dim, in_dim;
+  int32_t src_stride;
+  int32_t src_col0;
+  int32_t dst_off;
+} vtaco_pack_desc;
+int vtaco_pack_linear(const vtaco_pack_desc* descs_host, int32_t n_descs, float* dst, int64_t dst_floats, void* stream);
+int64_t vtaco_decoder_tc_floats(int32_t n_blocks);
+int vtaco_decoder_pack_tc(const float* packed, int32_t n_blocks, int32_t mixed, float* dst, void* stream);
 
 /* decode an ordered-int key written by the decoder / encoder kernels back to float (host helper) */
 float vtaco_key_to_float_host(int32_t key);

@@ -1,0 +1,307 @@
+"""Parity AT THE BENCHMARKED CONFIGURATION (BASELINE.json configs[3]: VTacOH dense 256^3 lattice,
+grid-64 features, forward_img with fingertip conditioning) — the default tcgen05 dense kernel
+against the oracle, plus the reference-signature wrappers and the regression tests for the
+round-1 advisor findings.  Tolerance (north_star): |a-b| <= 1e-4 * max(1, |b|)."""
+import numpy as np
+import pytest
+import torch
+
+from util import load, weights, close, rs_randn
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _decoder(W, division='true'):
+    from vtaco_b200.conv_onet.models import decoder_dict
+    dec = decoder_dict['simple_local'](dim=3, c_dim=32, padding=0.1, with_contact='fc_out_contact.weight' in W,
+                                       sample_mode='bilinear', hidden_size=32)
+    dec.load_state_dict(W, strict=True)
+    dec = dec.cuda().eval()
+    dec.division = division
+    return dec
+
+
+def _scene(seed=0):
+    rs = np.random.RandomState(seed)
+    tips = rs.uniform(-0.35, 0.35, size=(5, 3)).astype(np.float64)
+    tip_feat = rs.randn(5, 32).astype(np.float32)
+    touch = np.array([True, True, False, True, True])
+    return tips, tip_feat, touch
+
+
+@pytest.mark.parametrize('variant', [5, 6, 2])
+def test_dense_256_slabs_vs_oracle(variant):
+    """forward_dense(nx=256, R=64, use_img, tips) on x-slabs (first, one through a touching
+    fingertip, one through the untouched fingertip, last) == oracle.eval_points on the same rows
+    with the dense fingertip c_img_all of generation.py:190-200."""
+    from oracle import convonet as oc
+    g = load('decoder_relu.npz')
+    W = weights(g)
+    dec = _decoder(W)
+    dec.kernel_variant = variant
+    nx, R = 256, 64
+    feats = {'grid': torch.from_numpy(rs_randn(11, 1, 32, R, R, R))}
+    c = {'grid': feats['grid'].cuda()}
+    tips, tip_feat, touch = _scene()
+    ax = 1.1 * torch.linspace(-0.5, 0.5, nx)
+    rows_of = lambda x: int(np.argmin(np.abs(ax.numpy() - x)))   # noqa: E731
+    slabs = [(0, 2), (rows_of(tips[0, 0]) // 2 * 2, rows_of(tips[0, 0]) // 2 * 2 + 2),
+             (rows_of(tips[2, 0]) // 2 * 2, rows_of(tips[2, 0]) // 2 * 2 + 2), (nx - 2, nx)]
+    out = torch.full((nx, nx, nx), float('nan'), device='cuda')
+    tips_arg = (tips, torch.from_numpy(tip_feat).cuda(), touch, 0.05)
+    hit_rows = 0
+    with torch.no_grad():
+        for x0, x1 in slabs:
+            dec.forward_dense(c, nx, x0=x0, x1=x1, use_img=True, tips=tips_arg, out=out)
+            gx, gy, gz = torch.meshgrid(ax[x0:x1], ax, ax, indexing='ij')
+            p = torch.stack([gx, gy, gz], -1).reshape(-1, 3).contiguous()
+            c_img = oc.fingertip_c_img(p, tips, torch.from_numpy(tip_feat), touch, 0.05)
+            hit_rows += int((c_img.abs().sum(1) > 0).sum())
+            ref = oc.eval_points(p, feats, W, c_img)
+            got = out[x0:x1].reshape(-1).cpu().numpy()
+            assert close(got, ref.numpy()) < TOL, (variant, x0)
+    assert hit_rows > 100   # the fingertip rows are really exercised
+    covered = set()
+    for a, b in slabs:
+        covered |= set(range(a, b))
+    assert torch.isnan(out).sum().item() == (nx - len(covered)) * nx * nx   # slabs write nothing outside their rows
+
+
+@pytest.mark.parametrize('variant', [5, 6])
+def test_dense_equals_flat_256_slab(variant):
+    """dense mode == flat mode on 16 rows of the 256^3 lattice (R=64: the separable z-run gather's
+    zmin/zmax arithmetic at the benchmarked size), and the same rows with a per-query c_img tensor."""
+    g = load('decoder_relu.npz')
+    dec = _decoder(weights(g))
+    dec.kernel_variant = variant
+    nx, R = 256, 64
+    c = {'grid': torch.from_numpy(rs_randn(12, 1, 32, R, R, R)).cuda()}
+    ax = 1.1 * torch.linspace(-0.5, 0.5, nx)
+    tips, tip_feat, touch = _scene(1)
+    tips_arg = (tips, torch.from_numpy(tip_feat).cuda(), touch, 0.05)
+    with torch.no_grad():
+        for x0 in (0, 120, 240):
+            x1 = x0 + 16
+            gx, gy, gz = torch.meshgrid(ax[x0:x1], ax, ax, indexing='ij')
+            p = torch.stack([gx, gy, gz], -1).reshape(1, -1, 3).contiguous().cuda()
+            flat = dec(p, c)[0]
+            out = torch.zeros(nx, nx, nx, device='cuda')
+            dec.forward_dense(c, nx, x0=x0, x1=x1, out=out)
+            assert close(out[x0:x1].reshape(-1).cpu().numpy(), flat.cpu().numpy()) < 1e-5
+            # fingertip conditioning: compact form (dense) == explicit c_img tensor (flat, tcgen05 path)
+            from oracle import convonet as oc
+            c_img = oc.fingertip_c_img(p[0].cpu(), tips, torch.from_numpy(tip_feat), touch, 0.05).cuda()[None]
+            flat_img = dec.forward_img(p, c, c_img)[0]
+            dec.forward_dense(c, nx, x0=x0, x1=x1, use_img=True, tips=tips_arg, out=out)
+            assert close(out[x0:x1].reshape(-1).cpu().numpy(), flat_img.cpu().numpy()) < 1e-5
+
+
+def test_generator_eval_points_golden():
+    """Generator3D.eval_points itself (host tensor in, host tensor out; reference
+    generation.py:338-383) against the fixture produced by the reference's eval_points."""
+    from vtaco_b200.conv_onet.models import ConvolutionalOccupancyNetwork
+    from vtaco_b200.conv_onet.generation import Generator3D
+    from vtaco_b200.common import make_3d_grid
+    from oracle import convonet as oc
+    g = load('eval_points.npz')
+    W = weights(g)
+    dec = _decoder(W)
+    net = ConvolutionalOccupancyNetwork(dec, None, device='cuda')
+    nx, Rg = int(g['nx']), int(g['Rg'])
+    c = {'grid': torch.from_numpy(rs_randn(int(g['feat_seed']), 1, 32, Rg, Rg, Rg)).cuda()}
+    pts = 1.1 * make_3d_grid((-0.5,) * 3, (0.5,) * 3, (nx,) * 3)            # host tensor, like the reference
+    gen = Generator3D(net, device='cuda', resolution0=nx // 4, with_img=False, padding=0.1, input_type='pointcloud')
+    out = gen.eval_points(pts, c)
+    assert out.device.type == 'cpu' and out.shape == (nx ** 3,)
+    assert close(out.numpy(), g['logits']) < TOL
+    gen_img = Generator3D(net, device='cuda', resolution0=nx // 4, with_img=True, padding=0.1, input_type='pointcloud')
+    c_img_all = oc.fingertip_c_img(pts, g['tips'].astype(np.float64), torch.from_numpy(g['tip_feat']), g['touch'], 0.05)
+    out = gen_img.eval_points(pts, c, c_img_all[None])                      # (1, N, 32) host tensor
+    assert out.device.type == 'cpu' and close(out.numpy(), g['logits_img']) < TOL
+    # the generator's own dense fast path agrees with its reference-signature method
+    grid, _ = gen_img.eval_lattice(c, tips=(g['tips'].astype(np.float64), torch.from_numpy(g['tip_feat']).cuda(),
+                                            g['touch'], 0.05))
+    assert close(grid.reshape(-1).cpu().numpy(), out.numpy()) < 1e-5
+
+
+def test_feature_cache_not_stale_after_free():
+    """two different contiguous (NCDHW) grids of one shape decoded back to back,
+    the first freed in between — the caching allocator hands the second the same address and
+    version; the channels-last cache must not serve the first one's copy."""
+    g = load('decoder_relu.npz')
+    dec = _decoder(weights(g))
+    p = torch.from_numpy(g['p']).cuda()[:1]
+    R = 16
+
+    def run(seed):
+        t = torch.from_numpy(rs_randn(seed, 1, 32, R, R, R)).cuda()          # plain contiguous: the copy path
+        with torch.no_grad():
+            o = dec(p, {'grid': t}).clone()
+        return o, t.data_ptr()
+
+    o1, a1 = run(1)
+    o2, a2 = run(2)
+    with torch.no_grad():
+        ref2 = dec(p, {'grid': torch.from_numpy(rs_randn(2, 1, 32, R, R, R)).cuda().contiguous(
+            memory_format=torch.channels_last_3d)})
+    assert not torch.equal(o1, o2)
+    assert torch.equal(o2, ref2), 'stale channels-last copy served (same address %s)' % (a1 == a2)
+    # in-place update of a live tensor bumps _version -> re-copied
+    t = torch.from_numpy(rs_randn(3, 1, 32, R, R, R)).cuda()
+    with torch.no_grad():
+        a = dec(p, {'grid': t}).clone()
+        t.mul_(2.0)
+        b = dec(p, {'grid': t})
+    assert not torch.equal(a, b)
+
+
+def test_query_points_requiring_grad_and_data_updates():
+    """ADVICE r1 (medium x2): the reference builds p with requires_grad=True (training.py:310) —
+    must not raise, p.grad stays None; `.data` updates are picked up in training mode and after
+    invalidate() under no_grad."""
+    g = load('decoder_relu.npz')
+    dec = _decoder(weights(g))
+    feats = {'grid': torch.from_numpy(rs_randn(4, 2, 32, 16, 16, 16)).cuda()}
+    p = torch.from_numpy(g['p']).cuda().clone().requires_grad_(True)
+    c_img = torch.from_numpy(g['c_img']).cuda()
+    o = dec.forward_img(p, feats, c_img)
+    o.sum().backward()
+    assert p.grad is None and dec.fc_out.weight.grad is not None
+    with torch.no_grad():
+        before = dec(p.detach(), feats).clone()
+    dec.fc_out.bias.data.add_(1.0)                 # does not bump _version
+    dec.invalidate()
+    with torch.no_grad():
+        after = dec(p.detach(), feats)
+    assert torch.allclose(after, before + 1.0, atol=1e-5)
+    dec.fc_out.bias.data.add_(1.0)                 # training mode: re-packed on every call
+    o2 = dec(p.detach(), feats)
+    assert o2.requires_grad and torch.allclose(o2.detach(), before + 2.0, atol=1e-5)
+
+
+def test_pack_kernels_match_torch_packing():
+    """vtaco_pack_linear / vtaco_decoder_pack_tc == the slice-assign packing they replace."""
+    from vtaco_b200 import _abi
+    from vtaco_b200.encoder import encoder_dict
+    g = load('decoder_relu.npz')
+    dec = _decoder(weights(g))
+    nb = dec.n_blocks
+    buf = torch.zeros(_abi.dec_packed_floats(nb), device='cuda')
+    with torch.no_grad():
+        buf[0:96] = dec.fc_p.weight.t().reshape(-1)
+        buf[96:128] = dec.fc_p.bias
+        wpi = dec.fc_p_img.weight
+        buf[128:224] = wpi[:, :3].t().reshape(-1)
+        buf[224:256] = dec.fc_p_img.bias
+        buf[256:1280] = wpi[:, 3:].t().reshape(-1)
+        for i in range(nb):
+            o = _abi.DEC_OFF_BLOCKS + i * _abi.DEC_BLOCK_STRIDE
+            buf[o:o + 1024] = dec.fc_c[i].weight.t().reshape(-1)
+            buf[o + 1024:o + 1056] = dec.fc_c[i].bias
+            buf[o + 1056:o + 2080] = dec.blocks[i].fc_0.weight.t().reshape(-1)
+            buf[o + 2080:o + 2112] = dec.blocks[i].fc_0.bias
+            buf[o + 2112:o + 3136] = dec.blocks[i].fc_1.weight.t().reshape(-1)
+            buf[o + 3136:o + 3168] = dec.blocks[i].fc_1.bias
+        o = _abi.DEC_OFF_BLOCKS + nb * _abi.DEC_BLOCK_STRIDE
+        buf[o:o + 32] = dec.fc_out.weight.reshape(-1)
+        buf[o + 64] = dec.fc_out.bias[0]
+        if hasattr(dec, 'fc_out_contact'):
+            buf[o + 32:o + 64] = dec.fc_out_contact.weight.reshape(-1)
+            buf[o + 65] = dec.fc_out_contact.bias[0]
+    assert torch.equal(dec._packed_weights(), buf)
+
+    def split(w):
+        hi = ((w.contiguous().view(torch.int32) + 0x1000) & ~0x1fff).view(torch.float32)
+        lo = ((w - hi).view(torch.int32) & ~0x1fff).view(torch.float32)
+        return hi, lo
+
+    n = torch.arange(32, device='cuda').view(32, 1)
+    k = torch.arange(32, device='cuda').view(1, 32)
+    idx = ((k // 4) * 128 + (n // 8) * 32 + (n % 8) * 4 + (k % 4)).reshape(-1)
+    k64 = torch.arange(64, device='cuda').view(1, 64)
+    idx16 = ((k64 // 8) * 256 + (n // 8) * 64 + (n % 8) * 8 + (k64 % 8)).reshape(-1)
+    mats = []
+    for i in range(nb):
+        mats += [dec.fc_c[i].weight, dec.blocks[i].fc_0.weight, dec.blocks[i].fc_1.weight]
+    mats.append(dec.fc_p_img.weight[:, 3:])
+    for mixed in (False, True):
+        got = dec._packed_weights_tc(mixed=mixed)
+        assert got.numel() == _abi.dec_tc_floats(nb)
+        for m, w in enumerate(mats):
+            w = w.detach().float().contiguous()
+            hi, lo = split(w)
+            exp = torch.zeros(2, 1024, device='cuda')
+            exp[0, idx] = hi.reshape(-1)
+            if mixed:
+                exp[1].view(torch.bfloat16)[idx16] = torch.cat([w, w - hi], 1).to(torch.bfloat16).reshape(-1)
+            else:
+                exp[1, idx] = lo.reshape(-1)
+            off = m * 2048 if m < 3 * nb else 3 * nb * 2048 + (2 * nb + 1) * 256
+            assert torch.equal(got[off:off + 2048].view(torch.int32), exp.reshape(-1).view(torch.int32)), (mixed, m)
+        zero = torch.zeros(32, device='cuda')
+        steps = [dec.fc_c[0].bias.detach()]
+        for i in range(nb):
+            steps.append(dec.blocks[i].fc_0.bias.detach())
+            steps.append(dec.blocks[i].fc_1.bias.detach() + (dec.fc_c[i + 1].bias.detach() if i + 1 < nb else zero))
+        nn_ = torch.arange(32, device='cuda')
+        b0 = (nn_ // 8) * 32 + (nn_ % 8) * 4
+        for s_, b in enumerate(steps):
+            hi, lo = split(b.float())
+            exp = torch.zeros(256, device='cuda')
+            exp[b0] = hi
+            exp[b0 + 1] = lo
+            off = 3 * nb * 2048 + s_ * 256
+            assert torch.equal(got[off:off + 256], exp), (mixed, s_)
+    # encoder buffer
+    enc = encoder_dict['pointnet_local_pool'](dim=3, c_dim=32, hidden_dim=32, plane_type='grid', grid_resolution=16).cuda()
+    with torch.no_grad():
+        for b in enc.blocks:
+            b.fc_1.weight.normal_(0, 0.1)
+    ebuf = torch.zeros(256 + 5184 * enc.n_blocks + 1056, device='cuda')
+    with torch.no_grad():
+        ebuf[0:192] = enc.fc_pos.weight.t().reshape(-1)
+        ebuf[192:256] = enc.fc_pos.bias
+        for i, blk in enumerate(enc.blocks):
+            o = 256 + 5184 * i
+            ebuf[o:o + 2048] = blk.fc_0.weight.t().reshape(-1)
+            ebuf[o + 2048:o + 2080] = blk.fc_0.bias
+            ebuf[o + 2080:o + 3104] = blk.fc_1.weight.t().reshape(-1)
+            ebuf[o + 3104:o + 3136] = blk.fc_1.bias
+            ebuf[o + 3136:o + 5184] = blk.shortcut.weight.t().reshape(-1)
+        o = 256 + 5184 * enc.n_blocks
+        ebuf[o:o + 1024] = enc.fc_c.weight.t().reshape(-1)
+        ebuf[o + 1024:o + 1056] = enc.fc_c.bias
+    assert torch.equal(enc._packed_weights(), ebuf)
+
+
+@pytest.mark.parametrize('variant', [2, 5, 6])
+def test_forward_img_tensor_on_tcgen05(variant):
+    """forward_img with a per-query c_img tensor (the variant both shipped configs use,
+    decoder.py:71-103, VTacO_YCB.yaml:18) stays on the tcgen05 kernel: 10^5 random queries
+    (BASELINE config 1) and the training shape against the oracle; dense c_img_all too."""
+    from oracle import convonet as oc
+    g = load('decoder_relu.npz')
+    W = weights(g)
+    dec = _decoder(W)
+    dec.kernel_variant = variant
+    R = 32
+    for B, N in ((1, 100000), (4, 2048)):
+        feats = {'grid': torch.from_numpy(rs_randn(21, B, 32, R, R, R))}
+        rs = np.random.RandomState(22)
+        p = torch.from_numpy(rs.uniform(-0.55, 0.55, size=(B, N, 3)).astype(np.float32))
+        c_img = torch.from_numpy(rs.randn(B, N, 32).astype(np.float32)) * torch.from_numpy(
+            (rs.rand(B, N, 1) < 0.3).astype(np.float32))
+        with torch.no_grad():
+            ref = oc.decoder_forward(p, feats, W, 'img', c_img=c_img)
+            got = dec.forward_img(p.cuda(), {'grid': feats['grid'].cuda()}, c_img.cuda())
+        assert close(got.cpu().numpy(), ref.numpy()) < TOL
+    # dense lattice with an explicit (nx^3, 32) c_img_all, as Generator3D.eval_points receives it
+    nx = 24
+    feats = {'grid': torch.from_numpy(rs_randn(23, 1, 32, R, R, R))}
+    pts = oc.dense_grid_points(nx)
+    c_all = torch.from_numpy(rs_randn(24, nx ** 3, 32))
+    with torch.no_grad():
+        ref = oc.eval_points(pts, feats, W, c_all)
+        got = dec.forward_dense({'grid': feats['grid'].cuda()}, nx, use_img=True, c_img=c_all.cuda())
+    assert close(got.reshape(-1).cpu().numpy(), ref.numpy()) < TOL

@@ -101,3 +101,56 @@ def test_rescale_matches_reference_formula():
     v = np.array([[0, 64, 128]], dtype=np.float32)
     out = mc.rescale_vertices(v, 128)
     assert np.allclose(out, [[-0.55, 0.0, 0.55]])
+
+
+# ------------------------------------------------------------------------------------------------
+# Cross-check against scikit-image where it is importable ("if skimage turns out to be
+# importable, add a cross-check there; do not assume it").  It is NOT installed in the build
+# container nor on the GPU image, so this is skipped there and Lewiner parity stays UNPINNED; on a
+# machine that has it, this is the test that pins (or refutes) it.
+# ------------------------------------------------------------------------------------------------
+import importlib.util
+
+_HAS_SKIMAGE = importlib.util.find_spec('skimage') is not None
+
+
+def _canonical(verts, faces, decimals=4):
+    """order-independent form: vertices rounded and sorted; faces as sorted rows of rotation-normalised
+    triples of the vertices' sorted ranks."""
+    v = np.round(np.asarray(verts, dtype=np.float64), decimals)
+    order = np.lexsort((v[:, 2], v[:, 1], v[:, 0]))
+    rank = np.empty(len(v), dtype=np.int64)
+    rank[order] = np.arange(len(v))
+    f = rank[np.asarray(faces, dtype=np.int64)]
+    r = np.argmin(f, axis=1)
+    f = np.stack([f[np.arange(len(f)), (r + s) % 3] for s in range(3)], 1)   # rotate the smallest id first (keeps winding)
+    return v[order], f[np.lexsort((f[:, 2], f[:, 1], f[:, 0]))]
+
+
+@pytest.mark.skipif(not _HAS_SKIMAGE, reason='scikit-image not installed: Lewiner parity stays unpinned')
+@pytest.mark.parametrize('name', ['sphere', 'two_blobs', 'noise'])
+def test_cross_check_against_skimage(name):
+    from skimage import measure
+    x, y, z = lattice(40)
+    if name == 'sphere':
+        vol = (0.7 - np.sqrt(x * x + y * y + z * z)).astype(np.float32)
+    elif name == 'two_blobs':
+        vol = np.maximum(0.35 - np.sqrt((x - 0.45) ** 2 + y * y + z * z),
+                         0.35 - np.sqrt((x + 0.45) ** 2 + y * y + z * z)).astype(np.float32)
+    else:
+        vol = np.random.RandomState(0).randn(18, 19, 20).astype(np.float32)
+    sv, sf, _, _ = measure.marching_cubes(vol, gradient_direction='ascent')   # the reference's call, generation.py:270
+    v, f, _ = mc.marching_cubes(vol, None)
+    cv, cf = _canonical(v, f)
+    csv, csf = _canonical(sv, sf)
+    # table-independent parts must agree exactly: one vertex per cut edge at the same place
+    # (Lewiner may add interior vertices on ambiguous cells of the noise field only)
+    if name != 'noise':
+        assert cv.shape == csv.shape and np.abs(cv - csv).max() <= 1e-4
+        assert np.array_equal(cf, csf), 'triangulation differs from skimage on an unambiguous surface'
+    else:
+        assert len(csv) >= len(cv)
+        same = len(csf) == len(cf) and np.array_equal(cf, csf)
+        if not same:
+            pytest.xfail('ambiguous cases (3,4,6,7,10,12,13) are triangulated differently from skimage Lewiner: '
+                         '%d vs %d faces' % (len(cf), len(csf)))

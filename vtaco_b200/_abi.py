@@ -13,6 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'lib', 'libvtaco_b200.so')
 
 MAX_TIPS = 8
+MAX_BLOCKS = 8
 PLANE_XZ, PLANE_XY, PLANE_YZ, GRID = 0, 1, 2, 3
 KIND = {'xz': PLANE_XZ, 'xy': PLANE_XY, 'yz': PLANE_YZ, 'grid': GRID}
 DIV_RECIPROCAL, DIV_TRUE = 0, 1
@@ -68,6 +69,44 @@ class McArgs(C.Structure):
     ]
 
 
+class PackDesc(C.Structure):
+    _fields_ = [('src', C.c_void_p), ('out_dim', C.c_int32), ('in_dim', C.c_int32), ('src_stride', C.c_int32),
+                ('src_col0', C.c_int32), ('dst_off', C.c_int32)]
+
+
+PACK_MAX_DESCS = 64
+
+
+def dec_tc_floats(n_blocks):
+    return 3 * n_blocks * 2048 + (2 * n_blocks + 1) * 256 + 2048
+
+
+def pack_linear(entries, dst):
+    """One launch of vtaco_pack_linear.  entries: (tensor, dst_off[, col0, n_cols]) — an nn.Linear
+    weight (out,in) / bias (out,) goes K-major to dst[dst_off + k*out + n]."""
+    descs = (PackDesc * len(entries))()
+    keep = []
+    for d, e in zip(descs, entries):
+        t, off = e[0], e[1]
+        col0 = e[2] if len(e) > 2 else 0
+        t = t.detach()
+        if t.dtype != torch.float32 or not t.is_cuda:
+            raise TypeError('vtaco_b200: parameters must be float32 CUDA tensors')
+        if t.dim() == 1:
+            t = t.contiguous()
+            d.out_dim, d.in_dim, d.src_stride = t.shape[0], 1, 1
+        else:
+            if t.stride(1) != 1:
+                t = t.contiguous()
+            d.out_dim, d.src_stride = t.shape[0], t.stride(0)
+            d.in_dim = (e[3] if len(e) > 3 else t.shape[1] - col0)
+        keep.append(t)
+        d.src, d.src_col0, d.dst_off = t.data_ptr(), col0, off
+    with torch.cuda.device(dst.device):
+        st = lib().vtaco_pack_linear(descs, len(entries), ptr(dst), dst.numel(), stream_ptr(dst.device))
+    check(st, 'pack_linear')
+
+
 _lib = None
 
 
@@ -97,6 +136,10 @@ def lib():
     L.vtaco_key_to_float_host.restype = C.c_float
     L.vtaco_key_to_float_host.argtypes = [C.c_int32]
     L.vtaco_fp32_peak.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double), C.c_void_p]
+    L.vtaco_pack_linear.argtypes = [C.POINTER(PackDesc), C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]
+    L.vtaco_decoder_tc_floats.restype = C.c_int64
+    L.vtaco_decoder_tc_floats.argtypes = [C.c_int32]
+    L.vtaco_decoder_pack_tc.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
     for name, argtypes in _OPTIONAL.items():
         getattr(L, name).argtypes = argtypes
     L.vtaco_mc_scratch_bytes.restype = C.c_int64

@@ -12,7 +12,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'lib', 'libvtaco_b200.so')
-SOURCES = ['core.cu', 'decoder.cu', 'decoder_tc.cu', 'decoder_bwd.cu', 'encoder.cu', 'mcubes.cu', 'metrics.cu', 'tc_microbench.cu']
+SOURCES = ['core.cu', 'pack.cu', 'decoder.cu', 'decoder_tc.cu', 'decoder_bwd.cu', 'encoder.cu', 'mcubes.cu', 'metrics.cu']
+# debug / measurement kernels live in their own library (tools/ only), not in the product ABI
+BENCH_LIB = os.path.join(HERE, 'lib', 'libvtaco_microbench.so')
+BENCH_SOURCES = ['tc_microbench.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '--use_fast_math=false', '-Xcompiler', '-fPIC', '-Xcompiler', '-O2',
               '--fmad=true', '-Xptxas', '-v']
@@ -26,14 +29,14 @@ def _nvcc():
 
 
 def sources():
-    return [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    return [os.path.join(CSRC, s) for s in SOURCES + BENCH_SOURCES if os.path.exists(os.path.join(CSRC, s))]
 
 
 def needs_build():
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(BENCH_LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = sources() + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cuh', '.h'))]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cu', '.cuh', '.h', '.inl'))]
     deps.append(os.path.join(ROOT, 'include', 'vtaco_b200.h'))
     return any(os.path.getmtime(d) > t for d in deps)
 
@@ -55,10 +58,13 @@ def build(force=False, verbose=False):
         if pr.returncode != 0:
             raise RuntimeError('nvcc failed for %s:\n%s' % (src, out))
         objs.append(obj)
-    cmd = [_nvcc(), '-shared', '-o', LIB] + objs + ['-lcudart']
-    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    if r.returncode != 0:
-        raise RuntimeError('link failed:\n' + r.stdout)
+    bench_objs = [o for o in objs if os.path.basename(o)[:-2] + '.cu' in BENCH_SOURCES]
+    objs = [o for o in objs if o not in bench_objs]
+    for target, members in ((LIB, objs), (BENCH_LIB, bench_objs + [o for o in objs if os.path.basename(o) == 'core.o'])):
+        cmd = [_nvcc(), '-shared', '-o', target] + members + ['-lcudart']
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if r.returncode != 0:
+            raise RuntimeError('link failed:\n' + r.stdout)
     with open(os.path.join(HERE, 'lib', 'build.log'), 'w') as f:
         f.write('\n'.join(log))
     if verbose:

@@ -138,99 +138,76 @@ class LocalDecoder(nn.Module):
         if self.sample_mode not in _abi.SAMPLE:
             raise ValueError('sample_mode must be bilinear|nearest, got %r' % (self.sample_mode,))
 
+    def invalidate(self):
+        """Drop the packed-weight and channels-last caches.  They are keyed on each tensor's
+        (data_ptr, _version); an in-place update made through `param.data` (EMA / clipping code,
+        `w.data.normal_()`) does not bump `_version`, so call this after such an update when running
+        under torch.no_grad().  Not needed for training: with grad enabled every call re-packs (one
+        launch), and `.to()` / `load_state_dict` invalidate on their own."""
+        self._pack_cache = None
+        self._pack_tc_cache = None
+        self._cl_cache = {}
+
+    def _apply(self, fn, *args, **kwargs):
+        self.invalidate()
+        return super()._apply(fn, *args, **kwargs)
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self.invalidate()
+        return super()._load_from_state_dict(*args, **kwargs)
+
     def _packed_weights(self):
-        """Flat fp32 buffer in the layout documented in include/vtaco_b200.h."""
+        """Flat fp32 buffer in the layout documented in include/vtaco_b200.h — one launch of
+        vtaco_pack_linear into a fresh buffer (an earlier forward's autograd node may still hold
+        the previous one)."""
         params = list(self.parameters())
         key = tuple((p.data_ptr(), p._version) for p in params)
         if self._pack_cache is not None and self._pack_cache[0] == key:
             return self._pack_cache[1]
         dev = self.fc_p.weight.device
-        H, nb = 32, self.n_blocks
+        nb = self.n_blocks
+        if nb > _abi.MAX_BLOCKS:
+            raise NotImplementedError('vtaco_b200 decoder kernels hold at most %d blocks in shared memory' % _abi.MAX_BLOCKS)
         buf = torch.zeros(_abi.dec_packed_floats(nb), dtype=torch.float32, device=dev)
-        with torch.no_grad():
-            buf[0:96] = self.fc_p.weight.t().reshape(-1)
-            buf[96:128] = self.fc_p.bias
-            wpi = self.fc_p_img.weight
-            buf[128:224] = wpi[:, :3].t().reshape(-1)
-            buf[224:256] = self.fc_p_img.bias
+        ent = [(self.fc_p.weight, 0), (self.fc_p.bias, 96),
+               (self.fc_p_img.weight, 128, 0, 3), (self.fc_p_img.bias, 224)]
+        if self.c_dim:
+            ent.append((self.fc_p_img.weight, 256, 3, 32))
+        for i in range(nb):
+            o = _abi.DEC_OFF_BLOCKS + i * _abi.DEC_BLOCK_STRIDE
             if self.c_dim:
-                buf[256:1280] = wpi[:, 3:].t().reshape(-1)
-            for i in range(nb):
-                o = _abi.DEC_OFF_BLOCKS + i * _abi.DEC_BLOCK_STRIDE
-                if self.c_dim:
-                    buf[o:o + 1024] = self.fc_c[i].weight.t().reshape(-1)
-                    buf[o + 1024:o + 1056] = self.fc_c[i].bias
-                blk = self.blocks[i]
-                buf[o + 1056:o + 2080] = blk.fc_0.weight.t().reshape(-1)
-                buf[o + 2080:o + 2112] = blk.fc_0.bias
-                buf[o + 2112:o + 3136] = blk.fc_1.weight.t().reshape(-1)
-                buf[o + 3136:o + 3168] = blk.fc_1.bias
-            o = _abi.DEC_OFF_BLOCKS + nb * _abi.DEC_BLOCK_STRIDE
-            buf[o:o + H] = self.fc_out.weight.reshape(-1)
-            buf[o + 64] = self.fc_out.bias[0]
-            if hasattr(self, 'fc_out_contact'):
-                buf[o + H:o + 2 * H] = self.fc_out_contact.weight.reshape(-1)
-                buf[o + 65] = self.fc_out_contact.bias[0]
+                ent += [(self.fc_c[i].weight, o), (self.fc_c[i].bias, o + 1024)]
+            blk = self.blocks[i]
+            ent += [(blk.fc_0.weight, o + 1056), (blk.fc_0.bias, o + 2080),
+                    (blk.fc_1.weight, o + 2112), (blk.fc_1.bias, o + 3136)]
+        o = _abi.DEC_OFF_BLOCKS + nb * _abi.DEC_BLOCK_STRIDE
+        ent += [(self.fc_out.weight, o), (self.fc_out.bias, o + 64)]
+        if hasattr(self, 'fc_out_contact'):
+            ent += [(self.fc_out_contact.weight, o + 32), (self.fc_out_contact.bias, o + 65)]
+        _abi.pack_linear(ent, buf)
         self._pack_cache = (key, buf)
         self._pack_tc_cache = None
         return buf
 
     def _packed_weights_tc(self, mixed=False):
-        """The 3*n_blocks hidden matrices in the UMMA canonical K-major layout expected by the
-        tcgen05 kernel (include/vtaco_b200.h, `weights_tc`): per matrix 4 KB of TF32 hi followed by
-        4 KB of either TF32 lo (3xTF32, variant 2) or — `mixed`, variant 4 — the BF16 correction
-        operand with K = 64: rows k < 32 hold bf16(W), rows k >= 32 hold bf16(W - hi)."""
-        self._packed_weights()
+        """The 3*n_blocks hidden matrices (+ fc_p_img.weight[:, 3:]) in the UMMA canonical K-major
+        layout expected by the tcgen05 kernel (include/vtaco_b200.h, `weights_tc`): per matrix 4 KB
+        of TF32 hi followed by 4 KB of either TF32 lo (3xTF32) or — `mixed`, variants 4 / 6 — the
+        BF16 correction operand with K = 64; then the bias K-blocks.  One launch
+        (vtaco_decoder_pack_tc) from the packed fp32 buffer."""
+        w = self._packed_weights()
         if self._pack_tc_cache is None:
             self._pack_tc_cache = {}
+        mixed = bool(mixed)
         if mixed in self._pack_tc_cache:
             return self._pack_tc_cache[mixed]
-        dev = self.fc_p.weight.device
-        n = torch.arange(32, device=dev).view(32, 1)
-        k = torch.arange(32, device=dev).view(1, 32)
-        idx = ((k // 4) * 128 + (n // 8) * 32 + (n % 8) * 4 + (k % 4)).reshape(-1)
-        mats = []
-        with torch.no_grad():
-            for i in range(self.n_blocks):
-                wc = self.fc_c[i].weight if self.c_dim else torch.zeros(32, 32, device=dev)
-                mats += [wc, self.blocks[i].fc_0.weight, self.blocks[i].fc_1.weight]
-            def split(w):
-                w = w.detach().float().contiguous()
-                hi = ((w.view(torch.int32) + 0x1000) & ~0x1fff).view(torch.float32)   # round-to-nearest TF32 (ties away)
-                lo = ((w - hi).view(torch.int32) & ~0x1fff).view(torch.float32)
-                return hi, lo
-
-            out = torch.zeros(len(mats), 2, 1024, dtype=torch.float32, device=dev)
-            k64 = torch.arange(64, device=dev).view(1, 64)
-            idx16 = ((k64 // 8) * 256 + (n // 8) * 64 + (n % 8) * 8 + (k64 % 8)).reshape(-1)   # bf16 units
-            for m, w in enumerate(mats):
-                hi, lo = split(w)
-                out[m, 0, idx] = hi.reshape(-1)
-                if mixed:
-                    wf = w.detach().float()
-                    corr = torch.cat([wf, wf - hi], 1).to(torch.bfloat16)          # [n][k], k < 64
-                    out[m, 1].view(torch.bfloat16)[idx16] = corr.reshape(-1)
-                else:
-                    out[m, 1, idx] = lo.reshape(-1)
-            # bias K-blocks (K=8, N=32): row k=0 holds bias_hi, row k=1 bias_lo; step order
-            # bc_0 | b0_0, b1_0+bc_1 | b0_1, b1_1+bc_2 | ...
-            zero = torch.zeros(32, device=dev)
-            bc = [self.fc_c[i].bias.detach().float() if self.c_dim else zero for i in range(self.n_blocks)]
-            steps = [bc[0]]
-            for i in range(self.n_blocks):
-                steps.append(self.blocks[i].fc_0.bias.detach().float())
-                nxt = bc[i + 1] if i + 1 < self.n_blocks else zero
-                steps.append(self.blocks[i].fc_1.bias.detach().float() + nxt)
-            nn_ = torch.arange(32, device=dev)
-            bidx0 = (nn_ // 8) * 32 + (nn_ % 8) * 4          # k = 0
-            bias = torch.zeros(len(steps), 256, dtype=torch.float32, device=dev)
-            for m, b in enumerate(steps):
-                hi, lo = split(b)
-                bias[m, bidx0] = hi
-                bias[m, bidx0 + 1] = lo
-            out = torch.cat([out.reshape(-1), bias.reshape(-1)])
-        self._pack_tc_cache[mixed] = out.reshape(-1).contiguous()
-        return self._pack_tc_cache[mixed]
+        out = torch.empty(_abi.dec_tc_floats(self.n_blocks), dtype=torch.float32, device=w.device)
+        with torch.cuda.device(w.device):
+            st = _abi.lib().vtaco_decoder_pack_tc(_abi.ptr(w), self.n_blocks, int(mixed), _abi.ptr(out),
+                                                  _abi.stream_ptr(w.device))
+        _abi.check(st, 'decoder_pack_tc')
+        self._pack_tc_cache[mixed] = out
+        return out
 
     def _features_cl(self, c_plane):
         """Channels-last views/copies of the feature tensors (cached per tensor version)."""
@@ -246,16 +223,18 @@ class LocalDecoder(nn.Module):
                                  % (k, 'R,R,R' if k == 'grid' else 'R,R', tuple(t.shape)))
             if len(set(t.shape[2:])) != 1:
                 raise NotImplementedError('feature tensors must be cubic/square')
-            ck = (k, t.data_ptr(), t._version, tuple(t.shape), tuple(t.stride()))
-            live.add(ck)
-            hit = self._cl_cache.get(ck)
-            if hit is None:
-                hit = _as_channels_last(t)
-                self._cl_cache[ck] = hit
-            out[k] = hit
-        for ck in list(self._cl_cache):
-            if ck not in live:
-                del self._cl_cache[ck]
+            # The entry keeps the SOURCE tensor: `src is t` makes a recycled allocation (same address,
+            # version and shape after the caller dropped the previous features) a miss instead of a
+            # stale hit, and holding it keeps the address from being reused while the entry lives.
+            hit = self._cl_cache.get(k)
+            if hit is None or hit[0] is not t or hit[1] != t._version:
+                hit = (t, t._version, _as_channels_last(t))
+                self._cl_cache[k] = hit
+            live.add(k)
+            out[k] = hit[2]
+        for k in list(self._cl_cache):
+            if k not in live:
+                del self._cl_cache[k]
         return out
 
     # ------------------------------------------------------------------ kernel call
@@ -306,9 +285,10 @@ class LocalDecoder(nn.Module):
             raise ValueError('p must have shape (B, N, 3)')
         feats = {k: t for k, t in c_plane.items() if k in ('grid',) + _PLANES and torch.is_tensor(t)}
         if _abi.wants_grad(p, c_img, *self.parameters(), *feats.values()):
-            if p.requires_grad:
-                raise NotImplementedError('vtaco_b200: no gradient w.r.t. the query points p '
-                                          '(the reference never differentiates through them); detach p')
+            # The reference training loop builds its query points with requires_grad=True
+            # (training.py:310,362,614,729,868) but never reads p.grad: no gradient w.r.t. p is
+            # produced (backward returns None for it), everything else is differentiated.
+            self._pack_cache = None     # training: re-pack every step (one launch), immune to `.data` updates
             names, params = zip(*self.named_parameters())
             return _DecodeFn.apply(self, bool(use_img), bool(contact), tuple(feats.keys()), names, p, c_img,
                                    *feats.values(), *params)
@@ -335,8 +315,7 @@ class LocalDecoder(nn.Module):
                 raise ValueError('c_img must have shape (B, N, c_dim)')
             cic = c_img.contiguous()
             a.c_img = cic.data_ptr() if self.c_dim else None
-            if a.variant in (2, 4, 5, 6) and self.c_dim:
-                a.variant = 1  # per-query c_img tensor: packed-FFMA2 SIMT kernel
+            keep.append(cic)
         a.logits = out.data_ptr()
         if contact:
             if not hasattr(self, 'fc_out_contact'):
@@ -502,8 +481,6 @@ class LocalDecoder(nn.Module):
             if cic.size(0) != nx ** 3:
                 raise ValueError('dense c_img must have nx^3 rows')
             a.c_img = cic.data_ptr()
-            if a.variant in (2, 4, 5, 6):
-                a.variant = 1
         if use_img and tips is not None:
             pos, feat, touch, radius = tips
             F_ = len(pos)

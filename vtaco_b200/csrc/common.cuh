@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <atomic>
 #include "../../include/vtaco_b200.h"
 
 namespace vtaco {

@@ -9,14 +9,15 @@ static thread_local cudaError_t g_last_err = cudaSuccess;
 void set_last_cuda_error(cudaError_t e) { g_last_err = e; }
 
 int num_sms() {
-  static int cached[64] = {0};
+  static std::atomic<int> cached[64];
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-  int& c = cached[dev & 63];
+  int c = cached[dev & 63].load(std::memory_order_relaxed);
   if (c == 0) {
     int n = 0;
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
     c = n;
+    cached[dev & 63].store(n, std::memory_order_relaxed);
   }
   return c;
 }

@@ -399,13 +399,13 @@ extern "C" int vtaco_relayout_cf(const float* src, float* dst, int B, int C, int
 
 template <bool DENSE, bool F2>
 static int launch_decoder(const DecParams& P, size_t smem_bytes, cudaStream_t stream) {
-  static size_t configured[64] = {0};  // per instantiation, per device
+  static std::atomic<size_t> configured[64];  // per instantiation, per device; idempotent, thread-safe
   int dev = 0;
   VTACO_CUDA_CHECK(cudaGetDevice(&dev));
-  if (configured[dev & 63] < smem_bytes) {
+  if (configured[dev & 63].load(std::memory_order_relaxed) < smem_bytes) {
     VTACO_CUDA_CHECK(cudaFuncSetAttribute(decoder_kernel<DENSE, F2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)smem_bytes));
-    configured[dev & 63] = smem_bytes;
+    configured[dev & 63].store(smem_bytes, std::memory_order_relaxed);
   }
   const long long grid = P.n_tiles < (long long)num_sms() ? P.n_tiles : (long long)num_sms();
   decoder_kernel<DENSE, F2><<<(unsigned)grid, kThreads, smem_bytes, stream>>>(P);

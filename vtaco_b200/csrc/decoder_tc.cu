@@ -263,7 +263,7 @@ __host__ __device__ inline TcSmem tc_smem_layout(int n_blocks) {
   TcSmem s;
   s.w = 0;                                          // 3*nb matrices x (hi 4 KB | lo 4 KB)
   s.bias = s.w + 3 * n_blocks * 8192;               // (2*nb+1) bias K-blocks of 1 KB
-  s.small = s.bias + (2 * n_blocks + 1) * 1024;     // Wp[3][32], bp[32], Wout[64], bout[2]+pad
+  s.small = s.bias + (2 * n_blocks + 1) * 1024 + 8192;   // (+ fc_p_img.weight[:, 3:] hi|lo) Wp[3][32], bp[32], Wout[64], bout[2]+pad
   s.tips = s.small + (128 + 68) * 4;
   s.stage = s.tips + VTACO_MAX_TIPS * 32 * 4;
   s.stage = (s.stage + 15) / 16 * 16;
@@ -322,7 +322,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) decoder_tc_kernel(const __grid_
   const int nb = P.n_blocks;
 
   // ---- one-time setup: weights + bias blocks (contiguous in wtc), small vectors, barriers, TMEM ----
-  const int wtc_floats = 3 * nb * 2048 + (2 * nb + 1) * 256;
+  const bool cimg = P.use_img && P.c_img;   // per-query tactile feature tensor (decoder.py:83-85)
+  const int wtc_floats = 3 * nb * 2048 + (2 * nb + 1) * 256 + (cimg ? 2048 : 0);
   for (int i = tid; i < wtc_floats / 4; i += kTcThreads)
     reinterpret_cast<float4*>(sWtc)[i] = __ldg(reinterpret_cast<const float4*>(wtc) + i);
   for (int i = tid; i < 128; i += kTcThreads) sSmall[i] = P.weights[(P.use_img ? VTACO_DEC_OFF_WPI : VTACO_DEC_OFF_WP) + i];
@@ -357,6 +358,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) decoder_tc_kernel(const __grid_
   const uint32_t mC = mbase, mX = mbase + 64, mOnes = mbase + 128, mD = mbase + 136;
   const uint32_t bar = smem_u32(sBars + g);
   const uint32_t wsm = smem_u32(sWtc), bsm = smem_u32(tsm + L.bias);
+  const uint32_t wimg_sm = bsm + (uint32_t)(2 * nb + 1) * 1024u;
   uint32_t ph = 0;
   {  // the constant A block that multiplies the bias rows: columns (1, 1, 0, 0, 0, 0, 0, 0)
     const uint32_t one = __float_as_uint(1.0f);
@@ -405,8 +407,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) decoder_tc_kernel(const __grid_
     if (!valid) oidx = 0;
     TC_STAMP(13);  // tile start: coordinates loaded
 
-    // ---------------- gather ----------------
-    if (P.has_c) {
+    // ---------------- gather (+ the query's c_img row): operands of step 0 ----------------
+    if (P.has_c || cimg) {
+     if (P.has_c) {
       float cv[32];
       bool sep_done = false;
       if (DENSE && P.grid && !P.nearest && !(P.plane[0] || P.plane[1] || P.plane[2])) {
@@ -501,14 +504,30 @@ __global__ void __launch_bounds__(kTcThreads, 1) decoder_tc_kernel(const __grid_
       }  // generic gather
       TC_STAMP(15);  // features of the thread's query in registers
       split_store(tC, cv, mixed);
+     }
+      if (cimg) {   // fc_p_img(cat[p, c_img]) = fc_p_img[:, :3] p + b + W_img c_img: the last term rides in step 0
+        float xv[32];
+        const float4* row = reinterpret_cast<const float4*>(P.c_img + (size_t)oidx * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 v = __ldg(row + j);
+          xv[4 * j] = v.x; xv[4 * j + 1] = v.y; xv[4 * j + 2] = v.z; xv[4 * j + 3] = v.w;
+        }
+        split_store(tX, xv, mixed);
+      }
       tc_wait_st();
       tc_fence_before();
       group_sync(g);
       TC_STAMP(16);  // C in TMEM, group synced
-      if (wg == (step & 3) && elect_one()) {     // step 0: D = C*Wc_0 + ones*bc_0
+      if (wg == (step & 3) && elect_one()) {     // step 0: D = C*Wc_0 + ones*bc_0 [+ c_img*W_img]
         tc_fence_after();
-        issue_product(mD, mC, wsm, 0, P.tc_products);
-        tc_mma_ts(mD, mOnes, make_bdesc(bsm), 1);
+        uint32_t acc = 0;
+        if (P.has_c) {
+          issue_product(mD, mC, wsm, 0, P.tc_products);
+          tc_mma_ts(mD, mOnes, make_bdesc(bsm), 1);
+          acc = 1;
+        }
+        if (cimg) issue_product(mD, mX, wimg_sm, acc, P.tc_products);
         tc_commit(bar);
       }
       ++step;
@@ -540,7 +559,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) decoder_tc_kernel(const __grid_
     TC_STAMP(17);    // fc_p / tips done
     uint32_t r[32];
     float x[32];
-    if (P.has_c) {  // net += fc_c[0](c)
+    if (P.has_c || cimg) {  // net += fc_c[0](c) [+ W_img c_img]
       mbar_wait(bar, ph); ph ^= 1;
       tc_fence_after();
       tmem_ld32(tD, r);
@@ -707,7 +726,7 @@ __host__ __device__ inline Tc2Smem tc2_smem_layout(int n_blocks) {
   Tc2Smem s;
   s.w = 0;
   s.bias = s.w + 3 * n_blocks * 8192;
-  s.small = s.bias + (2 * n_blocks + 1) * 1024;
+  s.small = s.bias + (2 * n_blocks + 1) * 1024 + 8192;   // bias blocks, then fc_p_img.weight[:, 3:] hi|lo
   s.tips = s.small + (128 + 68) * 4;
   s.stage = s.tips + VTACO_MAX_TIPS * 32 * 4;
   s.stage = (s.stage + 15) / 16 * 16;
@@ -741,7 +760,8 @@ __global__ void __launch_bounds__(kTc2Threads, 1) decoder_tc2_kernel(const __gri
   const int nb = P.n_blocks;
   const int nx = P.nx;
 
-  const int wtc_floats = 3 * nb * 2048 + (2 * nb + 1) * 256;
+  const bool cimg = P.use_img && P.c_img;   // per-query tactile feature tensor (decoder.py:83-85)
+  const int wtc_floats = 3 * nb * 2048 + (2 * nb + 1) * 256 + (cimg ? 2048 : 0);
   for (int i = tid; i < wtc_floats / 4; i += kTc2Threads)
     reinterpret_cast<float4*>(sWtc)[i] = __ldg(reinterpret_cast<const float4*>(wtc) + i);
   for (int i = tid; i < 128; i += kTc2Threads) sSmall[i] = P.weights[(P.use_img ? VTACO_DEC_OFF_WPI : VTACO_DEC_OFF_WP) + i];
@@ -778,6 +798,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) decoder_tc2_kernel(const __gri
   const uint32_t mC = mbase, mX = mbase + 64, mOnes = mbase + 128, mD = mbase + 136;
   const uint32_t bar = smem_u32(sBars + g);
   const uint32_t wsm = smem_u32(sWtc), bsm = smem_u32(tsm + L.bias);
+  const uint32_t wimg_sm = bsm + (uint32_t)(2 * nb + 1) * 1024u;
   const int gsync_id = g + 1;
   auto group_sync2 = [&]() { asm volatile("bar.sync %0, 256;" ::"r"(gsync_id) : "memory"); };
   uint32_t ph = 0;
@@ -829,8 +850,9 @@ __global__ void __launch_bounds__(kTc2Threads, 1) decoder_tc2_kernel(const __gri
     }
     if (!valid) oidx = 0;
 
-    // ---------------- gather: this thread's 16 channels of its query ----------------
-    if (P.has_c) {
+    // ---------------- gather: this thread's 16 channels of its query (+ of its c_img row): operands of step 0 ----------------
+    if (P.has_c || cimg) {
+     if (P.has_c) {
       float cv[16];
       bool sep_done = false;
       if (sep_cfg) {
@@ -917,13 +939,29 @@ __global__ void __launch_bounds__(kTc2Threads, 1) decoder_tc2_kernel(const __gri
         __syncwarp();
       }
       split_store16<MIXED>(tC, hv, cv);
+     }
+      if (cimg) {   // fc_p_img(cat[p, c_img]) = fc_p_img[:, :3] p + b + W_img c_img: the last term rides in step 0
+        float xv[16];
+        const float4* row = reinterpret_cast<const float4*>(P.c_img + (size_t)oidx * 32 + ch0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 v = __ldg(row + j);
+          xv[4 * j] = v.x; xv[4 * j + 1] = v.y; xv[4 * j + 2] = v.z; xv[4 * j + 3] = v.w;
+        }
+        split_store16<MIXED>(tX, hv, xv);
+      }
       tc_wait_st();
       tc_fence_before();
       group_sync2();
-      if (wq == (step & 7) && elect_one()) {     // step 0: D = C*Wc_0 + ones*bc_0
+      if (wq == (step & 7) && elect_one()) {     // step 0: D = C*Wc_0 + ones*bc_0 [+ c_img*W_img]
         tc_fence_after();
-        issue_product(mD, mC, wsm, 0, n_prod);
-        tc_mma_ts(mD, mOnes, make_bdesc(bsm), 1);
+        uint32_t acc = 0;
+        if (P.has_c) {
+          issue_product(mD, mC, wsm, 0, n_prod);
+          tc_mma_ts(mD, mOnes, make_bdesc(bsm), 1);
+          acc = 1;
+        }
+        if (cimg) issue_product(mD, mX, wimg_sm, acc, n_prod);
         tc_commit(bar);
       }
       ++step;
@@ -954,7 +992,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) decoder_tc2_kernel(const __gri
     }
     uint32_t r[16];
     float x[16];
-    if (P.has_c) {  // net += fc_c[0](c)
+    if (P.has_c || cimg) {  // net += fc_c[0](c) [+ W_img c_img]
       mbar_wait(bar, ph); ph ^= 1;
       tc_fence_after();
       tmem_ld16(tD + ch0, r);
@@ -1050,7 +1088,6 @@ __global__ void __launch_bounds__(kTc2Threads, 1) decoder_tc2_kernel(const __gri
 
 int launch_decoder_tc(DecParams P, bool dense, const float* wtc, cudaStream_t stream) {
   if (!wtc) return VTACO_ERR_INVALID_ARG;
-  if (P.use_img && P.c_img) return VTACO_ERR_UNSUPPORTED;  // dense c_img tensor: SIMT kernel
   if (dense) {
     P.t_xend = P.x1;
     P.t_nbz = (P.nx + 31) / 32;
@@ -1068,13 +1105,13 @@ int launch_decoder_tc(DecParams P, bool dense, const float* wtc, cudaStream_t st
     using Kernel2 = void (*)(DecParams, const float*);
     const Kernel2 k2 = dense ? (mixed ? (Kernel2)decoder_tc2_kernel<true, true> : (Kernel2)decoder_tc2_kernel<true, false>)
                              : (mixed ? (Kernel2)decoder_tc2_kernel<false, true> : (Kernel2)decoder_tc2_kernel<false, false>);
-    static size_t configured2[4][64] = {{0}};
+    static std::atomic<size_t> configured2[4][64];   // idempotent opt-in cache, safe across host threads
     int dev2 = 0;
     VTACO_CUDA_CHECK(cudaGetDevice(&dev2));
     const int ki2 = (dense ? 2 : 0) + (mixed ? 1 : 0);
-    if (configured2[ki2][dev2 & 63] < (size_t)L2.total) {
+    if (configured2[ki2][dev2 & 63].load(std::memory_order_relaxed) < (size_t)L2.total) {
       VTACO_CUDA_CHECK(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, L2.total));
-      configured2[ki2][dev2 & 63] = L2.total;
+      configured2[ki2][dev2 & 63].store(L2.total, std::memory_order_relaxed);
     }
     long long grid2 = (P.n_tiles + kTcGroups - 1) / kTcGroups;
     if (grid2 > num_sms()) grid2 = num_sms();
@@ -1087,13 +1124,13 @@ int launch_decoder_tc(DecParams P, bool dense, const float* wtc, cudaStream_t st
   using Kernel = void (*)(DecParams, const float*, long long*);
   const Kernel kernel = dense ? (mixed ? (Kernel)decoder_tc_kernel<true, true> : (Kernel)decoder_tc_kernel<true, false>)
                               : (mixed ? (Kernel)decoder_tc_kernel<false, true> : (Kernel)decoder_tc_kernel<false, false>);
-  static size_t configured[4][64] = {{0}};
+  static std::atomic<size_t> configured[4][64];
   int dev = 0;
   VTACO_CUDA_CHECK(cudaGetDevice(&dev));
   const int ki = (dense ? 2 : 0) + (mixed ? 1 : 0);
-  if (configured[ki][dev & 63] < (size_t)L.total) {
+  if (configured[ki][dev & 63].load(std::memory_order_relaxed) < (size_t)L.total) {
     VTACO_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-    configured[ki][dev & 63] = L.total;
+    configured[ki][dev & 63].store(L.total, std::memory_order_relaxed);
   }
   long long grid = (P.n_tiles + kTcGroups - 1) / kTcGroups;
   if (grid > num_sms()) grid = num_sms();

@@ -457,13 +457,13 @@ extern "C" int vtaco_encoder_pointnet(const vtaco_encoder_args* a, void* stream)
   enc_index_kernel<<<g256, 256, 0, st>>>(P);
   enc_slot_kernel<<<g256, 256, 0, st>>>(P, 1);
   const size_t smem_blk = (ENC_BLOCK_STRIDE + 256 + 64 * kES) * sizeof(float);
-  static bool configured[64] = {false};
+  static std::atomic<bool> configured[64];
   int dev = 0;
   VTACO_CUDA_CHECK(cudaGetDevice(&dev));
-  if (!configured[dev & 63]) {
+  if (!configured[dev & 63].load(std::memory_order_relaxed)) {
     VTACO_CUDA_CHECK(cudaFuncSetAttribute(enc_block_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_blk));
     VTACO_CUDA_CHECK(cudaFuncSetAttribute(enc_block_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_blk));
-    configured[dev & 63] = true;
+    configured[dev & 63].store(true, std::memory_order_relaxed);
   }
   const int nb = a->n_blocks;
   // kernel i reads pool[(i-1)%3], scatters into pool[i%3], initialises pool[(i+1)%3]

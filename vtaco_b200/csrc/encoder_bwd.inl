@@ -317,15 +317,15 @@ extern "C" int vtaco_encoder_backward(const vtaco_encoder_bwd_args* a, void* str
   const size_t smem_blk = (ENC_BLOCK_STRIDE + 256 + 64 * kES) * sizeof(float);
   const size_t smem_bwd = (ENC_BLOCK_STRIDE + 256 + 128 * kES) * sizeof(float);
   const size_t smem_fin = (ENC_FCC_FLOATS + 32 * kES) * sizeof(float);
-  static bool configured[64] = {false};
+  static std::atomic<bool> configured[64];
   int dev = 0;
   VTACO_CUDA_CHECK(cudaGetDevice(&dev));
-  if (!configured[dev & 63]) {
+  if (!configured[dev & 63].load(std::memory_order_relaxed)) {
     VTACO_CUDA_CHECK(cudaFuncSetAttribute(enc_block_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_blk));
     VTACO_CUDA_CHECK(cudaFuncSetAttribute(enc_block_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_blk));
     VTACO_CUDA_CHECK(cudaFuncSetAttribute(encb_block_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bwd));
     VTACO_CUDA_CHECK(cudaFuncSetAttribute(encb_block_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bwd));
-    configured[dev & 63] = true;
+    configured[dev & 63].store(true, std::memory_order_relaxed);
   }
 
   // ---- 1. forward recompute, every level kept ----

@@ -173,7 +173,22 @@ class LocalPoolPointnet(nn.Module):
                 'vtaco_b200 encoder kernels implement dim=3, hidden_dim=32, c_dim=32 (every shipped VTacO '
                 'conv-occupancy config); got dim=%d hidden_dim=%d c_dim=%d' % (self.dim, self.hidden_dim, self.c_dim))
 
+    def invalidate(self):
+        """Drop the packed-weight cache (keyed on (data_ptr, _version) of the parameters; updates made
+        through `param.data` do not bump `_version` — call this after one when running under no_grad;
+        with grad enabled every call re-packs, and `.to()` / `load_state_dict` invalidate on their own)."""
+        self._pack_cache = None
+
+    def _apply(self, fn, *args, **kwargs):
+        self.invalidate()
+        return super()._apply(fn, *args, **kwargs)
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self.invalidate()
+        return super()._load_from_state_dict(*args, **kwargs)
+
     def _packed_weights(self):
+        """K-major fp32 buffer (layout in include/vtaco_b200.h), one vtaco_pack_linear launch."""
         params = [self.fc_pos.weight, self.fc_pos.bias, self.fc_c.weight, self.fc_c.bias] + \
             [p for b in self.blocks for p in b.parameters()]
         key = tuple((p.data_ptr(), p._version) for p in params)
@@ -181,19 +196,15 @@ class LocalPoolPointnet(nn.Module):
             return self._pack_cache[1]
         nb = self.n_blocks
         buf = torch.zeros(256 + 5184 * nb + 1056, dtype=torch.float32, device=self.fc_pos.weight.device)
-        with torch.no_grad():
-            buf[0:192] = self.fc_pos.weight.t().reshape(-1)
-            buf[192:256] = self.fc_pos.bias
-            for i, blk in enumerate(self.blocks):
-                o = 256 + 5184 * i
-                buf[o:o + 2048] = blk.fc_0.weight.t().reshape(-1)
-                buf[o + 2048:o + 2080] = blk.fc_0.bias
-                buf[o + 2080:o + 3104] = blk.fc_1.weight.t().reshape(-1)
-                buf[o + 3104:o + 3136] = blk.fc_1.bias
-                buf[o + 3136:o + 5184] = blk.shortcut.weight.t().reshape(-1)
-            o = 256 + 5184 * nb
-            buf[o:o + 1024] = self.fc_c.weight.t().reshape(-1)
-            buf[o + 1024:o + 1056] = self.fc_c.bias
+        ent = [(self.fc_pos.weight, 0), (self.fc_pos.bias, 192)]
+        for i, blk in enumerate(self.blocks):
+            o = 256 + 5184 * i
+            ent += [(blk.fc_0.weight, o), (blk.fc_0.bias, o + 2048), (blk.fc_1.weight, o + 2080),
+                    (blk.fc_1.bias, o + 3104), (blk.shortcut.weight, o + 3136)]
+        o = 256 + 5184 * nb
+        ent += [(self.fc_c.weight, o), (self.fc_c.bias, o + 1024)]
+        for j in range(0, len(ent), _abi.PACK_MAX_DESCS):
+            _abi.pack_linear(ent[j:j + _abi.PACK_MAX_DESCS], buf)
         self._pack_cache = (key, buf)
         return buf
 
@@ -213,11 +224,12 @@ class LocalPoolPointnet(nn.Module):
             raise ValueError('p must have shape (B, T, 3)')
         own = self._pointnet_params()
         if _abi.wants_grad(p, *[t for _, t in own]):
-            if p.requires_grad:
-                raise NotImplementedError('vtaco_b200: no gradient w.r.t. the input points p; detach p')
+            # no gradient w.r.t. the input cloud is produced (backward returns None for p), like the
+            # decoder: the reference never reads it
             if return_code or return_index:
                 raise NotImplementedError('vtaco_b200: return_code / return_index are inference-only outputs; '
                                           'call under torch.no_grad()')
+            self._pack_cache = None    # training: re-pack every step (one launch), immune to `.data` updates
             names, params = zip(*own)
             outs = _PointnetFn.apply(self, p, names, *params)
             return dict(zip([k for k in _KEY_ORDER_OUT if k in self._keys_in()], outs))
