@@ -11,14 +11,17 @@ fingertip conditioning), dense 256^3 lattice (resolution_0 = 64), marching cubes
 level 0.5*(min+max).  Synthetic cloud (3000 visual + 5x128 tactile points), random-init
 weights (fc_1 re-randomised, it is zero-initialised in the reference).
 
-A step = one pass over the whole lattice: fused decode of nx^3 queries (x-slabs over the
-ranks + NCCL all-gather of the logits and min/max exchange when N>1) + marching cubes.
+A step = one pass over the whole lattice: fused decode of nx^3 queries + marching cubes.  N>1:
+x-slabs over the ranks, every rank extracts the mesh piece of its slab and the pieces are gathered
+on rank 0 (device-side signalling over NVLink peer memory; --exchange selects the older schemes).
 `value`  : nx^3 / step time, features already resident in HBM (device timed, CUDA events).
-`e2e`    : the same through Generator3D.generate_mesh with HOST buffers: pinned point
-           cloud -> H2D -> encoder (PointNet kernels + UNet3D) -> decode -> MC -> mesh D2H.
+`e2e`    : the same through Generator3D.capture_generate with HOST buffers: pinned point
+           cloud -> H2D -> encoder (PointNet kernels + UNet3D) [-> broadcast] -> decode -> MC -> mesh D2H.
 `--impl reference`: the reference's CPU implementation of the path (the oracle port: same
-           torch CPU ops as the reference's modules; the reference is Python and is not
-           present on the GPU box) on a bounded sample of the same lattice.
+           torch CPU ops as the reference's modules + the numpy marching-cubes restatement; the
+           reference is Python and is not present on the GPU box) on a bounded sample of the lattice.
+`identity_ok` (N>1): the mesh assembled from the ranks' pieces equals, bit for bit, the mesh rank 0
+           computes alone from the same features (checked before the timed region).
 """
 import argparse
 import json
@@ -36,7 +39,7 @@ if ROOT not in sys.path:
 
 METRIC = 'occupancy query-points/sec (dense lattice decode + marching cubes)'
 UNIT = 'query-points/s'
-FLOP_PER_QUERY = 30976          # executed MLP FLOPs/query (LocalDecoder.forward)
+FLOP_PER_QUERY = 30976          # algorithmic MLP FLOPs/query (LocalDecoder.forward)
 FLOP_PER_QUERY_IMG = 33024      # forward_img with a dense c_img tensor
 
 
@@ -160,11 +163,18 @@ class CpuReference(object):
         self.p = torch.stack([gx, gy, gz], -1).reshape(-1, 3)[:n_sample].contiguous()
         self.c_img = oc.fingertip_c_img(self.p, tips, torch.from_numpy(tip_feat), touch, 0.05)
         self.n = self.p.shape[0]
+        self.rows, self.nx = rows, nx
         self.cores = torch.get_num_threads()
 
     def run(self):
+        """decode the sample rows (eval_points chunking) + marching cubes on them (generation.py:268-272)."""
+        from oracle import marching_cubes as omc
         t0 = time.perf_counter()
-        self.oc.eval_points(self.p, self.feats, self.W, self.c_img, points_batch_size=100000)
+        occ = self.oc.eval_points(self.p, self.feats, self.W, self.c_img, points_batch_size=100000)
+        if self.rows >= 2 and occ.numel() == self.rows * self.nx * self.nx:
+            vol = occ.reshape(self.rows, self.nx, self.nx).numpy()
+            v, f, _ = omc.marching_cubes(vol, None)
+            omc.rescale_vertices(v, self.nx)
         return time.perf_counter() - t0
 
     def run_torch_eager_gpu(self):
@@ -208,11 +218,40 @@ def run_reference(args, rank, world):
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                          'sample': '%d consecutive lattice points (x-rows from the middle of the %d^3 lattice) per '
                                    'step through the oracle port of Generator3D.eval_points + '
-                                   'LocalDecoder.forward_img (torch CPU ops, 100k chunks)' % (n, nx)},
+                                   'LocalDecoder.forward_img (torch CPU ops, 100k chunks) + the numpy marching-cubes '
+                                   'restatement on those rows; a rate, not a whole-lattice time' % (n, nx)},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0, 'wall_s': time.perf_counter() - t_all,
     }
     print(json.dumps(line))
+
+
+def measure_tensor_peaks(dev, n=8192, reps=10):
+    """cuBLAS burst peaks (TFLOP/s) of a TF32 and a BF16 GEMM n^3 on this GPU — roofline denominators, measured
+    after the timed regions (plain library GEMMs, not part of the product path)."""
+    out = []
+    prev = torch.backends.cuda.matmul.allow_tf32
+    try:
+        for dt, tf32 in ((torch.float32, True), (torch.bfloat16, False)):
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            a = torch.randn(n, n, device=dev, dtype=dt)
+            b = torch.randn(n, n, device=dev, dtype=dt)
+            for _ in range(3):
+                a @ b
+            best = float('inf')
+            for _ in range(reps):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize(dev)
+                e0.record()
+                a @ b
+                e1.record()
+                torch.cuda.synchronize(dev)
+                best = min(best, e0.elapsed_time(e1))
+            out.append(2.0 * n ** 3 / (best * 1e-3) / 1e12)
+            del a, b
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    return out[0], out[1]
 
 
 def workload_config(nx, args):
@@ -225,9 +264,15 @@ def workload_config(nx, args):
                                      'all-gather)',
                             'root': 'pushed into rank 0 by one bulk NVLink peer copy per rank (double-buffered; marching '
                                     'cubes on rank 0 overlaps the peers\' next decode)',
-                            'nccl': 'all-gathered with NCCL'}[getattr(args, 'exchange', 'root')]),
+                            'nccl': 'all-gathered with NCCL',
+                            'mesh': 'never leave their rank: marching cubes runs per slab (+2 halo rows) and only mesh '
+                                    'pieces are gathered on rank 0 (device-side signalling over NVLink peer memory)'}[
+                                getattr(args, 'exchange', 'mesh')]),
             'l2': 'flushed between timed steps (256 MiB write outside the step events)',
-            'kernel_variant': args.variant}
+            'kernel_variant': args.variant,
+            'unet3d_conv_math': 'e2e only: UNet3D convolutions run with torch.backends.cudnn.allow_tf32=%s (torch '
+                                'default, what the reference does on a GPU); PointNet, decoder and marching cubes are '
+                                'fp32-accurate (3xTF32 on the tensor pipe)' % torch.backends.cudnn.allow_tf32}
 
 
 # --------------------------------------------------------------------------------------
@@ -298,21 +343,25 @@ def run_ours(args, rank, local_rank, world):
             rr.fill_(max(2.0, per - mc_rows))
         dist.broadcast(rr, 0, group=group)
         gen.root_rows = int(rr.item()) // 2 * 2
-    if world > 1 and args.exchange in ('fused', 'root'):
+    if world > 1 and args.exchange in ('fused', 'root', 'mesh'):
         # symmetric-memory rendezvous must succeed on EVERY rank, else all ranks use NCCL
         ok = torch.ones(1, device=dev)
         try:
             for _ in range(2):
-                gen.eval_lattice(c, tips=tips_arg, group=group, exchange=args.exchange)
+                if args.exchange == 'mesh':
+                    gen.sharded_mesh(c, tips=tips_arg, group=group)
+                else:
+                    gen.eval_lattice(c, tips=tips_arg, group=group, exchange=args.exchange)
         except Exception as e:  # noqa: BLE001 - report and fall back to the NCCL plumbing
             ok.zero_()
-            exchange_note = 'fused exchange unavailable (%s); NCCL all-gather used' % type(e).__name__
+            exchange_note = 'peer-memory exchange unavailable (%s: %s); NCCL all-gather used' % (type(e).__name__, str(e)[:120])
         dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
         if ok.item() == 0:
             args.exchange = 'nccl'
             gen._fused = None
             gen._root_ex = None
-            exchange_note = exchange_note or 'fused exchange unavailable on a peer; NCCL all-gather used' 
+            gen._mesh_ex = None
+            exchange_note = exchange_note or 'peer-memory exchange unavailable on a peer; NCCL all-gather used' 
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
 
     def device_step():
@@ -334,6 +383,8 @@ def run_ours(args, rank, local_rank, world):
     # ---- warm-up ----
     for _ in range(max(args.warmup, 1)):
         device_step()
+    if world > 1 and args.exchange == 'mesh':
+        gen._settle_sharded(device_step, group)      # piece / destination buffers large enough on every rank
     # make sure the MC buffers are large enough, then no more host reads inside the steps
     if world > 1 and args.exchange == 'root' and max(args.warmup, 1) % 2 == 0:
         device_step()                      # keep the buffer parity even before the next pair of steps
@@ -342,8 +393,8 @@ def run_ours(args, rank, local_rank, world):
     grow = torch.zeros(1, device=dev)
     if out_ is not None:
         v_, f_, counts = out_
-        V, F = [int(x) for x in counts.cpu()]
-        if V > v_.shape[0] or F > f_.shape[0]:
+        V, F = [int(x) for x in counts[:2].cpu()]
+        if args.exchange != 'mesh' and (V > v_.shape[0] or F > f_.shape[0]):
             gen.mc._ensure(0, int(V * 1.25) + 16, int(F * 1.25) + 16)
             grow.fill_(1)
     if world > 1:
@@ -352,9 +403,31 @@ def run_ours(args, rank, local_rank, world):
         device_step()
         device_step()
 
-    # ---- CUDA graph of the step (decode [+ peer stores, barriers] + marching cubes) ----
+    # ---- N>1: the exchanged result == what rank 0 computes alone from the same features ----
+    identity = None
+    if world > 1:
+        import hashlib
+        ok_id = torch.ones(1, device=dev)
+        out_x = device_step()
+        torch.cuda.synchronize(dev)
+        if rank == 0:
+            with torch.no_grad():
+                vx, fx = out_x[0][:V].clone(), out_x[1][:F].clone()
+                g1, k1 = gen.eval_lattice(c, tips=tips_arg, group=False)          # whole lattice, this rank alone
+                v1, f1, c1 = gen.mc(g1, level_keys=k1, voffset=np.float32(nx / 2), vscale=np.float32(1.1 / nx), sync=False)
+                V1, F1 = [int(x) for x in c1[:2].cpu()]
+                same = (V1, F1) == (V, F) and torch.equal(v1[:V1], vx) and torch.equal(f1[:F1], fx)
+                ok_id.fill_(1.0 if same else 0.0)
+                h = hashlib.sha1(vx.cpu().numpy().tobytes())
+                h.update(fx.cpu().numpy().tobytes())
+                identity = {'ok': bool(same), 'mesh_sha1': h.hexdigest()[:16], 'single_rank_mesh': [V1, F1]}
+        dist.all_reduce(ok_id, op=dist.ReduceOp.MIN, group=group)
+        if world > 1 and args.exchange == 'root' and gen._root_ex is not None and gen._root_ex.parity:
+            device_step()                  # keep the double-buffer parity even
+
+    # ---- CUDA graph of the step (decode [+ exchange] + marching cubes) ----
     graph, graph_note = None, 'eager launches'
-    if not args.no_graph and (world == 1 or args.exchange in ('fused', 'root')):
+    if not args.no_graph and (world == 1 or args.exchange in ('fused', 'root', 'mesh')):
         ok = torch.ones(1, device=dev)
         try:
             graph, _ = gen.capture_step(c, tips=tips_arg, group=group, exchange=args.exchange)
@@ -407,6 +480,8 @@ def run_ours(args, rank, local_rank, world):
     _vd = __import__('vtaco_b200.dist', fromlist=['slab'])
     x0, x1 = (_vd.slab_root(nx, rank, world, gen.root_rows) if (world > 1 and args.exchange == 'root')
               else _vd.slab(nx, rank, world))
+    if world > 1 and args.exchange == 'mesh':
+        x1 = min(x1 + 2, nx)              # the two halo rows every rank decodes in addition
     if x1 <= x0:
         x0, x1 = 0, 2
     kq = (x1 - x0) * nx * nx
@@ -425,34 +500,51 @@ def run_ours(args, rank, local_rank, world):
     # ---- end-to-end through Generator3D with host buffers ----
     e2e_times, h2d, d2h = [], 0, 0
     e2e_run, e2e_mode = None, 'Generator3D.generate_mesh (eager launches)'
-    if world == 1 and not args.no_graph:
+    if not args.no_graph and (world == 1 or args.exchange == 'mesh'):
+        ok = torch.ones(1, device=dev)
         try:
-            e2e_run = gen.capture_generate(cloud_host, tips=(tips, tip_feat, touch, 0.05))
-            e2e_mode = 'Generator3D.capture_generate (CUDA graph: H2D + encoder + decode + MC)'
+            e2e_run = gen.capture_generate(cloud_host, tips=(tips, tip_feat, touch, 0.05), group=group)
+            e2e_mode = ('Generator3D.capture_generate (CUDA graph: H2D + encoder + decode + MC)' if world == 1 else
+                        'Generator3D.capture_generate (one CUDA graph per rank: rank 0 H2D + encoder, NCCL broadcast of the '
+                        'feature grid, slab decode, per-slab marching cubes, gather of mesh pieces on rank 0)')
         except Exception as e:  # noqa: BLE001
+            ok.zero_()
             e2e_run, e2e_mode = None, 'Generator3D.generate_mesh (eager; graph capture failed: %s)' % type(e).__name__
+        if world > 1:
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if ok.item() == 0:
+                e2e_run = None
+                if e2e_mode.startswith('Generator3D.capture'):
+                    e2e_mode = 'Generator3D.generate_mesh (eager; graph capture failed on a peer)'
     for s in range(max(args.warmup, 1) + args.steps):
         if e2e_run is not None:
-            torch.cuda.synchronize(dev)
+            barrier()
             t0 = time.perf_counter()
             tip_feat.copy_(tip_feat_host, non_blocking=True)     # H2D of the fingertip features
-            vh, fh = e2e_run()                                   # H2D cloud + encode + decode + MC, mesh D2H
-            torch.cuda.synchronize(dev)
+            res = e2e_run()                                      # H2D cloud + encode [+ broadcast] + decode + MC, mesh D2H
+            barrier()
             if s >= max(args.warmup, 1):
                 e2e_times.append(time.perf_counter() - t0)
-                h2d = cloud_host.numel() * 4 + tip_feat_host.numel() * 4
-                d2h = vh.size * 4 + fh.size * 4 + 16
+                if res is not None:
+                    vh, fh = res
+                    h2d = cloud_host.numel() * 4 + tip_feat_host.numel() * 4
+                    d2h = vh.size * 4 + fh.size * 4 + 16
             continue
         barrier()
         t0 = time.perf_counter()
         with torch.no_grad():
             cc = encode_features()                               # H2D of the pinned cloud + encoder (+ broadcast)
             tf = tip_feat_host.to(dev, non_blocking=True)        # H2D of the fingertip features
-            grid, keys = gen.eval_lattice(cc, tips=(tips, tf, touch, 0.05), group=group, exchange=args.exchange)
-            if grid is not None:
-                vv, ff = gen.extract_mesh(grid, keys)            # reads the two counters (D2H)
-                if rank == 0:
-                    vh, fh = gen._to_host(vv, ff)                # mesh D2H into pinned buffers
+            if world > 1 and args.exchange == 'mesh':
+                res = gen.generate_mesh(c=cc, tips=(tips, tf, touch, 0.05), group=group, exchange='mesh')
+                if res is not None:
+                    vh, fh = res
+            else:
+                grid, keys = gen.eval_lattice(cc, tips=(tips, tf, touch, 0.05), group=group, exchange=args.exchange)
+                if grid is not None:
+                    vv, ff = gen.extract_mesh(grid, keys)            # reads the two counters (D2H)
+                    if rank == 0:
+                        vh, fh = gen._to_host(vv, ff)                # mesh D2H into pinned buffers
         barrier()
         if s >= max(args.warmup, 1):
             e2e_times.append(time.perf_counter() - t0)
@@ -486,35 +578,43 @@ def run_ours(args, rank, local_rank, world):
                   'hbm_frac_of_measured': hbm_gbs / measured['hbm_gbs'] if 'hbm_gbs' in measured else None,
                   'traffic': traffic}
         if args.variant >= 2:
-            # executed tensor work per 128-query tile: per 32x32 matrix (3 per block) either 12 TF32 MMAs
-            # (3xTF32) or 4 TF32 + 4 BF16 MMAs (mixed), plus one TF32 bias MMA per step; an MMA is
-            # M128 x N32 x (K8 tf32 | K16 bf16) x 2 FLOP
+            # Denominator: the TF32 tensor peak MEASURED in this run (cuBLAS TF32 GEMM 8192^3, best of 10 — the
+            # method MEASURED_PEAKS.json uses for bf16).  fp32 fidelity on the TF32 pipe takes 3 passes (3xTF32:
+            # hi*hi + lo*hi + hi*lo), so the ceiling for ALGORITHMIC fp32 FLOPs is peak / 3 ("measured
+            # tensor peak of the precision used x passes"); the mixed mode (TF32 + BF16 corrections) needs
+            # 1 TF32 pass + 1 BF16 pass over K = 64, i.e. 1 + 2/2 = 2 TF32-pass equivalents.
+            tf32_peak, bf16_now = measure_tensor_peaks(dev)
             nb_ = 5
             mixed = args.variant in (4, 6)
             split = 2 if args.variant in (5, 6) else 1
+            passes = 2.0 if mixed else 3.0
+            alg_tflops = achieved / 1e12
+            ceiling = tf32_peak / passes
+            # executed tensor work (bias K-blocks and K padding included), reported separately, NOT the fraction:
             tf32_mmas = (4 if mixed else 12) * (3 * nb_) + (2 * nb_ + 1)
             bf16_mmas = 4 * (3 * nb_) if mixed else 0
             tf32_fpq = tf32_mmas * 128 * 32 * 8 * 2 / 128.0
             bf16_fpq = bf16_mmas * 128 * 32 * 16 * 2 / 128.0
-            tensor_flop_per_query = tf32_fpq + bf16_fpq
-            t_achieved = kq * tensor_flop_per_query / (k_ms * 1e-3) / 1e12
-            tf32_peak = bf16_peak / 2.0
-            # fraction of the kernel time the tensor pipe would need at peak rate for the executed MMAs
-            frac = kq * (tf32_fpq / (tf32_peak * 1e12) + bf16_fpq / (bf16_peak * 1e12)) / (k_ms * 1e-3)
+            exec_frac = kq * (tf32_fpq / (tf32_peak * 1e12) + bf16_fpq / (bf16_now * 1e12)) / (k_ms * 1e-3)
             kname = '%s<dense> (tcgen05 %s, %d thread%s per query)' % (
                 'decoder_tc2_kernel' if split == 2 else 'decoder_tc_kernel',
                 'kind::tf32 main + kind::f16 BF16 corrections' if mixed else 'kind::tf32, 3xTF32',
                 split, 's' if split > 1 else '')
             roofline = dict(common, bound='tensor', kernel=kname,
-                            achieved=t_achieved, peak=t_achieved / frac, unit='TFLOP/s', frac=frac,
-                            peak_source='TF32 dense = 1/2 of the %s bf16 cuBLAS burst peak (%.1f TFLOP/s, %s); '
-                                        'MEASURED_PEAKS.json has no TF32 figure%s'
-                                        % ('measured' if 'bf16_tflops' in measured else 'fallback', bf16_peak, peak_tag,
-                                           '; BF16 MMAs counted against the bf16 peak' if mixed else ''),
-                            tensor_flop_per_query=tensor_flop_per_query,
-                            note='3xTF32 executes 3.16x the algorithmic FLOPs to keep fp32 accuracy (the mixed mode '
-                                 '2.2x of them in TF32-time); the kernel is bound by the per-warp phase chain, not by '
-                                 'the tensor pipe: see profiles/decoder_tc_ncu_summary.json and DESIGN.md 4.1')
+                            achieved=alg_tflops, peak=ceiling, unit='TFLOP/s', frac=alg_tflops / ceiling,
+                            peak_source='measured in this run: cuBLAS TF32 GEMM 8192^3 burst = %.1f TFLOP/s (bf16 %.1f; '
+                                        'MEASURED_PEAKS.json bf16 %.1f), divided by %g passes (%s)'
+                                        % (tf32_peak, bf16_now, bf16_peak, passes,
+                                           'TF32 main product + BF16 K=64 correction product' if mixed else '3xTF32'),
+                            tf32_peak_measured_tflops=tf32_peak, passes=passes,
+                            executed_tensor_flop_per_query=tf32_fpq + bf16_fpq,
+                            executed_tensor_tflops=kq * (tf32_fpq + bf16_fpq) / (k_ms * 1e-3) / 1e12,
+                            executed_frac_of_tensor_peak=exec_frac,
+                            traffic_source='dram__bytes_read+write of one `ncu --set full` capture of this kernel at '
+                                           'this shape, read from profiles/%s (not re-measured in this run)'
+                                           % os.path.basename(prof),
+                            note='frac = algorithmic FLOPs (30 976 per query) x passes / kernel time / measured TF32 peak; '
+                                 'executed_* also counts the bias K-blocks and K padding the kernel issues')
         else:
             roofline = dict(common, bound='fp32', kernel='decoder_kernel<dense> (SIMT)', achieved=achieved / 1e12,
                             peak=fp32_peak / 1e12, unit='TFLOP/s', frac=achieved / fp32_peak,
@@ -532,7 +632,8 @@ def run_ours(args, rank, local_rank, world):
                     'ms_per_step': float(e2e_t.item()) / args.steps * 1e3,
                     'path': e2e_mode + ': pinned cloud -> H2D -> LocalPoolPointnet+UNet3D -> decode -> marching '
                             'cubes -> mesh D2H (pinned)'},
-            'gpu_launches': args.steps * 5,  # per step: 1 fused decoder + 4 marching-cubes kernels
+            # per step: 1 fused decoder + 3 marching-cubes kernels [+ 4 exchange kernels when N>1, mesh exchange]
+            'gpu_launches': args.steps * (4 + (4 if (world > 1 and args.exchange == 'mesh') else 0)),
             'stage_ms': ({'decode_plus_exchange': float(np.mean(dec_ms)), 'marching_cubes':
                           float(np.mean(step_ms)) - float(np.mean(dec_ms))} if dec_ms is not None else
                          {'decoder_kernel_alone': k_ms, 'rest_of_step(exchange+marching_cubes)':
@@ -542,7 +643,12 @@ def run_ours(args, rank, local_rank, world):
             'clocks': clocks.summary(), 'wall_s_timed_region': wall,
         }
         if world > 1:
+            line['identity_ok'] = bool(identity and identity['ok'])
+            line['identity'] = identity
             line['exchange'] = args.exchange if exchange_note is None else exchange_note
+            if gen._mesh_ex is not None:
+                line['exchange'] += (' (per-slab marching cubes, mesh pieces gathered on rank 0 by device-side signalling; '
+                                     'timed out: %s)' % gen._mesh_ex.timed_out())
             if gen._fused is not None:
                 line['exchange'] += ' (NVLS multicast stores)' if gen._fused.grid_multicast else ' (unicast peer stores)'
             if gen._root_ex is not None:
@@ -554,8 +660,8 @@ def run_ours(args, rank, local_rank, world):
             line['cpu_baseline'] = {
                 'value': ref.n / sec, 'unit': UNIT, 'cores': ref.cores, 'kind': 'port',
                 'sample': '%d consecutive lattice points of the %d^3 lattice, best of 3 after 1 warm-up, oracle port '
-                          'of Generator3D.eval_points + LocalDecoder.forward_img (torch CPU ops, 100k chunks)'
-                          % (ref.n, nx)}
+                          'of Generator3D.eval_points + LocalDecoder.forward_img (torch CPU ops, 100k chunks) + numpy '
+                          'marching cubes on those rows; a rate' % (ref.n, nx)}
             refg = CpuReference(nx, 16 * args.cpu_sample)
             refg.run_torch_eager_gpu()
             secg = min(refg.run_torch_eager_gpu() for _ in range(3))
@@ -584,15 +690,15 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-multicast', action='store_true', help='fused exchange with unicast peer stores only')
     ap.add_argument('--no-graph', action='store_true', help='launch the step eagerly instead of replaying a CUDA graph')
-    ap.add_argument('--exchange', default='auto', choices=['auto', 'root', 'fused', 'nccl'],
-                    help='N>1: auto = root for N <= 4, fused for N = 8 (measured best, profiles/r01_scaling_exchanges.json); '
+    ap.add_argument('--exchange', default='auto', choices=['auto', 'mesh', 'root', 'fused', 'nccl'],
+                    help='N>1: auto = mesh (logits stay on their rank, marching cubes per slab, mesh pieces gathered on rank 0); '
                          'root = slabs pushed into rank 0 only by bulk peer copies (double-buffered, 1 barrier/step, MC on '
                          'rank 0, rank 0 decodes fewer rows); fused = decoder stores slabs into every rank (NVLS multicast); '
                          'nccl = all_gather_into_tensor')
     args = ap.parse_args()
     rank, local_rank, world = env_int('RANK', 0), env_int('LOCAL_RANK', 0), env_int('WORLD_SIZE', 1)
     if args.exchange == 'auto':
-        args.exchange = 'root' if world <= 4 else 'fused'
+        args.exchange = 'mesh'
     os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
     if args.impl == 'reference':
         run_reference(args, rank, world)

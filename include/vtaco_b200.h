@@ -346,10 +346,17 @@ int vtaco_scatter_mean(const float* c, const int32_t* idx32, int32_t B, int64_t 
  * lattice order of the owning point, then axis); faces in lattice order of the
  * cell, then table order (oracle/mc_tables.py); vertices are
  * (index_coordinate - voffset) * vscale  (0,1 -> array-index coordinates).
- * counts (device int64[2]) always receives {V, F}; if V > vertex_capacity or
- * F > face_capacity nothing is emitted and the caller re-runs phase 2 with
- * larger buffers.  phase: 1 = count, 2 = emit (after a count on the same
- * scratch), 3 = both.
+ * counts (device int64[4]) always receives {V, F, V_numbered, -}; vertices / faces beyond the
+ * given capacities are counted but not written (V > vertex_capacity or F > face_capacity: the
+ * caller re-runs phase 2 with larger buffers).  phase: 1 = count, 2 = emit (after a count on the
+ * same scratch), 3 = both.
+ * Slab mode, for extraction sharded over GPUs by x-rows ("gather of mesh pieces"):
+ * `grid` holds the slab's rows followed by up to two halo rows and x_emit = number of owned rows.
+ * Vertex ids are numbered over the whole sub-volume, but only vertices owned by rows < x_emit and
+ * faces of cells in rows < x_emit are emitted / counted (V_numbered also counts the halo rows'),
+ * so that a face may name a vertex id >= V: it is the (id - V)-th vertex of the NEXT slab.
+ * Concatenating the pieces of consecutive slabs (ids + sum of the previous slabs' V) gives
+ * exactly the mesh of the whole volume.  x_emit = 0 or nx: whole volume.
  * ------------------------------------------------------------------------- */
 typedef struct vtaco_mc_args {
   const float* grid;
@@ -363,9 +370,12 @@ typedef struct vtaco_mc_args {
   int64_t vertex_capacity;
   int32_t* faces;              /* [face_capacity][3] */
   int64_t face_capacity;
-  int64_t* counts;             /* device int64[2] */
+  int64_t* counts;             /* device int64[4] */
   float voffset, vscale;
   int32_t phase;
+  int32_t x_emit;              /* slab mode: rows [0, x_emit) are owned; 0 = all */
+  int32_t x_origin;            /* slab mode: lattice row of grid row 0 (vertex x = local row + x_origin) */
+  const float* level_ptr;      /* optional device float: the level (takes precedence; written by vtaco_exchange_level) */
 } vtaco_mc_args;
 
 int64_t vtaco_mc_scratch_bytes(int32_t nx, int32_t ny, int32_t nz);
@@ -377,6 +387,49 @@ int vtaco_grid_minmax(const float* grid, int64_t n, int32_t* keys, void* stream)
  * all ranks' tables for an all-gather, only the root's for a gather), then reset `keys` to
  * (INT32_MAX, INT32_MIN) for the next step. */
 int vtaco_publish_keys(int32_t* keys, int32_t* const* tables_host_array, int32_t n_peers, int32_t rank, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * (6b) Multi-GPU exchange of the sharded extraction (call site of the pieces:
+ * generation.py:268-272 on x-slabs).  Device-side signalling over peer-mapped memory — no host
+ * synchronisation, capturable in a CUDA graph.  Every rank owns a zero-initialised control block
+ * of VTACO_EXCHANGE_CTRL_BYTES in memory that all ranks can address (torch symmetric memory /
+ * CUDA IPC); ctrl[r] is rank r's block as mapped into THIS process.  All ranks must make the same
+ * sequence of calls.  A wait that sees no peer for ~2 s gives up and sets the int32 at
+ * VTACO_EXCHANGE_ERR_OFFSET of the local block to 1 (results are then undefined).
+ *
+ * vtaco_exchange_level: all-gather of the ranks' (min,max) ordered-int key pairs (`keys`, as the
+ *   decoder maintains them; reset to (INT32_MAX, INT32_MIN) by the call); writes
+ *   0.5f*(min+max) — skimage's level=None over the WHOLE lattice — to the float at
+ *   VTACO_EXCHANGE_LEVEL_OFFSET of the local block (pass that address as vtaco_mc_args.level_ptr).
+ * vtaco_exchange_mesh: all-gather of the pieces' (V,F) counts (the slab-mode counts of
+ *   vtaco_marching_cubes), exclusive scan, then every rank copies its vertices to
+ *   dst_vertices[r] + 3*vbase and its faces (+vbase) to dst_faces[r] + 3*fbase for every r with
+ *   non-NULL destinations (peer-mapped buffers of rank r: all ranks for an all-gather, one for a
+ *   gather).  A destination rank returns (in stream order) only after all pieces have landed;
+ *   total_counts (local device int64[2], optional) receives the mesh totals {V, F}.  Pieces that
+ *   exceed the capacities are truncated — compare the totals with the capacities.
+ *   Re-use of the destination buffers by the next step is safe when the destination rank
+ *   consumes them in stream order before its next vtaco_exchange_mesh.
+ * ------------------------------------------------------------------------- */
+#define VTACO_EXCHANGE_CTRL_BYTES 1024
+#define VTACO_EXCHANGE_ERR_OFFSET 556
+#define VTACO_EXCHANGE_LEVEL_OFFSET 560
+#define VTACO_EXCHANGE_BASE_OFFSET 568   /* int64[4]: this rank's vertex base, face base, total V, total F */
+typedef struct vtaco_exchange {
+  void* ctrl[8];
+  int32_t world, rank;
+} vtaco_exchange;
+typedef struct vtaco_mesh_piece {
+  const int64_t* counts;       /* device int64[>=2]: {V, F} of this rank's piece */
+  const float* vertices;       /* [V][3] */
+  const int32_t* faces;        /* [F][3], vertex ids local to the piece (may exceed V: next piece) */
+  float* dst_vertices[8];
+  int32_t* dst_faces[8];
+  int64_t vertex_capacity, face_capacity;   /* of every destination buffer, in vertices / faces */
+  int64_t* total_counts;
+} vtaco_mesh_piece;
+int vtaco_exchange_level(const vtaco_exchange* ex, int32_t* keys, void* stream);
+int vtaco_exchange_mesh(const vtaco_exchange* ex, const vtaco_mesh_piece* piece, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * (7) GroupNorm of the UNet3D that post-processes the feature grid

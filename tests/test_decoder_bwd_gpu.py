@@ -133,10 +133,13 @@ def test_backward_trains():
     assert losses[-1] < 0.5 * losses[0], losses[::10]
 
 
-def test_backward_rejects_point_gradients():
+def test_query_points_with_requires_grad_get_no_gradient():
+    """The reference training loop builds p with requires_grad=True (training.py:310,362,614,729,868)
+    and never reads p.grad: the call must work, p.grad stays None, parameters get their gradients."""
     g = load('decoder_grads.npz')
     W = {k[len('img_grid_relu') + 3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith('img_grid_relu.w.')}
     dec = make_decoder(W)
     p = torch.zeros(1, 4, 3, device='cuda', requires_grad=True)
-    with pytest.raises(NotImplementedError):
-        dec(p, {'grid': decoder_feats(g, 'cuda')['grid'][:1]})
+    out = dec(p, {'grid': decoder_feats(g, 'cuda')['grid'][:1]})
+    out.sum().backward()
+    assert p.grad is None and dec.fc_p.weight.grad is not None

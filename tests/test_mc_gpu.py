@@ -106,7 +106,7 @@ def test_cuda_graph_paths_match_eager():
         c = net.encode_inputs(cloud.cuda())
     graph, out = gen.capture_step(c, tips=tips)
     graph.replay()
-    V, F = [int(x) for x in out[2].cpu()]
+    V, F = [int(x) for x in out[2][:2].cpu()]
     assert F == f0.shape[0] and np.array_equal(out[1][:F].cpu().numpy(), f0)
     assert np.abs(out[0][:V].cpu().numpy() - v0).max() <= 1e-6
     # the encoder's scatter_mean uses fp32 atomics (order not fixed), so two encoder runs may differ
@@ -120,3 +120,100 @@ def test_cuda_graph_paths_match_eager():
     v2, f2 = run()
     v3, f3 = gen.generate_mesh(inputs=cloud, tips=tips)
     assert similar(f2, f3)
+
+
+def _mc_pieces(vol_t, level, slabs):
+    """slab-mode marching cubes on each x-slab (+ 2 halo rows), pieces concatenated with their bases —
+    the single-GPU emulation of the sharded extraction (csrc/mcubes.cu slab mode + exchange.cu's rebase)."""
+    from vtaco_b200.mcubes import MarchingCubes
+    ex = MarchingCubes('cuda')
+    nx = vol_t.shape[0]
+    vs, fs, base = [], [], 0
+    for x0, x1 in slabs:
+        xh = min(x1 + 2, nx)
+        v, f, counts = ex(vol_t[x0:xh], level, x_emit=x1 - x0, x_origin=x0, sync=False)
+        V, F, Vnum = [int(x) for x in counts[:3].cpu()]
+        if V > v.shape[0] or F > f.shape[0]:
+            ex._ensure(0, V + 16, F + 16)
+            v, f, counts = ex(vol_t[x0:xh], level, x_emit=x1 - x0, x_origin=x0, sync=False)
+        assert Vnum >= V
+        vs.append(v[:V].clone())
+        fs.append(f[:F].clone() + base)
+        base += V
+    return torch.cat(vs), torch.cat(fs)
+
+
+@pytest.mark.parametrize('name,slabs', [
+    ('sphere', [(0, 12), (12, 24), (24, 36), (36, 48)]),
+    ('sphere', [(0, 1), (1, 2), (2, 47), (47, 48)]),
+    ('noise', [(0, 7), (7, 8), (8, 20), (20, 22)]),
+    ('ragged', [(0, 2), (2, 5)]),
+    ('tiny', [(0, 1), (1, 2)]),
+])
+def test_slab_pieces_concatenate_to_the_whole_mesh(name, slabs):
+    """vertex / face ids and order of the concatenated slab pieces == marching cubes of the whole
+    volume, bit-for-bit (what makes the N-GPU mesh identical to the 1-GPU mesh)."""
+    from vtaco_b200.mcubes import marching_cubes
+    vol = torch.from_numpy(fields()[name]).cuda()
+    level = 0.0 if name != 'tiny' else 3.5
+    v, f = marching_cubes(vol, level)
+    pv, pf = _mc_pieces(vol, level, slabs)
+    assert pv.shape == v.shape and pf.shape == f.shape
+    assert torch.equal(pf, f) and torch.equal(pv, v)
+
+
+def test_slab_pieces_256_lattice():
+    """the benchmarked size: 8 slabs of a decoded 256^3 lattice reproduce the whole mesh."""
+    from vtaco_b200.conv_onet.models import decoder_dict, ConvolutionalOccupancyNetwork
+    from vtaco_b200.conv_onet.generation import Generator3D
+    from vtaco_b200.mcubes import keys_to_level, marching_cubes
+    torch.manual_seed(0)
+    dec = decoder_dict['simple_local'](dim=3, c_dim=32, hidden_size=32)
+    with torch.no_grad():
+        for b in dec.blocks:
+            b.fc_1.weight.normal_(0, 0.1)
+    net = ConvolutionalOccupancyNetwork(dec, None, device='cuda')
+    gen = Generator3D(net, device='cuda', resolution0=64, with_img=False, padding=0.1, input_type='pointcloud')
+    grid, keys = gen.eval_lattice({'grid': torch.randn(1, 32, 64, 64, 64, device='cuda')})
+    level = keys_to_level(keys)
+    v, f = marching_cubes(grid, level)
+    pv, pf = _mc_pieces(grid, level, [(32 * r, 32 * r + 32) for r in range(8)])
+    assert f.shape[0] > 1000 and torch.equal(pf, f) and torch.equal(pv, v)
+
+
+def test_exchange_kernels_world_1():
+    """vtaco_exchange_level / vtaco_exchange_mesh with a single rank (plain device memory as the
+    control block): level == 0.5*(min+max) of the published keys, the piece lands rebased at base 0,
+    totals and sequence numbers advance; three steps in a row (double-buffer parity)."""
+    import ctypes as C
+    from vtaco_b200 import _abi
+    L = _abi.lib()
+    dev = torch.device('cuda')
+    ctrl = torch.zeros(_abi.EXCHANGE_CTRL_BYTES // 4, dtype=torch.int32, device=dev)
+    ex = _abi.Exchange()
+    ex.ctrl[0], ex.world, ex.rank = ctrl.data_ptr(), 1, 0
+    st = _abi.stream_ptr(dev)
+    for step in range(3):
+        g = torch.randn(1000, device=dev) * (step + 1)
+        keys = torch.zeros(2, dtype=torch.int32, device=dev)
+        _abi.check(L.vtaco_grid_minmax(_abi.ptr(g), g.numel(), _abi.ptr(keys), st), 'minmax')
+        _abi.check(L.vtaco_exchange_level(C.byref(ex), _abi.ptr(keys), st), 'level')
+        level = ctrl[_abi.EXCHANGE_LEVEL_OFFSET // 4:_abi.EXCHANGE_LEVEL_OFFSET // 4 + 1].view(torch.float32).item()
+        want = (torch.tensor(0.5) * (g.min().cpu() + g.max().cpu())).item()
+        assert level == want
+        assert keys.tolist() == [2 ** 31 - 1, -2 ** 31]          # reset for the next step
+        V, F = 50 + step, 80 + step
+        verts = torch.randn(V, 3, device=dev)
+        faces = torch.randint(0, V, (F, 3), dtype=torch.int32, device=dev)
+        counts = torch.tensor([V, F, V, 0], dtype=torch.int64, device=dev)
+        dv = torch.zeros(100, 3, device=dev)
+        df = torch.zeros(100, 3, dtype=torch.int32, device=dev)
+        tot = torch.zeros(2, dtype=torch.int64, device=dev)
+        m = _abi.MeshPiece()
+        m.counts, m.vertices, m.faces = counts.data_ptr(), verts.data_ptr(), faces.data_ptr()
+        m.dst_vertices[0], m.dst_faces[0] = dv.data_ptr(), df.data_ptr()
+        m.vertex_capacity, m.face_capacity, m.total_counts = 100, 100, tot.data_ptr()
+        _abi.check(L.vtaco_exchange_mesh(C.byref(ex), C.byref(m), st), 'mesh')
+        assert tot.tolist() == [V, F]
+        assert torch.equal(dv[:V], verts) and torch.equal(df[:F], faces)
+        assert ctrl[_abi.EXCHANGE_ERR_OFFSET // 4].item() == 0

@@ -48,6 +48,9 @@ def _worker(rank, world, port, nx, q, exchange='nccl'):
         if exchange == 'root':
             _root_worker(gen, c, nx, rank, q)
             return
+        if exchange == 'mesh':
+            _mesh_worker(gen, c, nx, rank, q)
+            return
         grid, keys = gen.eval_lattice(c, group=dist.group.WORLD, exchange=exchange)
         v, f = gen.extract_mesh(grid, keys)
         v, f = v.clone(), f.clone()
@@ -62,6 +65,32 @@ def _worker(rank, world, port, nx, q, exchange='nccl'):
         q.put((rank, bool(ok), bool(ok_mesh), int(f.shape[0])))
     finally:
         dist.destroy_process_group()
+
+
+def _mesh_worker(gen, c, nx, rank, q):
+    """sharded marching cubes + gather of mesh pieces: eager (with buffer growth), then CUDA-graph
+    replays; the assembled mesh must equal the single-GPU mesh bit-for-bit (ids and order too)."""
+    single, skeys = gen.eval_lattice(c, group=False)
+    v1, f1 = [t.clone() for t in gen.extract_mesh(single.clone(), skeys.clone())]
+    ok, ok_mesh = True, True
+    for gather in ('root', 'all'):
+        gen.mesh_gather = gather
+        res = gen.generate_mesh(c=c, group=dist.group.WORLD, exchange='mesh', to_host=False)
+        if rank == 0 or gather == 'all':
+            ok = ok and res is not None and torch.equal(res[0], v1) and torch.equal(res[1], f1)
+        else:
+            ok = ok and res is None
+        graph, out = gen.capture_step(c, group=dist.group.WORLD, exchange='mesh')
+        for _ in range(4):
+            graph.replay()
+        torch.cuda.synchronize()
+        V, F = [int(x) for x in out[2].cpu()]
+        ok_mesh = ok_mesh and (V, F) == (v1.shape[0], f1.shape[0])
+        if rank == 0 or gather == 'all':
+            ok_mesh = ok_mesh and torch.equal(out[0][:V], v1) and torch.equal(out[1][:F], f1)
+        ok_mesh = ok_mesh and not gen._mesh_ex.timed_out()
+        dist.barrier()
+    q.put((rank, bool(ok), bool(ok_mesh), int(f1.shape[0])))
 
 
 def _root_worker(gen, c, nx, rank, q):
@@ -87,7 +116,7 @@ def _root_worker(gen, c, nx, rank, q):
     torch.cuda.synchronize()
     ok_mesh = True
     if rank == 0:
-        V, F = [int(x) for x in out[2].cpu()]
+        V, F = [int(x) for x in out[2][:2].cpu()]
         from vtaco_b200.mcubes import keys_to_level
         ok_mesh = F == f1.shape[0] and torch.equal(out[1][:F], f1)
         nxh = np.float32(nx / 2)
@@ -96,7 +125,7 @@ def _root_worker(gen, c, nx, rank, q):
     q.put((rank, bool(ok), bool(ok_mesh), int(f1.shape[0])))
 
 
-@pytest.mark.parametrize('exchange', ['fused', 'nccl', 'root'])
+@pytest.mark.parametrize('exchange', ['mesh', 'fused', 'nccl', 'root'])
 @pytest.mark.parametrize('nx', [64, 40])
 def test_sharded_extraction_matches_single_gpu(nx, exchange):
     world = min(torch.cuda.device_count(), 4)

@@ -66,7 +66,21 @@ class McArgs(C.Structure):
         ('faces', C.c_void_p), ('face_capacity', C.c_int64),
         ('counts', C.c_void_p),
         ('voffset', C.c_float), ('vscale', C.c_float), ('phase', C.c_int32),
+        ('x_emit', C.c_int32), ('x_origin', C.c_int32), ('level_ptr', C.c_void_p),
     ]
+
+
+class Exchange(C.Structure):
+    _fields_ = [('ctrl', C.c_void_p * 8), ('world', C.c_int32), ('rank', C.c_int32)]
+
+
+class MeshPiece(C.Structure):
+    _fields_ = [('counts', C.c_void_p), ('vertices', C.c_void_p), ('faces', C.c_void_p),
+                ('dst_vertices', C.c_void_p * 8), ('dst_faces', C.c_void_p * 8),
+                ('vertex_capacity', C.c_int64), ('face_capacity', C.c_int64), ('total_counts', C.c_void_p)]
+
+
+EXCHANGE_CTRL_BYTES, EXCHANGE_ERR_OFFSET, EXCHANGE_LEVEL_OFFSET, EXCHANGE_BASE_OFFSET = 1024, 556, 560, 568
 
 
 class PackDesc(C.Structure):
@@ -154,6 +168,8 @@ _OPTIONAL = {
     'vtaco_mc_scratch_bytes': [C.c_int32, C.c_int32, C.c_int32],
     'vtaco_grid_minmax': [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p],
     'vtaco_publish_keys': [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_void_p],
+    'vtaco_exchange_level': [C.POINTER(Exchange), C.c_void_p, C.c_void_p],
+    'vtaco_exchange_mesh': [C.POINTER(Exchange), C.POINTER(MeshPiece), C.c_void_p],
     'vtaco_group_norm_cl': [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64,
                             C.c_double, C.c_void_p, C.c_void_p],
     'vtaco_group_norm': [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64,

@@ -62,6 +62,8 @@ class Generator3D(object):
         self._pin = None
         self._fused = None
         self._root_ex = None
+        self._mesh_ex = None
+        self.mesh_gather = 'root'   # exchange='mesh': 'root' = the mesh is assembled on rank 0, 'all' = on every rank
         self.root_rows = None       # exchange='root': lattice rows decoded by rank 0 (None: nx / world)
         self.use_multicast = True   # NVLS multimem.st for the fused exchange when the fabric supports it
 
@@ -171,10 +173,50 @@ class Generator3D(object):
                            sync=sync)
         return self.mc(grid, level=level, level_keys=keys, sync=sync)
 
+    def sharded_mesh(self, c, tips=None, c_img_all=None, group=None):
+        """exchange='mesh' ("gather of mesh pieces"): every rank decodes its x-slab plus two
+        halo rows into its LOCAL grid, the ranks agree on the iso-level (16 B each), every rank runs
+        marching cubes on its slab and the pieces are concatenated into the destination rank(s) —
+        vertex / face order and ids identical to the single-GPU mesh.  No host synchronisation;
+        returns (vertex buffer, face buffer, int64[2] totals) of vdist.MeshExchange (valid on the
+        destination ranks)."""
+        nx = self.resolution0 * 4
+        dev = self.device
+        dec = self.model.decoder
+        rank, world = vdist.rank_world(group)
+        if self._grid is None or self._grid.shape[0] != nx:
+            self._grid = torch.empty((nx, nx, nx), dtype=torch.float32, device=dev)
+            self._axis = dense_axis(nx, self.padding, dev)
+        if self._keys is None:
+            self._keys_init = new_minmax_key(dev)
+            self._keys = self._keys_init.clone()
+        if self._mesh_ex is None or self._mesh_ex.gather != self.mesh_gather:
+            cap = max(1024, 12 * nx * nx)
+            self._mesh_ex = vdist.MeshExchange(dev, group, cap, 2 * cap, gather=self.mesh_gather)
+        ex = self._mesh_ex
+        x0, x1 = vdist.slab(nx, rank, world)
+        xh = min(x1 + 2, nx)          # two halo rows: the next slab's first row and the row that numbers its vertices
+        with torch.no_grad():
+            if x1 > x0:
+                dec.forward_dense(c, nx, x0=x0, x1=xh, use_img=self.with_img, c_img=c_img_all, tips=tips,
+                                  out=self._grid, minmax_key=self._keys, axis=self._axis)
+            ex.level(self._keys)          # publishes (min,max), waits for every rank's, resets the keys
+            if x1 > x0:
+                v, f, counts = self.mc(self._grid[x0:xh], level_ptr=ex.level_ptr, x_emit=x1 - x0, x_origin=x0,
+                                       voffset=np.float32(nx / 2), vscale=np.float32((1 + self.padding) / nx), sync=False)
+            else:                         # more ranks than row pairs: an empty piece
+                self.mc._ensure(0, 16, 16)
+                v, f, counts = self.mc._verts, self.mc._faces, self.mc._counts
+                counts.zero_()
+            ex.push(counts, v, f)
+        return ex.verts, ex.faces, ex.totals
+
     def lattice_and_mesh(self, c, tips=None, c_img_all=None, group=None, exchange=None):
         """One device-resident pass: lattice logits (+ exchange) and marching cubes, no host
         synchronisation.  Returns the extractor's (vertex buffer, face buffer, int64[2] counts)."""
         nx = self.resolution0 * 4
+        if exchange == 'mesh' and vdist.rank_world(group)[1] > 1:
+            return self.sharded_mesh(c, tips=tips, c_img_all=c_img_all, group=group)
         grid, keys = self.eval_lattice(c, tips=tips, c_img_all=c_img_all, group=group, exchange=exchange)
         if grid is None:      # exchange='root' on a non-root rank: the mesh is extracted by rank 0 only
             return None
@@ -188,9 +230,18 @@ class Generator3D(object):
         all buffers are baked into the graph: re-capture when they change."""
         if exchange == 'root' and vdist.rank_world(group)[1] > 1:
             return self._capture_root_steps(c, tips, c_img_all, group, warmup)
+        if exchange == 'mesh' and vdist.rank_world(group)[1] > 1:
+            for _ in range(max(1, warmup)):
+                self.sharded_mesh(c, tips, c_img_all, group)
+            self._settle_sharded(lambda: self.sharded_mesh(c, tips, c_img_all, group), group)
+            torch.cuda.synchronize(self.device)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = self.sharded_mesh(c, tips, c_img_all, group)
+            return graph, out
         for _ in range(max(1, warmup)):          # allocations, attribute set-up, rendezvous
             out = self.lattice_and_mesh(c, tips, c_img_all, group, exchange)
-        V, F = [int(x) for x in out[2].cpu()]
+        V, F = [int(x) for x in out[2][:2].cpu()]
         if V > out[0].shape[0] or F > out[1].shape[0]:
             self.mc._ensure(0, int(V * 1.5) + 16, int(F * 1.5) + 16)
             self.lattice_and_mesh(c, tips, c_img_all, group, exchange)
@@ -199,6 +250,29 @@ class Generator3D(object):
         with torch.cuda.graph(graph):
             out = self.lattice_and_mesh(c, tips, c_img_all, group, exchange)
         return graph, out
+
+    def _settle_sharded(self, step, group):
+        """After a sharded step ran: grow this rank's piece buffers and (collectively) the destination
+        buffers until the mesh fits, re-running `step` on every rank while any rank had to grow.
+        Host-synchronising — warm-up / eager path only."""
+        import torch.distributed as dist
+        ex = self._mesh_ex
+        for _ in range(4):
+            V, F = [int(x) for x in self.mc._counts[:2].cpu()]
+            tv, tf = [int(x) for x in ex.totals.cpu()]
+            grew = torch.zeros(1, device=self.device)
+            if V > self.mc._verts.shape[0] or F > self.mc._faces.shape[0]:
+                self.mc._ensure(0, int(V * 1.5) + 16, int(F * 1.5) + 16)
+                grew.fill_(1)
+            if ex.ensure_capacity(tv, tf):        # same decision on every rank
+                grew.fill_(1)
+            dist.all_reduce(grew, op=dist.ReduceOp.MAX, group=group)
+            if grew.item() == 0:
+                break
+            step()
+        if ex.timed_out():
+            raise RuntimeError('vtaco_b200: a rank did not arrive at the mesh exchange within 2 s')
+        return ex.verts, ex.faces, ex.totals
 
     def _capture_root_steps(self, c, tips, c_img_all, group, warmup):
         """exchange='root': the step alternates between two symmetric buffers, so two graphs are
@@ -209,7 +283,7 @@ class Generator3D(object):
             out = self.lattice_and_mesh(c, tips, c_img_all, group, 'root')
         need = torch.zeros(1, device=self.device)
         if rank == 0:
-            V, F = [int(x) for x in out[2].cpu()]
+            V, F = [int(x) for x in out[2][:2].cpu()]
             if V > out[0].shape[0] or F > out[1].shape[0]:
                 self.mc._ensure(0, int(V * 1.5) + 16, int(F * 1.5) + 16)
                 need.fill_(1)
@@ -236,40 +310,70 @@ class Generator3D(object):
 
         return _Alternating(), outs[1]
 
-    def capture_generate(self, inputs_host, tips=None, warmup=2):
-        """CUDA graph of the whole single-GPU extraction for a fixed input shape:
+    def capture_generate(self, inputs_host, tips=None, warmup=2, group=None):
+        """CUDA graph of the whole extraction for a fixed input shape:
         H2D copy of the (pinned) host cloud -> encoder (PointNet kernels + UNet/UNet3D) ->
         lattice decode -> marching cubes.  Usage:
             run = gen.capture_generate(pinned_cloud, tips)      # once per shape
             pinned_cloud.copy_(new_cloud); v, f = run()         # per scene (host arrays)
         The tip positions / touch mask are baked in; tip features are read from the tensor
-        passed in `tips` at replay time (update it in place)."""
-        if not inputs_host.is_pinned():
+        passed in `tips` at replay time (update it in place).
+        With a process group (one process per GPU): rank 0 copies and encodes, the channels-last
+        feature grid is broadcast (NCCL, captured in the graph) so that every rank decodes from
+        identical bits, then the sharded step (exchange='mesh') runs; `run()` returns the mesh on
+        the destination rank(s) and None elsewhere.  Every rank must call `run()` per scene."""
+        rank, world = vdist.rank_world(group)
+        if rank == 0 and not inputs_host.is_pinned():
             raise ValueError('inputs_host must be a pinned host tensor (it is re-read at every replay)')
         dev = self.device
         static_in = torch.empty(inputs_host.shape, dtype=torch.float32, device=dev)
         self.model.eval()
+        feat = None
+        if world > 1:
+            import torch.distributed as dist
+            R = self.model.encoder.reso_grid
+            feat = torch.empty((1, R, R, R, self.model.encoder.c_dim), dtype=torch.float32, device=dev)
 
         def body():
-            static_in.copy_(inputs_host, non_blocking=True)
-            c = self.model.encode_inputs(static_in)
-            return self.lattice_and_mesh(c, tips=tips)
+            if world == 1:
+                static_in.copy_(inputs_host, non_blocking=True)
+                c = self.model.encode_inputs(static_in)
+                return self.lattice_and_mesh(c, tips=tips)
+            if rank == 0:
+                static_in.copy_(inputs_host, non_blocking=True)
+                g = self.model.encode_inputs(static_in)['grid'].permute(0, 2, 3, 4, 1)
+                if g.is_contiguous():
+                    feat_r = g
+                else:
+                    feat.copy_(g)
+                    feat_r = feat
+            else:
+                feat_r = feat
+            dist.broadcast(feat_r, 0, group=group)
+            return self.sharded_mesh({'grid': feat_r.permute(0, 4, 1, 2, 3)}, tips=tips, group=group)
 
         with torch.no_grad():
             for _ in range(max(1, warmup)):
                 out = body()
-            V, F = [int(x) for x in out[2].cpu()]
-            if V > out[0].shape[0] or F > out[1].shape[0]:
-                self.mc._ensure(0, int(V * 1.5) + 16, int(F * 1.5) + 16)
-                body()
+            if world > 1:
+                self._settle_sharded(body, group)
+            else:
+                V, F = [int(x) for x in out[2][:2].cpu()]
+                if V > out[0].shape[0] or F > out[1].shape[0]:
+                    self.mc._ensure(0, int(V * 1.5) + 16, int(F * 1.5) + 16)
+                    body()
             torch.cuda.synchronize(dev)
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            # thread_local: NCCL's watchdog thread polls CUDA events while we capture
+            with torch.cuda.graph(graph, capture_error_mode='thread_local' if world > 1 else 'global'):
                 out = body()
+        has_result = world == 1 or self._mesh_ex.has_result()
 
         def run():
             graph.replay()
-            V, F = [int(x) for x in out[2].cpu()]           # D2H of the two counters (synchronises)
+            if not has_result:
+                return None
+            V, F = [int(x) for x in out[2][:2].cpu()]           # D2H of the two counters (synchronises)
             if V > out[0].shape[0] or F > out[1].shape[0]:
                 raise RuntimeError('mesh larger than the captured buffers (%d vertices, %d faces): re-capture' % (V, F))
             return self._to_host(out[0][:V], out[1][:F])
@@ -285,6 +389,16 @@ class Generator3D(object):
         with torch.no_grad():
             if c is None:
                 c = self.model.encode_inputs(inputs.to(dev, non_blocking=True))
+            if exchange == 'mesh' and vdist.rank_world(group)[1] > 1:
+                # sharded marching cubes; with gather='root' only rank 0 gets the mesh (others: None)
+                step = lambda: self.sharded_mesh(c, tips=tips, c_img_all=c_img_all, group=group)   # noqa: E731
+                step()
+                vb, fb, tot = self._settle_sharded(step, group)
+                if not self._mesh_ex.has_result():
+                    return None
+                V, F = [int(x) for x in tot.cpu()]
+                v, f = vb[:V], fb[:F]
+                return self._to_host(v, f) if to_host else (v, f)
             grid, keys = self.eval_lattice(c, tips=tips, c_img_all=c_img_all, group=group, exchange=exchange)
             v, f = self.extract_mesh(grid, keys)
         if to_host:

@@ -7,19 +7,27 @@
 // are not available offline — parity with skimage is UNPINNED, parity with the oracle is
 // bit-exact on case indices / faces and to rounding on vertices).
 //
-// HBM-bound stream compaction in four launches:
+// HBM-bound stream compaction in three launches (no scan kernel):
 //   classify : 1 thread / run of 8 consecutive z points — four rows of 9 samples as float4
-//              loads -> "above" bit rows -> per point 3-bit own-edge mask + triangle count
-//              (1 byte code, 8 B store per thread), per-block totals
-//   scan     : one block, exclusive scan of the per-block totals, grand totals
-//   vertices : blocks without a cut edge exit at once; otherwise intra-block scan -> vertex
-//              base id per point, vertices of the point's own cut edges (inverse-distance
-//              weighting in double, like Lewiner's code)
-//   faces    : blocks without a triangle exit at once; otherwise intra-block scan -> triangle
-//              base per cell, vertex ids looked up from the owners' base ids;
+//              loads -> "above" bit rows -> per point 3-bit own-edge mask + triangle count;
+//              the 8 one-byte codes of a run are stored only by blocks that contain a cut edge
+//              or triangle; per-block totals + one 64-bit atomic per block into the totals of
+//              its super-block (256 blocks)
+//   vertices : blocks without a cut edge exit at once; an active block forms its own exclusive
+//              prefix from the super-block totals and the <= 255 block totals before it (two
+//              level, so no dependent scan launch), then intra-block scan -> vertex base id
+//              per point, vertices of the point's own cut edges (inverse-distance weighting in
+//              double, like Lewiner's code); one extra block writes the counters
+//   faces    : same for triangles; vertex ids looked up from the owners' base ids;
 //              output order = lattice order, then table order.
-// Algorithmic bytes: 4*n (grid) + 12*V + 12*F; scratch traffic adds ~1 B / point + the
-// active blocks' base ids.
+// Slab mode (x_emit < nx; multi-GPU extraction, SURVEY 8e "gather of mesh pieces"): the volume
+// holds the rank's x-rows plus two halo rows; vertex ids are numbered over the whole volume (so a
+// halo-row vertex gets the id it has as the NEXT rank's first vertices), but only vertices owned
+// by rows < x_emit and faces of cells in rows < x_emit are emitted and counted.  The pieces of
+// consecutive slabs then concatenate to exactly the single-volume mesh (ids + the vertex base of
+// the slab).
+// Algorithmic bytes: 4*n (grid) + 12*V + 12*F; scratch traffic adds the active blocks' codes
+// and base ids.
 #include "common.cuh"
 #include "mc_tables.h"
 #include <float.h>
@@ -29,19 +37,23 @@ namespace vtaco {
 constexpr int kMcThreads = 256;   // threads per block
 constexpr int kMcRun = 8;         // consecutive z points per thread
 constexpr int kMcBlockPts = kMcThreads * kMcRun;
+constexpr int kMcSuper = 256;     // blocks per super-block of the two-level prefix
 
 struct McParams {
   const float* grid;
   int nx, ny, nz, nzc;            // nzc = ceil(nz / kMcRun) runs per (x,y) row
+  int x_emit;                     // rows [0, x_emit) emit vertices / faces (== nx: whole volume)
+  int x_origin;                   // lattice row of the sub-volume's row 0 (vertex coordinates are global)
   long long npts, nruns;
   float level;
   const int32_t* level_keys;
   int n_level_keys;
+  const float* level_ptr;
   uint8_t* code;                  // [nruns][8]: bits 0-2 own-edge mask (x,y,z), bits 3-5 triangle count
   uint32_t* vbase;                // [nruns][8]: id of the first vertex owned by the point (active blocks only)
-  uint2* block_sums;
-  ulonglong2* block_offs;
-  int nblocks;
+  unsigned long long* block_sums; // [nblocks]: vertices | triangles << 32
+  unsigned long long* super_sums; // [nsuper], zeroed before classify
+  int nblocks, nsuper;
   long long* counts;
   float* verts;
   long long vcap;
@@ -51,6 +63,7 @@ struct McParams {
 };
 
 __device__ __forceinline__ float mc_level(const McParams& P) {
+  if (P.level_ptr) return *P.level_ptr;
   if (P.level_keys) {
     int32_t lo = P.level_keys[0], hi = P.level_keys[1];
     for (int r = 1; r < P.n_level_keys; ++r) {
@@ -93,6 +106,35 @@ __device__ __forceinline__ unsigned block_scan_excl(unsigned v, unsigned& total)
   return warp_excl[w] + inc - v;
 }
 
+// sum of a 64-bit value over the block (all threads get it)
+__device__ __forceinline__ unsigned long long block_sum64(unsigned long long v) {
+  constexpr int kWarps = kMcThreads / 32;
+  __shared__ unsigned long long part[kWarps];
+  __shared__ unsigned long long tot64;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long s = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) s += part[w];
+    tot64 = s;
+  }
+  __syncthreads();
+  return tot64;
+}
+
+// exclusive prefix (vertices | triangles << 32) of block b: whole super-blocks before it + the
+// blocks of its own super-block before it
+__device__ __forceinline__ unsigned long long block_prefix(const McParams& P, int b) {
+  const int sb = b / kMcSuper, first = sb * kMcSuper;
+  unsigned long long acc = 0;
+  for (int i = threadIdx.x; i < sb; i += kMcThreads) acc += P.super_sums[i];
+  if (first + (int)threadIdx.x < b) acc += P.block_sums[first + threadIdx.x];
+  return block_sum64(acc);
+}
+
 // run -> lattice coordinates of its first point
 __device__ __forceinline__ void run_coords(const McParams& P, long long run, int& i, int& j, int& k0) {
   const unsigned ru = (unsigned)run;           // nruns < 2^31 (checked by the host wrapper)
@@ -110,10 +152,11 @@ __device__ __forceinline__ unsigned row_bits(const McParams& P, int i, int j, in
   j = min(j, P.ny - 1);
   const float* row = P.grid + ((long long)i * P.ny + j) * P.nz;
   unsigned bits = 0;
-  if (k0 + kMcRun < P.nz && (P.nz & 3) == 0) {
+  if ((P.nz & 7) == 0) {   // uniform over the grid: the last run of a row takes this path too (a per-lane
+                           // test sent one lane of EVERY warp through the scalar path below: 750 instructions per thread)
     const float4 a = __ldg(reinterpret_cast<const float4*>(row + k0));
     const float4 b = __ldg(reinterpret_cast<const float4*>(row + k0 + 4));
-    const float c = __ldg(row + k0 + 8);
+    const float c = __ldg(row + min(k0 + 8, P.nz - 1));
     bits = (unsigned)(a.x > level) | ((unsigned)(a.y > level) << 1) | ((unsigned)(a.z > level) << 2) |
            ((unsigned)(a.w > level) << 3) | ((unsigned)(b.x > level) << 4) | ((unsigned)(b.y > level) << 5) |
            ((unsigned)(b.z > level) << 6) | ((unsigned)(b.w > level) << 7) | ((unsigned)(c > level) << 8);
@@ -140,7 +183,8 @@ __device__ __forceinline__ unsigned run_codes(const McParams& P, int i, int j, i
   const unsigned fy = hy ? ((r00 ^ r01) & m8) : 0u;
   const unsigned fz = (r00 ^ (r00 >> 1)) & mz;
   const unsigned any = r00 | r10 | r01 | r11, all = r00 & r10 & r01 & r11;
-  const unsigned cut = (hx && hy) ? (((any | (any >> 1)) & ~(all & (all >> 1))) & mz) : 0u;
+  // halo rows (i >= x_emit) keep their vertex flags (the numbering runs through them) but own no cells
+  const unsigned cut = (hx && hy && i < P.x_emit) ? (((any | (any >> 1)) & ~(all & (all >> 1))) & mz) : 0u;
   codes = 0;
   unsigned todo = fx | fy | fz | cut;
   unsigned packed = __popc(fx) + __popc(fy) + __popc(fz);
@@ -165,59 +209,67 @@ __device__ __forceinline__ unsigned run_codes(const McParams& P, int i, int j, i
 __global__ void __launch_bounds__(kMcThreads) mc_classify_kernel(const __grid_constant__ McParams P) {
   const long long run = (long long)blockIdx.x * kMcThreads + threadIdx.x;
   unsigned packed = 0;
+  unsigned long long codes = 0;
   if (run < P.nruns) {
     int i, j, k0;
     run_coords(P, run, i, j, k0);
-    unsigned long long codes;
     packed = run_codes(P, i, j, k0, mc_level(P), codes);
-    reinterpret_cast<unsigned long long*>(P.code)[run] = codes;
   }
   unsigned total;
   block_scan_excl(packed, total);
-  if (threadIdx.x == 0) P.block_sums[blockIdx.x] = make_uint2(total & 0xffffu, total >> 16);
+  if (total != 0 && run < P.nruns) reinterpret_cast<unsigned long long*>(P.code)[run] = codes;   // inactive blocks are never read
+  if (threadIdx.x == 0) {
+    const unsigned long long s = (unsigned long long)(total & 0xffffu) | ((unsigned long long)(total >> 16) << 32);
+    P.block_sums[blockIdx.x] = s;
+    if (s) atomicAdd(P.super_sums + blockIdx.x / kMcSuper, s);
+  }
 }
 
-__global__ void __launch_bounds__(1024) mc_scan_blocks_kernel(const __grid_constant__ McParams P) {
-  __shared__ unsigned long long sv[1024], sf[1024];
-  const int t = threadIdx.x;
-  const int per = (P.nblocks + 1023) / 1024;
-  const int b0 = t * per, b1 = min(P.nblocks, b0 + per);
-  unsigned long long v = 0, f = 0;
-  for (int b = b0; b < b1; ++b) { const uint2 s = P.block_sums[b]; v += s.x; f += s.y; }
-  sv[t] = v; sf[t] = f;
-  __syncthreads();
-  for (int d = 1; d < 1024; d <<= 1) {  // Hillis-Steele inclusive scan
-    unsigned long long av = 0, af = 0;
-    if (t >= d) { av = sv[t - d]; af = sf[t - d]; }
-    __syncthreads();
-    sv[t] += av; sf[t] += af;
-    __syncthreads();
+// the extra block of the vertices kernel: counts[0] = vertices owned by rows < x_emit,
+// counts[1] = triangles (halo cells were classified as empty), counts[2] = vertices of the whole
+// volume, halo rows included
+__device__ void mc_write_counts(const McParams& P) {
+  unsigned long long acc = 0;
+  for (int i = threadIdx.x; i < P.nsuper; i += kMcThreads) acc += P.super_sums[i];
+  const unsigned long long tot = block_sum64(acc);
+  unsigned long long v_emit = tot & 0xffffffffull;
+  if (P.x_emit < P.nx) {
+    const long long r_emit = (long long)P.x_emit * P.ny * P.nzc;     // first run of the first halo row
+    const int b = (int)(r_emit / kMcThreads), t_emit = (int)(r_emit % kMcThreads);
+    const unsigned long long pre = block_prefix(P, b) & 0xffffffffull;
+    unsigned long long part = 0;
+    if ((P.block_sums[b] & 0xffffffffull) != 0 && (int)threadIdx.x < t_emit) {
+      const unsigned long long codes = reinterpret_cast<const unsigned long long*>(P.code)[(long long)b * kMcThreads + threadIdx.x];
+#pragma unroll
+      for (int t = 0; t < kMcRun; ++t) part += __popc((unsigned)(codes >> (8 * t)) & 7u);
+    }
+    v_emit = pre + block_sum64(part);
   }
-  unsigned long long ov = sv[t] - v, of = sf[t] - f;
-  for (int b = b0; b < b1; ++b) {
-    const uint2 s = P.block_sums[b];
-    P.block_offs[b] = make_ulonglong2(ov, of);
-    ov += s.x; of += s.y;
+  if (threadIdx.x == 0) {
+    P.counts[0] = (long long)v_emit;
+    P.counts[1] = (long long)(tot >> 32);
+    P.counts[2] = (long long)(tot & 0xffffffffull);
   }
-  if (t == 1023) { P.counts[0] = (long long)sv[1023]; P.counts[1] = (long long)sf[1023]; }
 }
 
 // vertex base ids + vertices; blocks without any cut edge return at once.
 __global__ void __launch_bounds__(kMcThreads) mc_vertices_kernel(const __grid_constant__ McParams P) {
-  if (P.block_sums[blockIdx.x].x == 0) return;
+  if ((int)blockIdx.x == P.nblocks) { mc_write_counts(P); return; }
+  if ((P.block_sums[blockIdx.x] & 0xffffffffull) == 0) return;
   const long long run = (long long)blockIdx.x * kMcThreads + threadIdx.x;
-  const bool fits = P.counts[0] <= P.vcap && P.counts[1] <= P.fcap && P.counts[0] < 0x7fffffffll;
   unsigned long long codes = 0;
   if (run < P.nruns) codes = reinterpret_cast<const unsigned long long*>(P.code)[run];
   unsigned nv = 0;
 #pragma unroll
   for (int t = 0; t < kMcRun; ++t) nv += __popc((unsigned)(codes >> (8 * t)) & 7u);
+  const unsigned long long pre = block_prefix(P, blockIdx.x) & 0xffffffffull;
   unsigned total;
   const unsigned excl = block_scan_excl(nv, total);
   if (run >= P.nruns) return;
-  unsigned long long vb = P.block_offs[blockIdx.x].x + excl;
+  unsigned long long vb = pre + excl;
   int i, j, k0;
   run_coords(P, run, i, j, k0);
+  const bool emit = i < P.x_emit;
   const double level = (double)mc_level(P);
   const long long stride[3] = {(long long)P.ny * P.nz, (long long)P.nz, 1};
   uint32_t vb_out[kMcRun];
@@ -225,23 +277,25 @@ __global__ void __launch_bounds__(kMcThreads) mc_vertices_kernel(const __grid_co
   for (int t = 0; t < kMcRun; ++t) {
     vb_out[t] = (uint32_t)vb;
     const unsigned flags = (unsigned)(codes >> (8 * t)) & 7u;
-    if (flags && fits) {
+    if (flags && emit) {
       const int k = k0 + t;
       const long long p = ((long long)i * P.ny + j) * P.nz + k;
       const double d0 = fabs((double)P.grid[p] - level);
-      const float base[3] = {(float)i, (float)j, (float)k};
+      const float base[3] = {(float)(i + P.x_origin), (float)j, (float)k};
 #pragma unroll
       for (int a = 0; a < 3; ++a) {
         if (flags & (1u << a)) {
-          const double d1 = fabs((double)P.grid[p + stride[a]] - level);
-          const double w0 = 1.0 / ((double)FLT_EPSILON + d0), w1 = 1.0 / ((double)FLT_EPSILON + d1);
-          const double tt = w1 / (w0 + w1);
-          float pos[3] = {base[0], base[1], base[2]};
-          pos[a] = (float)((double)base[a] + tt);
-          float* o = P.verts + vb * 3;
-          o[0] = (pos[0] - P.voffset) * P.vscale;
-          o[1] = (pos[1] - P.voffset) * P.vscale;
-          o[2] = (pos[2] - P.voffset) * P.vscale;
+          if ((long long)vb < P.vcap) {      // capacity overflow: counted, not written (the caller re-runs the emit phase)
+            const double d1 = fabs((double)P.grid[p + stride[a]] - level);
+            const double w0 = 1.0 / ((double)FLT_EPSILON + d0), w1 = 1.0 / ((double)FLT_EPSILON + d1);
+            const double tt = w1 / (w0 + w1);
+            float pos[3] = {base[0], base[1], base[2]};
+            pos[a] = (float)((double)base[a] + tt);
+            float* o = P.verts + vb * 3;
+            o[0] = (pos[0] - P.voffset) * P.vscale;
+            o[1] = (pos[1] - P.voffset) * P.vscale;
+            o[2] = (pos[2] - P.voffset) * P.vscale;
+          }
           ++vb;
         }
       }
@@ -260,18 +314,18 @@ __device__ __forceinline__ long long run_slot(const McParams& P, int i, int j, i
 }
 
 __global__ void __launch_bounds__(kMcThreads) mc_faces_kernel(const __grid_constant__ McParams P) {
-  if (P.block_sums[blockIdx.x].y == 0) return;
+  if ((P.block_sums[blockIdx.x] >> 32) == 0) return;
   const long long run = (long long)blockIdx.x * kMcThreads + threadIdx.x;
-  const bool fits = P.counts[0] <= P.vcap && P.counts[1] <= P.fcap && P.counts[0] < 0x7fffffffll;
   unsigned long long codes = 0;
   if (run < P.nruns) codes = reinterpret_cast<const unsigned long long*>(P.code)[run];
   unsigned nt_run = 0;
 #pragma unroll
   for (int t = 0; t < kMcRun; ++t) nt_run += ((unsigned)(codes >> (8 * t)) & 0xffu) >> 3;
+  const unsigned long long pre = block_prefix(P, blockIdx.x) >> 32;
   unsigned total;
   const unsigned excl = block_scan_excl(nt_run, total);
-  if (run >= P.nruns || !nt_run || !fits) return;
-  unsigned long long tb = P.block_offs[blockIdx.x].y + excl;
+  if (run >= P.nruns || !nt_run) return;
+  unsigned long long tb = pre + excl;
   int i, j, k0;
   run_coords(P, run, i, j, k0);
   const float level = mc_level(P);
@@ -285,6 +339,7 @@ __global__ void __launch_bounds__(kMcThreads) mc_faces_kernel(const __grid_const
                         (((r01 >> (t + 1)) & 1u) << 6) | (((r11 >> (t + 1)) & 1u) << 7);
     const int k = k0 + t;
     for (unsigned tr = 0; tr < nt; ++tr) {
+      if ((long long)(tb + tr) >= P.fcap) break;
       int32_t* o = P.faces + (tb + tr) * 3;
 #pragma unroll
       for (int corner = 0; corner < 3; ++corner) {
@@ -346,7 +401,8 @@ extern "C" int64_t vtaco_mc_scratch_bytes(int32_t nx, int32_t ny, int32_t nz) {
   if (nx < 1 || ny < 1 || nz < 1) return VTACO_ERR_INVALID_ARG;
   const long long nruns = (long long)nx * ny * ((nz + kMcRun - 1) / kMcRun);
   const long long nb = (nruns + kMcThreads - 1) / kMcThreads;
-  return mc_align(nruns * kMcRun) + mc_align(4 * nruns * kMcRun) + mc_align(8 * nb) + mc_align(16 * nb);
+  const long long nsuper = (nb + kMcSuper - 1) / kMcSuper;
+  return mc_align(nruns * kMcRun) + mc_align(4 * nruns * kMcRun) + mc_align(8 * nb) + mc_align(8 * nsuper);
 }
 
 extern "C" int vtaco_grid_minmax(const float* grid, int64_t n, int32_t* keys, void* stream) {
@@ -361,10 +417,15 @@ extern "C" int vtaco_grid_minmax(const float* grid, int64_t n, int32_t* keys, vo
   return VTACO_OK;
 }
 
+__global__ void __launch_bounds__(kMcThreads) mc_counts_kernel(const __grid_constant__ vtaco::McParams P) {
+  vtaco::mc_write_counts(P);
+}
+
 extern "C" int vtaco_marching_cubes(const vtaco_mc_args* a, void* stream) {
   if (!a || !a->grid || !a->scratch || !a->counts) return VTACO_ERR_INVALID_ARG;
   if (a->nx < 1 || a->ny < 1 || a->nz < 1) return VTACO_ERR_INVALID_ARG;
   if (a->phase < 1 || a->phase > 3) return VTACO_ERR_INVALID_ARG;
+  if (a->x_emit < 0 || a->x_emit > a->nx) return VTACO_ERR_INVALID_ARG;
   const long long n = (long long)a->nx * a->ny * a->nz;
   if (n >= (1ll << 31)) return VTACO_ERR_UNSUPPORTED;
   if (vtaco_mc_scratch_bytes(a->nx, a->ny, a->nz) > a->scratch_bytes) return VTACO_ERR_CAPACITY;
@@ -373,26 +434,30 @@ extern "C" int vtaco_marching_cubes(const vtaco_mc_args* a, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   McParams P = {};
   P.grid = a->grid; P.nx = a->nx; P.ny = a->ny; P.nz = a->nz; P.npts = n;
-  P.level = a->level; P.level_keys = a->level_keys;
+  P.x_emit = a->x_emit > 0 ? a->x_emit : a->nx;
+  P.x_origin = a->x_origin;
+  P.level = a->level; P.level_keys = a->level_keys; P.level_ptr = a->level_ptr;
   P.n_level_keys = a->n_level_keys > 1 ? a->n_level_keys : 1;
   P.nzc = (a->nz + kMcRun - 1) / kMcRun;
   P.nruns = (long long)a->nx * a->ny * P.nzc;
   P.nblocks = (int)((P.nruns + kMcThreads - 1) / kMcThreads);
+  P.nsuper = (P.nblocks + kMcSuper - 1) / kMcSuper;
   char* s = reinterpret_cast<char*>(a->scratch);
   P.code = reinterpret_cast<uint8_t*>(s); s += mc_align(P.nruns * kMcRun);
   P.vbase = reinterpret_cast<uint32_t*>(s); s += mc_align(4 * P.nruns * kMcRun);
-  P.block_sums = reinterpret_cast<uint2*>(s); s += mc_align(8ll * P.nblocks);
-  P.block_offs = reinterpret_cast<ulonglong2*>(s);
+  P.block_sums = reinterpret_cast<unsigned long long*>(s); s += mc_align(8ll * P.nblocks);
+  P.super_sums = reinterpret_cast<unsigned long long*>(s);
   P.counts = reinterpret_cast<long long*>(a->counts);
   P.verts = a->vertices; P.vcap = a->vertex_capacity;
   P.faces = a->faces; P.fcap = a->face_capacity;
   P.voffset = a->voffset; P.vscale = a->vscale;
   if (a->phase & 1) {
+    VTACO_CUDA_CHECK(cudaMemsetAsync(P.super_sums, 0, 8ll * P.nsuper, st));
     mc_classify_kernel<<<P.nblocks, kMcThreads, 0, st>>>(P);
-    mc_scan_blocks_kernel<<<1, 1024, 0, st>>>(P);
+    if (!(a->phase & 2)) mc_counts_kernel<<<1, kMcThreads, 0, st>>>(P);
   }
   if (a->phase & 2) {
-    mc_vertices_kernel<<<P.nblocks, kMcThreads, 0, st>>>(P);
+    mc_vertices_kernel<<<P.nblocks + 1, kMcThreads, 0, st>>>(P);   // + the counter block
     mc_faces_kernel<<<P.nblocks, kMcThreads, 0, st>>>(P);
   }
   VTACO_LAUNCH_CHECK();

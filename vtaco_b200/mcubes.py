@@ -34,7 +34,7 @@ class MarchingCubes(object):
         self._scratch = None
         self._verts = None
         self._faces = None
-        self._counts = torch.zeros(2, dtype=torch.int64, device=self.device)
+        self._counts = torch.zeros(4, dtype=torch.int64, device=self.device)
         self._keys = torch.zeros(2, dtype=torch.int32, device=self.device)
 
     def _ensure(self, nbytes, vcap, fcap):
@@ -45,12 +45,16 @@ class MarchingCubes(object):
         if self._faces is None or self._faces.size(0) < fcap:
             self._faces = torch.empty((int(fcap), 3), dtype=torch.int32, device=self.device)
 
-    def __call__(self, volume, level=None, level_keys=None, voffset=0.0, vscale=1.0, sync=True):
+    def __call__(self, volume, level=None, level_keys=None, voffset=0.0, vscale=1.0, sync=True,
+                 x_emit=None, x_origin=0, level_ptr=None):
         """volume: (nx,ny,nz) float32 CUDA tensor (axis0 = x).  level: float, or None ->
-        0.5*(min+max) (from `level_keys` if the decoder tracked them, else computed here).
+        0.5*(min+max) (from `level_keys` if the decoder tracked them, else computed here);
+        `level_ptr`: address of a device float holding the level (multi-GPU exchange).
         Returns (vertices (V,3) float32, faces (F,3) int32) views of internal buffers
         (valid until the next call) — or, with sync=False, the un-trimmed buffers and the
-        device counter tensor."""
+        device counter tensor (int64[4]: V, F, numbered vertices, -).
+        Slab mode (`x_emit` rows owned, the rest of the volume are halo rows, `x_origin` = lattice
+        row of volume[0]): include/vtaco_b200.h, vtaco_marching_cubes."""
         _abi.require_cuda(volume, 'volume')
         if volume.dim() != 3 or not volume.is_contiguous():
             raise ValueError('volume must be a contiguous (nx,ny,nz) tensor')
@@ -65,7 +69,9 @@ class MarchingCubes(object):
         a.grid, a.nx, a.ny, a.nz = volume.data_ptr(), nx, ny, nz
         st = _abi.stream_ptr(self.device)
         with torch.cuda.device(self.device):
-            if level is None:
+            if level_ptr is not None:
+                a.level_ptr = int(level_ptr)
+            elif level is None:
                 if level_keys is None:
                     _abi.check(L.vtaco_grid_minmax(_abi.ptr(volume), n, _abi.ptr(self._keys), st), 'grid_minmax')
                     level_keys = self._keys
@@ -79,10 +85,12 @@ class MarchingCubes(object):
             a.vertices, a.vertex_capacity = self._verts.data_ptr(), self._verts.size(0)
             a.faces, a.face_capacity = self._faces.data_ptr(), self._faces.size(0)
             a.phase = 3
+            if x_emit is not None:
+                a.x_emit, a.x_origin = int(x_emit), int(x_origin)
             _abi.check(L.vtaco_marching_cubes(C.byref(a), st), 'marching_cubes')
             if not sync:
                 return self._verts, self._faces, self._counts
-            V, F = [int(v) for v in self._counts.cpu()]
+            V, F = [int(v) for v in self._counts[:2].cpu()]
             if V > self._verts.size(0) or F > self._faces.size(0):
                 self._ensure(nbytes, int(V * 1.25) + 16, int(F * 1.25) + 16)
                 a.vertices, a.vertex_capacity = self._verts.data_ptr(), self._verts.size(0)
