@@ -449,6 +449,8 @@ def run_ours(args, rank, local_rank, world):
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
            torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
+    if world > 1 and graph is not None:
+        graph.replay()          # untimed: the step's own device-side waits align the ranks after the host barrier
     wall0 = time.perf_counter()
     with ClockSampler(local_rank) as clocks:
         for s in range(args.steps):
@@ -471,8 +473,12 @@ def run_ours(args, rank, local_rank, world):
     if graph is not None:   # stages are inside one graph launch: split by the separately timed decoder kernel below
         dec_ms = None
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    per_rank_steps = None
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX, group=group)
+        allsteps = [torch.zeros(args.steps, dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(allsteps, torch.tensor(step_ms, dtype=torch.float64, device=dev), group=group)
+        per_rank_steps = [[round(float(x), 4) for x in t.cpu()] for t in allsteps]
     total_ms = float(total_ms.item())
     value = nx ** 3 * args.steps / (total_ms * 1e-3)
 
@@ -643,6 +649,7 @@ def run_ours(args, rank, local_rank, world):
             'clocks': clocks.summary(), 'wall_s_timed_region': wall,
         }
         if world > 1:
+            line['step_ms_per_rank'] = per_rank_steps
             line['identity_ok'] = bool(identity and identity['ok'])
             line['identity'] = identity
             line['exchange'] = args.exchange if exchange_note is None else exchange_note
@@ -671,9 +678,18 @@ def run_ours(args, rank, local_rank, world):
                           'reference executes) on this GPU under torch %s eager, with the chunking and host<->device '
                           'copies of Generator3D.eval_points (generation.py:352-383) - compare with e2e, not value'
                           % (refg.n, torch.__version__)}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Tear down in a fixed order: graphs that captured NCCL / symmetric-memory work first, then a last
+        # barrier, then leave without the process-group destructor (ncclCommDestroy with captured graphs alive
+        # can block; the line above is already flushed).
+        del e2e_run, graph
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=group)
+        torch.cuda.synchronize(dev)
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

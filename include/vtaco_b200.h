@@ -172,6 +172,11 @@ typedef struct vtaco_decoder_args {
    * when non-NULL (and n_peers > 0) each logit is written ONCE with multimem.st and the NVSwitch
    * replicates it to every rank, instead of n_peers unicast stores. */
   float* logits_multicast;
+  /* compact tactile conditioning, third form (use_img): one byte per query (flat: [B*N]; dense:
+   * [nx^3] in lattice order) — 0 = no tactile feature, k = tip_feat[k-1] (n_tips rows, tips[] /
+   * tip_touch[] / tip_radius unused).  Built by vtaco_fingertip_ids / vtaco_tactile_point_map.
+   * tcgen05 variants only. */
+  const uint8_t* tip_map;
 } vtaco_decoder_args;
 
 int vtaco_decoder_forward(const vtaco_decoder_args* args, void* stream);
@@ -220,6 +225,23 @@ typedef struct vtaco_decoder_bwd_args {
 } vtaco_decoder_bwd_args;
 size_t vtaco_decoder_backward_workspace_bytes(int64_t total_queries, int32_t n_blocks);
 int vtaco_decoder_backward(const vtaco_decoder_bwd_args* args, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * (3b) Tactile conditioning maps — replace the reference's host-side construction
+ * of c_img_all (scipy.cdist over all query points + a dense (N, c_dim) tensor).
+ * vtaco_fingertip_ids: generation.py:190-200 / training.py:560-575.  ids[i] = f+1 where f is the
+ *   NEAREST fingertip of query p[i] (float64 distances, first minimum), if that distance < radius
+ *   and touch_host[f] != 0; else 0.  p: [n][3] device; tips_host: [n_tips][3] host doubles.
+ * vtaco_tactile_point_map: generation.py:222-255 (encode_t2d).  map[i] = value for every query
+ *   closer than `radius` (float64) to any of the n_pts points (device doubles [n_pts][3]); other
+ *   entries are left untouched: zero the map, then call once per touched sensor t in increasing
+ *   order with value = t+1 (later sensors overwrite, like the reference's loop).  Queries: flat
+ *   p [n][3], or (p == NULL) the dense lattice axis[nx]^3 in lattice order.
+ * ------------------------------------------------------------------------- */
+int vtaco_fingertip_ids(const float* p, int64_t n, const double* tips_host, const int32_t* touch_host,
+                        int32_t n_tips, double radius, uint8_t* ids, void* stream);
+int vtaco_tactile_point_map(const float* p, int64_t n, const float* axis, int32_t nx, const double* pts,
+                            int32_t n_pts, double radius, int32_t value, uint8_t* map, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * (4c) Weight packing, one launch each.  nn.Linear stores weight[out][in]; the kernels read
@@ -470,6 +492,20 @@ int vtaco_fp32_peak(int variant, int iters, double* flops_per_s_host, void* stre
  * value is chamfer1 + chamfer2. */
 int vtaco_chamfer(const float* p1, const float* p2, int32_t B, int64_t T1, int64_t T2, float* dist12, int32_t* idx12,
                   float* dist21, int32_t* idx21, float* chamfer1, float* chamfer2, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * (10) Earth-Mover distance — the other metric of generate_obj_mesh_wnf
+ * (src/common.py:45-51, called at generation.py:282): cost of the minimum-cost matching
+ * between p1 [n1][3] and p2 [n2][3] under the float64 Euclidean distance, divided by n1
+ * (scipy cdist + linear_sum_assignment in the reference).  Float64 auction algorithm with
+ * epsilon-scaling on the device; the result is within eps_final (<= 0: 1e-9) of the optimum.
+ * n1 != n2: min(n1,n2) pairs are matched, like linear_sum_assignment.  assignment (optional,
+ * device int32[n1]): matched row of p2 or -1.  Synchronises the stream (the auction's
+ * termination test and the result are host reads). max(n1,n2) <= 8192.
+ * ------------------------------------------------------------------------- */
+int64_t vtaco_emd_workspace_bytes(int64_t n1, int64_t n2);
+int vtaco_emd(const float* p1, int64_t n1, const float* p2, int64_t n2, void* workspace, int64_t workspace_bytes,
+              double eps_final, double* emd_host, int32_t* assignment, int64_t* iterations_host, void* stream);
 
 #ifdef __cplusplus
 }

@@ -320,3 +320,34 @@ def chamfer_distance_kdtree(points1, points2, give_id=False):
     if give_id:
         return c1, c2, i12, i21
     return c1 + c2
+
+
+def tactile_points_c_img(p, points_per_sensor, sensor_feat, touch, radius=0.015):
+    """generation.py:222-255 (encode_t2d branch), the part after the depth back-projection:
+    for t in 0..4, if the sensor touched, every query within `radius` (float64 cdist) of ANY of
+    sensor t's world points takes c_img[t]; later sensors overwrite.  (The reference walks the
+    lattice in 8 hard-coded chunks of 64**3 — only valid for nx = 128; the chunking does not
+    change the result and is not restated.)"""
+    pn = p.detach().cpu().numpy().astype(np.float64)
+    out = torch.zeros(p.shape[0], sensor_feat.shape[1], dtype=torch.float32)
+    for t, pts in enumerate(points_per_sensor):
+        if pts is None or not touch[t]:
+            continue
+        q = np.asarray(pts, dtype=np.float64).reshape(-1, 3)
+        if q.shape[0] == 0:
+            continue
+        hit = np.zeros(pn.shape[0], dtype=bool)
+        for s in range(0, pn.shape[0], 65536):
+            d = np.sqrt(((q[:, None, :] - pn[None, s:s + 65536, :]) ** 2).sum(-1))
+            hit[s:s + 65536] = (d < radius).any(0)
+        out[np.where(hit)[0]] = sensor_feat[t]
+    return out
+
+
+def earth_mover_distance(points1, points2):
+    """src/common.py:45-51 (scipy is the reference's own dependency: requirements.txt)."""
+    from scipy.optimize import linear_sum_assignment
+    from scipy.spatial import distance
+    d = distance.cdist(points1, points2)
+    assignment = linear_sum_assignment(d)
+    return d[assignment].sum() / len(d)

@@ -267,6 +267,8 @@ def main():
     make_grads(common, encoder_dict, models, generation)
     make_encoder_grads(common, encoder_dict, models, generation)
     make_chamfer(common)
+    make_emd(common)
+    make_helpers(common)
     for f in sorted(os.listdir(HERE)):
         if f.endswith('.npz'):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, 'KiB')
@@ -367,8 +369,49 @@ def make_chamfer(common):
     np.savez_compressed(os.path.join(HERE, 'chamfer.npz'), **g)
 
 
+def make_emd(common):
+    """G9: src/common.py EarthMoverDistance (scipy cdist + linear_sum_assignment), generation.py:282."""
+    g = {}
+    for tag, n1, n2 in (('t2048', 2048, 2048), ('t300', 300, 300), ('rect', 256, 200), ('rect2', 120, 300)):
+        a = rs_uniform(181, -0.5, 0.5, n1, 3)
+        b = rs_uniform(182, -0.5, 0.5, n2, 3)
+        k = min(n1, n2) // 2
+        b[:k] = a[:k][::-1] + rs_randn(183, k, 3, scale=0.01)      # half of the points have a near partner
+        g[tag + '.p1'], g[tag + '.p2'] = a, b
+        g[tag + '.emd'] = np.float64(common.EarthMoverDistance(a, b))
+    np.savez_compressed(os.path.join(HERE, 'emd.npz'), **g)
+
+
+def make_helpers(common):
+    """G10: src/common.py R_from_PYR / norm_pc_1 and the fingertip transform of generation.py:177-188
+    (the inline code there, evaluated with the reference's own helper functions)."""
+    rs = np.random.RandomState(191)
+    g = {}
+    angles = rs.uniform(-np.pi, np.pi, size=(4, 3))
+    g['angles'] = angles
+    g['R'] = np.stack([common.R_from_PYR(a) for a in angles])
+    pc_obj = rs.randn(500, 3) * 0.1 + np.array([0.3, -0.2, 0.5])
+    pc = rs.randn(7, 3) * 0.2
+    g['pc_obj'], g['pc'] = pc_obj, pc
+    g['norm'] = common.norm_pc_1(pc, pc_obj)
+    joints = rs.randn(21, 3).astype(np.float32) * 0.05
+    wrist_rot, wrist_pos = rs.uniform(-1, 1, 3), rs.randn(3) * 0.1
+    tips_pos = joints[[4, 8, 12, 16, 20]]
+    tips_pos = tips_pos - np.array([0.11, 0.005, 0], dtype=np.float32)
+    tips_pos = np.linalg.inv(common.R_from_PYR(np.array([-np.pi / 2, np.pi / 2, 0]))) @ tips_pos.T
+    tips_pos = np.linalg.inv(common.R_from_PYR(np.array(wrist_rot))) @ tips_pos
+    tips_pos_b = tips_pos.T + wrist_pos
+    g['joints'], g['wrist_rot'], g['wrist_pos'] = joints, wrist_rot, wrist_pos
+    g['tips'] = common.norm_pc_1(tips_pos_b, pc_obj)
+    np.savez_compressed(os.path.join(HERE, 'helpers.npz'), **g)
+
+
 if __name__ == '__main__':
-    if sys.argv[1:] == ['chamfer']:
+    if sys.argv[1:] == ['emd']:
+        make_emd(import_reference()[0])
+    elif sys.argv[1:] == ['helpers']:
+        make_helpers(import_reference()[0])
+    elif sys.argv[1:] == ['chamfer']:
         make_chamfer(import_reference()[0])
     elif sys.argv[1:] == ['grads']:
         torch.set_num_threads(4)

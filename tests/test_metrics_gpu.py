@@ -59,3 +59,20 @@ def test_mesh_to_chamfer_end_to_end(tmp_path):
     gen = Generator3D(torch.nn.Identity(), device='cuda', resolution0=16, padding=0.1)
     cd2 = gen.mesh_chamfer(v, gt, generator=torch.Generator(device='cuda').manual_seed(0))
     assert cd2.shape == (1,) and cd2.item() < 2 * (0.03 ** 2)
+
+
+@pytest.mark.parametrize('tag', ['t300', 'rect', 'rect2', 't2048'])
+def test_emd_matches_reference_golden(tag):
+    """EarthMoverDistance (auction algorithm on the GPU) == the reference's scipy Hungarian value
+    (fixture made by the reference's own function, tests/golden/make_golden.py) to 1e-6 relative."""
+    from vtaco_b200.common import EarthMoverDistance
+    g = load('emd.npz')
+    p1, p2 = g[tag + '.p1'], g[tag + '.p2']
+    got, assign = EarthMoverDistance(torch.from_numpy(p1).cuda(), p2, return_assignment=True)
+    want = float(g[tag + '.emd'])
+    assert abs(got - want) <= 1e-6 * want, (got, want, EarthMoverDistance.last_iterations)
+    a = assign.cpu().numpy()
+    used = a[a >= 0]
+    assert len(used) == min(len(p1), len(p2)) and len(np.unique(used)) == len(used)      # a matching
+    d = np.sqrt(((p1.astype(np.float64)[a >= 0] - p2.astype(np.float64)[used]) ** 2).sum(-1))
+    assert abs(d.sum() / len(p1) - got) <= 1e-12 + 1e-9 * got                            # the value is that matching's cost

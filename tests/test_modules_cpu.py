@@ -192,3 +192,19 @@ def test_c_example_compiles_and_links(tmp_path):
                         os.path.join(root, 'examples', 'dense_extract.c'), '-L', os.path.dirname(_abi.LIB_PATH),
                         '-lvtaco_b200', '-L', cuda_lib, '-lcudart', '-lm', '-o', exe], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_generation_helpers_match_reference_golden():
+    """R_from_PYR / norm_pc_1 / the fingertip transform of generation.py:177-188 against values computed
+    by the reference's own functions (tests/golden/make_golden.py helpers)."""
+    import numpy as np
+    from util import load
+    from vtaco_b200.conv_onet.generation import R_from_PYR, norm_pc_1, fingertips_from_mano, Mesh
+    g = load('helpers.npz')
+    for a, R in zip(g['angles'], g['R']):
+        assert np.allclose(R_from_PYR(a), R, rtol=0, atol=1e-15)
+    assert np.allclose(norm_pc_1(g['pc'], g['pc_obj']), g['norm'], rtol=0, atol=1e-14)
+    tips = fingertips_from_mano(g['joints'], g['wrist_rot'], g['wrist_pos'], g['pc_obj'])
+    assert np.allclose(tips, g['tips'], rtol=0, atol=1e-13)
+    m = Mesh(np.zeros((3, 3), np.float32), np.array([[0, 1, 2]], np.int32))
+    assert m.vertices.shape == (3, 3) and m.faces.shape == (1, 3)

@@ -178,3 +178,9 @@ def test_chamfer_matches_reference(tag):
     c1, c2, i12, i21 = oc.chamfer_distance_kdtree(a, b, give_id=True)
     assert np.array_equal(i12.numpy(), g[tag + '.kd_i12']) and np.array_equal(i21.numpy(), g[tag + '.kd_i21'])
     assert close(c1.numpy(), g[tag + '.kd_c1'], 1e-6) < 1e-6 and close(c2.numpy(), g[tag + '.kd_c2'], 1e-6) < 1e-6
+
+
+@pytest.mark.parametrize('tag', ['t300', 'rect'])
+def test_emd_oracle_matches_reference(tag):
+    g = load('emd.npz')
+    assert abs(oc.earth_mover_distance(g[tag + '.p1'], g[tag + '.p2']) - float(g[tag + '.emd'])) < 1e-12

@@ -41,6 +41,7 @@ class DecoderArgs(C.Structure):
         ('logits', C.c_void_p), ('contact', C.c_void_p), ('minmax_key', C.c_void_p),
         ('variant', C.c_int32), ('weights_tc', C.c_void_p),
         ('logits_peers', C.c_void_p * 8), ('n_peers', C.c_int32), ('logits_multicast', C.c_void_p),
+        ('tip_map', C.c_void_p),
     ]
 
 
@@ -168,6 +169,10 @@ _OPTIONAL = {
     'vtaco_mc_scratch_bytes': [C.c_int32, C.c_int32, C.c_int32],
     'vtaco_grid_minmax': [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p],
     'vtaco_publish_keys': [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_void_p],
+    'vtaco_fingertip_ids': [C.c_void_p, C.c_int64, C.POINTER(C.c_double), C.POINTER(C.c_int32), C.c_int32, C.c_double,
+                            C.c_void_p, C.c_void_p],
+    'vtaco_tactile_point_map': [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_double,
+                                C.c_int32, C.c_void_p, C.c_void_p],
     'vtaco_exchange_level': [C.POINTER(Exchange), C.c_void_p, C.c_void_p],
     'vtaco_exchange_mesh': [C.POINTER(Exchange), C.POINTER(MeshPiece), C.c_void_p],
     'vtaco_group_norm_cl': [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64,

@@ -138,3 +138,38 @@ def chamfer_distance(points1, points2, use_kdtree=True, give_id=False):
     if use_kdtree:
         return chamfer_distance_kdtree(points1, points2, give_id=give_id)
     return chamfer_distance_naive(points1, points2)
+
+
+# --------------------------------------------------------------------------- #
+# Earth-Mover distance (reference src/common.py:45-51) — the second metric of
+# generate_obj_mesh_wnf (generation.py:282); SURVEY §8f-4.
+# --------------------------------------------------------------------------- #
+def EarthMoverDistance(points1, points2, eps=1e-9, return_assignment=False):
+    """reference: d = cdist(points1, points2); d[linear_sum_assignment(d)].sum() / len(d).
+    points (T,3) array-likes or tensors (moved to the GPU); the minimum-cost matching is found by
+    a float64 auction algorithm on the device (csrc/emd.cu), whose cost is within T*eps of the
+    Hungarian optimum scipy returns — the value agrees to ~eps.  Returns a Python float
+    (and, optionally, the int32 assignment of points1's rows)."""
+    import ctypes as C
+    dev = points1.device if torch.is_tensor(points1) and points1.is_cuda else (
+        points2.device if torch.is_tensor(points2) and points2.is_cuda else torch.device('cuda', torch.cuda.current_device()))
+    p1 = torch.as_tensor(points1, dtype=torch.float32).to(dev).reshape(-1, 3).contiguous()
+    p2 = torch.as_tensor(points2, dtype=torch.float32).to(dev).reshape(-1, 3).contiguous()
+    L = _abi.lib()
+    L.vtaco_emd_workspace_bytes.restype = C.c_int64
+    L.vtaco_emd_workspace_bytes.argtypes = [C.c_int64, C.c_int64]
+    L.vtaco_emd.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_double,
+                            C.POINTER(C.c_double), C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]
+    n1, n2 = p1.shape[0], p2.shape[0]
+    nbytes = L.vtaco_emd_workspace_bytes(n1, n2)
+    if nbytes < 0:
+        _abi.check(int(nbytes), 'emd_workspace_bytes')
+    ws = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
+    assign = torch.empty(n1, dtype=torch.int32, device=dev) if return_assignment else None
+    out, iters = C.c_double(0.0), C.c_int64(0)
+    with torch.cuda.device(dev):
+        st = L.vtaco_emd(_abi.ptr(p1), n1, _abi.ptr(p2), n2, _abi.ptr(ws), ws.numel(), float(eps), C.byref(out),
+                         _abi.ptr(assign), C.byref(iters), _abi.stream_ptr(dev))
+    _abi.check(st, 'emd')
+    EarthMoverDistance.last_iterations = iters.value
+    return (out.value, assign) if return_assignment else out.value

@@ -18,6 +18,55 @@ from ..mcubes import MarchingCubes, new_minmax_key
 from .. import dist as vdist
 
 
+class Mesh(object):
+    """Minimal stand-in for trimesh.Trimesh(vertices, faces) — what generate_obj_mesh_wnf returns when
+    trimesh is not installed: `.vertices` (V,3) float32, `.faces` (F,3) int32, `.export(path)` (.off)."""
+
+    def __init__(self, vertices, faces):
+        self.vertices = np.asarray(vertices)
+        self.faces = np.asarray(faces)
+
+    def export(self, path):
+        from ..io import export_off
+        export_off(path, self.vertices, self.faces)
+        return path
+
+
+def _make_mesh(vertices, faces):
+    try:
+        import trimesh
+        return trimesh.Trimesh(vertices, faces, process=False)
+    except ImportError:
+        return Mesh(vertices, faces)
+
+
+def R_from_PYR(wrist_rot):
+    """reference src/common.py:591-604 (roll about z, pitch about x, yaw about y; R_pitch @ R_yaw @ R_roll)."""
+    roll, pitch, yaw = wrist_rot
+    cr, sr, cp, sp, cy, sy = np.cos(roll), np.sin(roll), np.cos(pitch), np.sin(pitch), np.cos(yaw), np.sin(yaw)
+    R_roll = np.array([[cr, -sr, 0], [sr, cr, 0], [0, 0, 1]])
+    R_pitch = np.array([[1, 0, 0], [0, cp, sp], [0, -sp, cp]])
+    R_yaw = np.array([[cy, 0, -sy], [0, 1, 0], [sy, 0, cy]])
+    return R_pitch @ R_yaw @ R_roll
+
+
+def norm_pc_1(pc, pc_obj):
+    """reference src/common.py:606-612: centre on pc_obj's centroid, scale by twice its radius."""
+    centroid = np.mean(pc_obj, axis=0)
+    m = np.max(np.sqrt(np.sum((pc_obj - centroid) ** 2, axis=1)))
+    return (pc - centroid) / (2 * m)
+
+
+def fingertips_from_mano(mano_joints, wrist_rot_euler, wrist_pos, pc_ply):
+    """generation.py:177-188: MANO joints (21,3) -> the five fingertip positions in the normalised
+    object frame the query points live in."""
+    tips = np.asarray(mano_joints)[[4, 8, 12, 16, 20]]
+    tips = tips - np.array([0.11, 0.005, 0], dtype=np.float32)
+    tips = np.linalg.inv(R_from_PYR(np.array([-np.pi / 2, np.pi / 2, 0]))) @ tips.T
+    tips = np.linalg.inv(R_from_PYR(np.array(wrist_rot_euler))) @ tips
+    return norm_pc_1(tips.T + wrist_pos, pc_ply)
+
+
 class Generator3D(object):
     '''  Generator class for Occupancy Networks (reference generation.py:21-72).
 
@@ -93,13 +142,82 @@ class Generator3D(object):
                 occ = self.model.decode(pi, c, **kwargs).logits
         return occ.squeeze(0).detach().cpu()
 
+    def generate_obj_mesh_wnf(self, data):
+        ''' Object mesh + metrics for one scene — reference generation.py:115-284, same signature and
+        return triple `(mesh, emd, cd)`; called by train.py:246.
+
+        Everything from the feature grid on runs on the device: fused lattice decode with the compact
+        tactile conditioning, marching cubes, Chamfer distance and Earth-Mover distance of 2048
+        shuffled mesh vertices against `points.points_obj` (generation.py:275-282).
+
+        Inputs read from `data` (the reference's keys): 'inputs' (1,T,3), 'points.points_obj' (1,2048,3),
+        and with `with_img`: 'inputs.touch_success' (1,5) plus
+          * the tactile features: 'tactile.features' (1,5,c_dim), else `model.encode_img_inputs(
+            data['inputs.img'])` when an image encoder is attached to the model;
+          * fingertip branch (encode_t2d False): 'tactile.tips' (5,3) fingertip positions, else computed
+            like generation.py:172-188 from the attached hand encoder's 'mano_joints' and
+            'points.wrist', 'points.mano', 'inputs.pc_ply';
+          * encode_t2d branch: 'tactile.points' — list of 5 (n,3) arrays, the back-projected tactile
+            point clouds in the normalised object frame (generation.py:222-246 computes them with the
+            RFUniverse camera model, which is outside the hot path).
+        The hand / tactile-image networks themselves are out of scope: attach
+        your own modules as `encoder_hand` / `encoder_img`, or pass the 'tactile.*' entries.
+
+        The vertex rescale uses the reference's hard-coded 1.1/nx (generation.py:272), which equals
+        (1+padding)/nx for the shipped padding 0.1.  Triangulation of ambiguous cells follows
+        oracle/mc_tables.py, not skimage's Lewiner tables (parity unpinned, DESIGN.md §2).'''
+        from ..common import chamfer_distance, EarthMoverDistance
+        from . import tactile
+        self.model.eval()
+        dev = self.device
+        nx = self.resolution0 * 4
+        inputs = data.get('inputs', torch.empty(1, 0)).to(dev)
+        points_obj = data.get('points.points_obj')
+        tips = tip_map = None
+        with torch.no_grad():
+            c = self.model.encode_inputs(inputs)
+            if self.with_img:
+                touch = torch.as_tensor(data.get('inputs.touch_success')).reshape(-1).cpu().numpy().astype(bool)
+                c_img = data.get('tactile.features')
+                if c_img is None:
+                    c_img = self.model.encode_img_inputs(data.get('inputs.img').to(dev))
+                c_img = torch.as_tensor(c_img, dtype=torch.float32).to(dev).reshape(1, touch.shape[0], -1)
+                if not self.encode_t2d:
+                    tp = data.get('tactile.tips')
+                    if tp is None:
+                        c_hand = self.model.encode_hand_inputs(inputs)
+                        tp = fingertips_from_mano(
+                            c_hand['mano_joints'].detach().cpu().numpy()[0],
+                            data.get('points.wrist').squeeze().detach().cpu().numpy(),
+                            data.get('points.mano').squeeze().detach().cpu().numpy()[:3],
+                            data.get('inputs.pc_ply').detach().cpu().numpy().squeeze())
+                    tips = (np.asarray(torch.as_tensor(tp).cpu(), dtype=np.float64).reshape(-1, 3), c_img[0], touch, 0.05)
+                else:
+                    pts = data.get('tactile.points')
+                    if pts is None:
+                        raise KeyError("generate_obj_mesh_wnf(encode_t2d=True) needs data['tactile.points'] (the "
+                                       'back-projected tactile point clouds, generation.py:222-246)')
+                    tip_map = (tactile.tactile_point_map(pts, touch, 0.015, nx=nx, padding=self.padding, device=dev),
+                               c_img[0])
+            grid, keys = self.eval_lattice(c, tips=tips, tip_map=tip_map, group=False)
+            v, f = self.mc(grid, level_keys=keys, voffset=np.float32(nx / 2), vscale=np.float32(1.1 / nx))
+            vertices, faces = self._to_host(v, f)
+        vertices, faces = vertices.copy(), faces.copy()
+        mesh = _make_mesh(vertices.copy(), faces)
+        np.random.shuffle(vertices)                      # numpy's global RNG, like the reference
+        vertices = np.ascontiguousarray(vertices[:2048], dtype=np.float32)
+        vt = torch.from_numpy(vertices)[None].to(dev)
+        cd = chamfer_distance(torch.as_tensor(points_obj).to(dev), vt, use_kdtree=False)
+        emd = EarthMoverDistance(torch.as_tensor(points_obj)[0].to(dev), vt[0])
+        return mesh, emd, cd.item()
+
     # ------------------------------------------------------------------ device-resident fast path
     def lattice_points(self):
         """(1+padding) * make_3d_grid(nx^3) of reference generation.py:155-157 (host tensor)."""
         nx = self.resolution0 * 4
         return (1 + self.padding) * make_3d_grid((-0.5,) * 3, (0.5,) * 3, (nx,) * 3)
 
-    def eval_lattice(self, c, tips=None, c_img_all=None, group=None, exchange=None):
+    def eval_lattice(self, c, tips=None, c_img_all=None, group=None, exchange=None, tip_map=None):
         """Logits on the dense lattice, device tensor (nx,nx,nx), + int32 min/max keys.
         With a process group the x-slabs are decoded by different ranks; `exchange`:
           'fused' (default): the decoder kernel stores its slab into every rank's grid over
@@ -157,7 +275,7 @@ class Generator3D(object):
         with torch.no_grad():
             if x1 > x0:
                 dec.forward_dense(c, nx, x0=x0, x1=x1, use_img=self.with_img, c_img=c_img_all, tips=tips,
-                                  out=self._grid, minmax_key=keys, axis=self._axis)
+                                  out=self._grid, minmax_key=keys, axis=self._axis, tip_map=tip_map)
             if world > 1:
                 vdist.all_gather_slabs(self._grid, nx, group)
                 vdist.all_reduce_minmax(keys, group)

@@ -279,7 +279,9 @@ class LocalDecoder(nn.Module):
             keep.append(wtc)
         return a, keep
 
-    def _decode(self, p, c_plane, use_img=False, c_img=None, contact=False):
+    def _decode(self, p, c_plane, use_img=False, c_img=None, contact=False, tip_ids=None):
+        """tip_ids = (ids (B,N) uint8, features (F,c_dim) or (1,F,c_dim)): compact per-query tactile
+        conditioning instead of a dense c_img tensor (inference only; vtaco_b200.conv_onet.tactile)."""
         _abi.require_cuda(p, 'p')
         if p.dim() != 3 or p.size(2) != 3:
             raise ValueError('p must have shape (B, N, 3)')
@@ -289,13 +291,30 @@ class LocalDecoder(nn.Module):
             # (training.py:310,362,614,729,868) but never reads p.grad: no gradient w.r.t. p is
             # produced (backward returns None for it), everything else is differentiated.
             self._pack_cache = None     # training: re-pack every step (one launch), immune to `.data` updates
+            if tip_ids is not None:
+                raise NotImplementedError('vtaco_b200: tip_ids is an inference-only form; pass '
+                                          'tactile.c_img_from_ids(ids, c_img) as c_img when training')
             names, params = zip(*self.named_parameters())
             return _DecodeFn.apply(self, bool(use_img), bool(contact), tuple(feats.keys()), names, p, c_img,
                                    *feats.values(), *params)
-        out, out_c, _ = self._decode_impl(p, c_plane, use_img, c_img, contact)
+        out, out_c, _ = self._decode_impl(p, c_plane, use_img, c_img, contact, tip_ids)
         return (out, out_c) if contact else out
 
-    def _decode_impl(self, p, c_plane, use_img=False, c_img=None, contact=False):
+    def _tip_map_args(self, a, keep, ids, feat, n_queries):
+        ids = ids.reshape(-1)
+        if ids.dtype != torch.uint8 or not ids.is_cuda or ids.numel() != n_queries:
+            raise ValueError('tip ids must be a CUDA uint8 tensor with one entry per query')
+        feat = feat.reshape(-1, feat.shape[-1]).contiguous()
+        _abi.require_cuda(feat, 'tip features')
+        if feat.shape[0] > _abi.MAX_TIPS or feat.shape[1] != 32:
+            raise ValueError('tip features must be (F <= %d, 32)' % _abi.MAX_TIPS)
+        if a.variant not in (2, 4, 5, 6):
+            raise NotImplementedError('the per-query tactile id map needs a tcgen05 kernel variant (2, 4, 5, 6)')
+        ids = ids.contiguous()
+        a.tip_map, a.tip_feat, a.n_tips = ids.data_ptr(), feat.data_ptr(), feat.shape[0]
+        keep += [ids, feat]
+
+    def _decode_impl(self, p, c_plane, use_img=False, c_img=None, contact=False, tip_ids=None):
         """Launch the forward kernel; returns (logits, contact|None, tensors the launch reads)."""
         B, N = p.shape[0], p.shape[1]
         pc = p.contiguous()
@@ -307,7 +326,11 @@ class LocalDecoder(nn.Module):
         a.p = pc.data_ptr()
         a.N = N
         a.use_img = int(use_img)
-        if use_img:
+        if use_img and tip_ids is not None:
+            if B != 1 and tip_ids[1].dim() == 3 and tip_ids[1].shape[0] != 1:
+                raise NotImplementedError('tip_ids: one feature table per call (B = 1, or features shared by the batch)')
+            self._tip_map_args(a, keep, tip_ids[0], tip_ids[1], B * N)
+        elif use_img:
             if c_img is None:
                 raise ValueError('forward_img needs c_img')
             _abi.require_cuda(c_img, 'c_img')
@@ -423,9 +446,10 @@ class LocalDecoder(nn.Module):
         """reference decoder.py:135-161 -> logits (B,N)."""
         return self._decode(p, c_plane)
 
-    def forward_img(self, p, c_plane, c_img, **kwargs):
-        """reference decoder.py:71-103 -> logits (B,N)."""
-        return self._decode(p, c_plane, use_img=True, c_img=c_img)
+    def forward_img(self, p, c_plane, c_img=None, tip_ids=None, **kwargs):
+        """reference decoder.py:71-103 -> logits (B,N).  Extra: `tip_ids=(ids, features)` instead of
+        the dense c_img tensor (see _decode)."""
+        return self._decode(p, c_plane, use_img=True, c_img=c_img, tip_ids=tip_ids)
 
     def forward_contact(self, p, c_plane, **kwargs):
         """reference decoder.py:105-133 -> (logits, contact) each (B,N)."""
@@ -454,7 +478,7 @@ class LocalDecoder(nn.Module):
 
     # ------------------------------------------------------------------ dense lattice (Generator3D fast path)
     def forward_dense(self, c_plane, nx, x0=0, x1=None, use_img=False, c_img=None, tips=None,
-                      out=None, minmax_key=None, axis=None, peers=None, multicast=None):
+                      out=None, minmax_key=None, axis=None, peers=None, multicast=None, tip_map=None):
         """Evaluate the extraction lattice (1+padding)*make_3d_grid(nx^3) (reference
         generation.py:155-157) for rows x in [x0,x1) directly into `out` (nx,nx,nx).
 
@@ -481,7 +505,9 @@ class LocalDecoder(nn.Module):
             if cic.size(0) != nx ** 3:
                 raise ValueError('dense c_img must have nx^3 rows')
             a.c_img = cic.data_ptr()
-        if use_img and tips is not None:
+        if use_img and tip_map is not None:       # (uint8 map (nx^3,), features (F,32)): tactile.tactile_point_map
+            self._tip_map_args(a, keep, tip_map[0], tip_map[1], nx ** 3)
+        elif use_img and tips is not None:
             pos, feat, touch, radius = tips
             F_ = len(pos)
             if F_ > _abi.MAX_TIPS:

@@ -423,7 +423,8 @@ extern "C" int vtaco_decoder_forward(const vtaco_decoder_args* a, void* stream) 
   DecParams P;
   P.p = a->p; P.axis = a->axis; P.grid = a->grid;
   for (int i = 0; i < 3; ++i) P.plane[i] = a->plane[i];
-  P.weights = a->weights; P.c_img = a->c_img; P.tip_feat = a->tip_feat;
+  P.weights = a->weights; P.c_img = a->c_img; P.tip_feat = a->tip_feat; P.tip_map = a->tip_map;
+  if (a->tip_map && !(a->variant >= 2 && a->variant <= 6)) return VTACO_ERR_UNSUPPORTED;   // byte map: tcgen05 kernels only
   P.logits = a->logits; P.contact = a->contact; P.minmax_key = a->minmax_key;
   P.B = a->B; P.Rg = a->reso_grid; P.Rp = a->reso_plane;
   P.n_blocks = a->n_blocks; P.leaky = a->leaky ? 1 : 0; P.use_img = a->use_img ? 1 : 0;

@@ -20,6 +20,7 @@ struct DecParams {
   const float* weights;
   const float* c_img;
   const float* tip_feat;
+  const uint8_t* tip_map;   // optional: per-query tactile id (0 = none), replaces the in-kernel fingertip test
   float* logits;
   float* contact;
   int32_t* minmax_key;
@@ -133,6 +134,15 @@ __device__ __forceinline__ float4 sample_plane(const float4* __restrict__ pl, in
 }
 
 // generation.py:190-200: nearest fingertip in float64 (scipy cdist), within radius, touched.
+__device__ __forceinline__ int tip_assign(const DecParams& P, float x, float y, float z);
+// tactile feature row of a query: from the byte map when given, else the in-kernel fingertip test
+__device__ __forceinline__ int tip_of_query(const DecParams& P, long long qidx, float x, float y, float z) {
+  if (P.tip_map) {
+    const int f = (int)__ldg(P.tip_map + qidx) - 1;
+    return f < P.n_tips ? f : -1;
+  }
+  return tip_assign(P, x, y, z);
+}
 __device__ __forceinline__ int tip_assign(const DecParams& P, float x, float y, float z) {
   bool near = false;
   for (int f = 0; f < P.n_tips; ++f) {
