@@ -39,7 +39,7 @@ def test_fingertip_ids_match_oracle():
     assert hits > 50
 
 
-@pytest.mark.parametrize('nx', [32, 50])
+@pytest.mark.parametrize('nx', [32, 96])
 def test_tactile_point_map_matches_oracle(nx):
     from oracle import convonet as oc
     from vtaco_b200.conv_onet import tactile
@@ -53,10 +53,10 @@ def test_tactile_point_map_matches_oracle(nx):
     ref = oc.tactile_points_c_img(lattice, pts, feat, touch, 0.015)
     m = tactile.tactile_point_map(pts, touch, 0.015, nx=nx, device='cuda')
     got = tactile.c_img_from_ids(m[None], feat[None].cuda())[0].cpu()
-    assert torch.equal(got, ref) and int((m > 0).sum()) > 20
+    assert torch.equal(got, ref) and int((m > 0).sum()) > 5
     # flat queries (arbitrary points) through the brute-force kernel
     q = torch.from_numpy(rs.uniform(-0.45, 0.45, size=(30000, 3)).astype(np.float32))
-    q[:600] = torch.from_numpy((np.concatenate(pts)[:600] + rs.randn(600, 3) * 0.01).astype(np.float32))
+    q[:400] = torch.from_numpy((np.concatenate(pts)[:400] + rs.randn(400, 3) * 0.01).astype(np.float32))
     ref = oc.tactile_points_c_img(q, pts, feat, touch, 0.015)
     m2 = tactile.tactile_point_map(pts, touch, 0.015, p=q.cuda())
     assert torch.equal(tactile.c_img_from_ids(m2[None], feat[None].cuda())[0].cpu(), ref) and int((m2 > 0).sum()) > 20
@@ -88,7 +88,7 @@ def test_decoder_byte_map_equals_dense_c_img(variant):
         assert close(got.reshape(-1).cpu().numpy(), ref.numpy()) < 1e-4
         flat = dec.forward_img(lattice[None].cuda(), c, tip_ids=(m[None], feat.cuda()))
         assert close(flat.reshape(-1).cpu().numpy(), ref.numpy()) < 1e-4
-    assert int((m > 0).sum()) > 50
+    assert int((m > 0).sum()) > 20
 
 
 def test_training_samples_construction():
