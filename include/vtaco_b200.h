@@ -467,6 +467,48 @@ int vtaco_group_norm(const float* x, float* y, const float* gamma, const float* 
 int vtaco_group_norm_cl(const float* x, float* y, const float* gamma, const float* beta, int32_t N, int32_t C,
                         int32_t G, int64_t S, double eps, double* stats_ws, void* stream);
 
+/* ------------------------------------------------------------------------- *
+ * (7b) UNet3D layers on the tensor cores (reference src/encoder/unet3d.py:
+ * SingleConv order 'gcr' = GroupNorm -> Conv3d(3x3x3, padding 1, no bias) -> ReLU; Encoder =
+ * MaxPool3d(2) + DoubleConv; Decoder = nearest-upsample + concat + DoubleConv; final 1x1x1 conv).
+ * Activations are CHANNELS-LAST [N][D][H][W][C] fp32.  vtaco_conv3d_cl is one fused layer:
+ *   y = [relu]( conv_k( GN(x_cat) ) [+ bias] ),  x_cat = cat(x, nearest_upsample(x2)) along C
+ * where GN is applied per element from per-channel statistics: in_stats[n][c] = (sum, sum of
+ * squares) of x_cat's channel c over the sample's D*H*W voxels, accumulated by the PRODUCER of
+ * the tensor (this call's out_stats, vtaco_maxpool2_cl, vtaco_channel_stats_cl; for the upsampled
+ * half multiply the half-resolution sums by 8).  in_stats = NULL: no GroupNorm.  x2 = NULL (C2 =
+ * 0): no concat.  out_stats (optional, ZEROED by the caller) receives the per-channel sums of y.
+ * Arithmetic: implicit GEMM on tcgen05 in single-pass TF32 (operands rounded to nearest TF32,
+ * fp32 accumulation) — the arithmetic of the reference on a GPU (cuDNN, allow_tf32 default).
+ * Packed weights: float index of W[co][ci][dz][dy][dx] =
+ *   ((((co/32) * (Cin/16) + ci/16) * k^3 + (dz*k+dy)*k+dx) * 4 + (ci%16)/4) * 128 + (co%32)*4 + ci%4,
+ * values pre-rounded to TF32.  Requires C1 % 16 == C2 % 16 == 0, Cout % 32 == 0, Cin <= 512, k in {1,3}.
+ * ------------------------------------------------------------------------- */
+typedef struct vtaco_conv3d_args {
+  const float* x;          /* [N][D][H][W][C1] */
+  const float* x2;         /* optional [N][D2][H2][W2][C2], read at nearest-upsampled positions */
+  int32_t N, D, H, W, C1, C2, D2, H2, W2;
+  const float* w_packed;
+  const float* bias;       /* optional [Cout] */
+  int32_t Cout, ksize;
+  const double* in_stats;  /* optional [N][C1+C2][2] */
+  const float* gamma;      /* GroupNorm weight [C1+C2] (NULL: 1) */
+  const float* beta;       /* GroupNorm bias (NULL: 0) */
+  int32_t groups;
+  double eps;
+  int32_t relu;
+  float* y;                /* [N][D][H][W][Cout] */
+  double* out_stats;       /* optional [N][Cout][2], accumulated */
+} vtaco_conv3d_args;
+int vtaco_conv3d_cl(const vtaco_conv3d_args* args, void* stream);
+/* MaxPool3d(kernel 2, stride 2), channels-last; stats (optional, zeroed by the caller, N must be 1):
+ * per-channel (sum, sumsq) of y.  D, H, W even; C % 4 == 0. */
+int vtaco_maxpool2_cl(const float* x, float* y, int32_t N, int32_t D, int32_t H, int32_t W, int32_t C,
+                      double* stats, void* stream);
+/* per-channel (sum, sumsq) of one channels-last sample x [S][C] accumulated into stats [C][2]
+ * (zeroed by the caller); C % 4 == 0 and C/4 divides 256. */
+int vtaco_channel_stats_cl(const float* x, int64_t S, int32_t C, double* stats, void* stream);
+
 /* UNet3D decoder input in one pass (src/encoder/unet3d.py Decoder.forward):
  * out [N][C1+C2][Do][Ho][Wo] = cat(skip [N][C1][Do][Ho][Wo], nearest-upsample(x [N][C2][Di][Hi][Wi]), dim=1),
  * contiguous NCDHW fp32, ATen's nearest source index min(floor(dst * in/out), in-1).

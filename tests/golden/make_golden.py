@@ -269,6 +269,7 @@ def main():
     make_chamfer(common)
     make_emd(common)
     make_helpers(common)
+    make_unet3d_shipped()
     for f in sorted(os.listdir(HERE)):
         if f.endswith('.npz'):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, 'KiB')
@@ -382,6 +383,19 @@ def make_emd(common):
     np.savez_compressed(os.path.join(HERE, 'emd.npz'), **g)
 
 
+def make_unet3d_shipped():
+    """G11: the reference's UNet3D with the SHIPPED kwargs (VTacO_YCB.yaml:26-31: num_levels 4, f_maps 32,
+    32 -> 32 channels) on a 16^3 grid, fp32 on the CPU.  Parameters come from `randomise(module, 91)` (a numpy
+    stream), so the test re-creates them instead of storing 4.1 M weights."""
+    from src.encoder.unet3d import UNet3D
+    u = UNet3D(in_channels=32, out_channels=32, num_levels=4, f_maps=32)
+    randomise(u, 91)
+    x = rs_randn(92, 1, 32, 16, 16, 16) * (np.random.RandomState(93).rand(1, 32, 16, 16, 16) < 0.2)
+    with torch.no_grad():
+        y = u.eval()(torch.from_numpy(x.astype(np.float32))).numpy()
+    np.savez_compressed(os.path.join(HERE, 'unet3d_shipped.npz'), y=y, seed_w=np.int64(91), seed_x=np.array([92, 93]))
+
+
 def make_helpers(common):
     """G10: src/common.py R_from_PYR / norm_pc_1 and the fingertip transform of generation.py:177-188
     (the inline code there, evaluated with the reference's own helper functions)."""
@@ -411,6 +425,9 @@ if __name__ == '__main__':
         make_emd(import_reference()[0])
     elif sys.argv[1:] == ['helpers']:
         make_helpers(import_reference()[0])
+    elif sys.argv[1:] == ['unet3d']:
+        import_reference()
+        make_unet3d_shipped()
     elif sys.argv[1:] == ['chamfer']:
         make_chamfer(import_reference()[0])
     elif sys.argv[1:] == ['grads']:

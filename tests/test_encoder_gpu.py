@@ -143,6 +143,7 @@ def test_encoder_decoder_end_to_end_with_unet3d():
                 b.fc_1.weight.normal_(0, 0.1)
     net = ConvolutionalOccupancyNetwork(dec, enc, device='cuda').eval()
     enc.division = dec.division = 'true'
+    enc.unet3d.fused = False      # fp32 torch.nn / cuDNN modules here; the fused TF32 kernels: tests/test_unet3d_gpu.py
     p = torch.from_numpy(synthetic_cloud(9, 3000)[0])[None]
     q = torch.from_numpy(np.random.RandomState(4).uniform(-0.55, 0.55, size=(1, 5000, 3)).astype(np.float32))
     c_img = torch.from_numpy(rs_randn(10, 1, 5000, 32))

@@ -49,3 +49,18 @@ def synthetic_cloud(seed, n_visual, n_tactile_per_tip=128, n_tips=5):
     tac = (tips[:, None, :] + rs.randn(n_tips, n_tactile_per_tip, 3) * 0.01).reshape(-1, 3)
     pts = np.concatenate([vis, tac], 0) + rs.randn(n_visual + n_tips * n_tactile_per_tip, 3) * 0.005
     return pts.astype(np.float32), tips.astype(np.float32)
+
+
+def randomise(module, seed):
+    """the parameter stream of tests/golden/make_golden.py: every parameter (sorted by name) re-drawn from
+    RandomState(seed); ResnetBlockFC.fc_1.weight ~ N(0, 0.1^2), the rest uniform(+-1/sqrt(fan_in))."""
+    rs = np.random.RandomState(seed)
+    with torch.no_grad():
+        for name, prm in sorted(module.named_parameters()):
+            fan_in = prm.shape[1] if prm.dim() > 1 else prm.shape[0]
+            bound = 1.0 / np.sqrt(max(fan_in, 1))
+            if name.endswith('fc_1.weight'):
+                val = rs.randn(*prm.shape) * 0.1
+            else:
+                val = rs.uniform(-bound, bound, size=tuple(prm.shape))
+            prm.copy_(torch.from_numpy(val.astype(np.float32)))

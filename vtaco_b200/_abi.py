@@ -84,6 +84,15 @@ class MeshPiece(C.Structure):
 EXCHANGE_CTRL_BYTES, EXCHANGE_ERR_OFFSET, EXCHANGE_LEVEL_OFFSET, EXCHANGE_BASE_OFFSET = 1024, 556, 560, 568
 
 
+class Conv3dArgs(C.Structure):
+    _fields_ = [('x', C.c_void_p), ('x2', C.c_void_p),
+                ('N', C.c_int32), ('D', C.c_int32), ('H', C.c_int32), ('W', C.c_int32), ('C1', C.c_int32),
+                ('C2', C.c_int32), ('D2', C.c_int32), ('H2', C.c_int32), ('W2', C.c_int32),
+                ('w_packed', C.c_void_p), ('bias', C.c_void_p), ('Cout', C.c_int32), ('ksize', C.c_int32),
+                ('in_stats', C.c_void_p), ('gamma', C.c_void_p), ('beta', C.c_void_p), ('groups', C.c_int32),
+                ('eps', C.c_double), ('relu', C.c_int32), ('y', C.c_void_p), ('out_stats', C.c_void_p)]
+
+
 class PackDesc(C.Structure):
     _fields_ = [('src', C.c_void_p), ('out_dim', C.c_int32), ('in_dim', C.c_int32), ('src_stride', C.c_int32),
                 ('src_col0', C.c_int32), ('dst_off', C.c_int32)]
@@ -169,6 +178,10 @@ _OPTIONAL = {
     'vtaco_mc_scratch_bytes': [C.c_int32, C.c_int32, C.c_int32],
     'vtaco_grid_minmax': [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p],
     'vtaco_publish_keys': [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_void_p],
+    'vtaco_conv3d_cl': [C.POINTER(Conv3dArgs), C.c_void_p],
+    'vtaco_maxpool2_cl': [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                          C.c_void_p],
+    'vtaco_channel_stats_cl': [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p],
     'vtaco_fingertip_ids': [C.c_void_p, C.c_int64, C.POINTER(C.c_double), C.POINTER(C.c_int32), C.c_int32, C.c_double,
                             C.c_void_p, C.c_void_p],
     'vtaco_tactile_point_map': [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_double,

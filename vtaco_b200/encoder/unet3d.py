@@ -1,6 +1,13 @@
 """3-D U-Net applied to the feature grid — state_dict-compatible with reference
 src/encoder/unet3d.py:361-491 (encoders.N.basic_module.SingleConv{1,2}.{groupnorm,conv,...},
-decoders.N.basic_module..., final_conv).  Library-backed (torch.nn / cuDNN), SURVEY §2 row 8."""
+decoders.N.basic_module..., final_conv).
+
+Inference on CUDA runs on our own kernels (csrc/conv3d.cu): every 'gcr' layer is one
+tcgen05 implicit-GEMM kernel over channels-last activations with GroupNorm-apply, nearest-upsample +
+concat, ReLU and the next layer's GroupNorm statistics fused in; the output is written in the
+decoder's channels-last layout.  Arithmetic: single-pass TF32 with fp32 accumulation, i.e. what the
+reference computes on a GPU (cuDNN, torch.backends.cudnn.allow_tf32 = True by default); set
+`UNet3D.fused = False` for the torch.nn / cuDNN modules (used for training: autograd)."""
 from collections import OrderedDict
 
 import torch
@@ -121,11 +128,26 @@ class _Decoder(nn.Module):
         return self.basic_module(_upsample_concat(skip, x))
 
 
+def _pack_conv_weight(w):
+    """(Cout, Cin, k, k, k) -> the tcgen05 operand layout of vtaco_conv3d_cl (include/vtaco_b200.h),
+    values rounded to nearest TF32."""
+    Cout, Cin, k = w.shape[0], w.shape[1], w.shape[2]
+    taps = k ** 3
+    wt = w.detach().float().reshape(Cout // 32, 32, Cin // 16, 4, 4, taps)       # [nt][n][ch][kc][kk][tap]
+    wt = wt.permute(0, 2, 5, 3, 1, 4).contiguous()                               # [nt][ch][tap][kc][n][kk]
+    wt = ((wt.view(torch.int32) + 0x1000) & ~0x1fff).view(torch.float32)
+    return wt.reshape(-1)
+
+
 class UNet3D(nn.Module):
+    fused = True     # CUDA inference through vtaco_conv3d_cl (class-wide switch; per-instance override allowed)
+
     def __init__(self, in_channels, out_channels, final_sigmoid=True, f_maps=64, layer_order='gcr',
                  num_groups=8, num_levels=4, is_segmentation=True, testing=False, **kwargs):
         super().__init__()
         self.testing = testing
+        self.layer_order = layer_order
+        self._wcache = {}
         if isinstance(f_maps, int):
             f_maps = [f_maps * 2 ** k for k in range(num_levels)]
         self.encoders = nn.ModuleList([
@@ -140,7 +162,101 @@ class UNet3D(nn.Module):
         else:
             self.final_activation = None
 
+    # ------------------------------------------------------------------ fused CUDA inference path
+    def _fusable(self, x):
+        if not (self.fused and x.is_cuda and x.dtype == torch.float32 and x.dim() == 5 and self.layer_order == 'gcr'):
+            return False
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            return False
+        if self.testing and self.final_activation is not None:
+            return False
+        convs = [m for m in self.modules() if isinstance(m, nn.Conv3d)]
+        ok = all(c.in_channels % 16 == 0 and c.out_channels % 32 == 0 and c.in_channels <= 512 and
+                 c.kernel_size[0] in (1, 3) and c.kernel_size[0] == c.kernel_size[1] == c.kernel_size[2] for c in convs)
+        D, H, W = x.shape[2:]
+        n_pool = sum(1 for e in self.encoders if e.pooling is not None)
+        return ok and all(d % (2 ** n_pool) == 0 for d in (D, H, W))
+
+    def _packed(self, conv):
+        key = (id(conv), conv.weight.data_ptr(), conv.weight._version)
+        hit = self._wcache.get(id(conv))
+        if hit is None or hit[0] != key:
+            hit = (key, _pack_conv_weight(conv.weight))
+            self._wcache[id(conv)] = hit
+        return hit[1]
+
+    def _conv(self, x, x2, gn, conv, in_stats, relu, want_stats):
+        """one fused layer on channels-last tensors (N,D,H,W,C); returns (y, y_stats | None)."""
+        from .. import _abi
+        import ctypes as C
+        N, D, H, W, C1 = x.shape
+        a = _abi.Conv3dArgs()
+        a.x, a.N, a.D, a.H, a.W, a.C1 = x.data_ptr(), N, D, H, W, C1
+        if x2 is not None:
+            a.x2, a.C2, a.D2, a.H2, a.W2 = x2.data_ptr(), x2.shape[4], x2.shape[1], x2.shape[2], x2.shape[3]
+        wp = self._packed(conv)
+        a.w_packed = wp.data_ptr()
+        if conv.bias is not None:
+            a.bias = conv.bias.data_ptr()
+        a.Cout, a.ksize = conv.out_channels, conv.kernel_size[0]
+        if gn is not None:
+            a.in_stats = in_stats.data_ptr()
+            a.gamma, a.beta = gn.weight.data_ptr(), gn.bias.data_ptr()
+            a.groups, a.eps = gn.num_groups, float(gn.eps)
+        a.relu = int(relu)
+        y = torch.empty((N, D, H, W, conv.out_channels), dtype=torch.float32, device=x.device)
+        a.y = y.data_ptr()
+        ys = None
+        if want_stats:
+            ys = torch.zeros((N, conv.out_channels, 2), dtype=torch.float64, device=x.device)
+            a.out_stats = ys.data_ptr()
+        with torch.cuda.device(x.device):
+            st = _abi.lib().vtaco_conv3d_cl(C.byref(a), _abi.stream_ptr(x.device))
+        _abi.check(st, 'conv3d_cl')
+        return y, ys
+
+    def _forward_fused(self, x):
+        from .. import _abi
+        L = _abi.lib()
+        dev = x.device
+        cur = x.permute(0, 2, 3, 4, 1)
+        if not cur.is_contiguous():
+            cur = cur.contiguous()
+        N = cur.shape[0]
+        stream = _abi.stream_ptr(dev)
+        with torch.cuda.device(dev):
+            stats = torch.zeros((N, cur.shape[4], 2), dtype=torch.float64, device=dev)
+            for n in range(N):
+                _abi.check(L.vtaco_channel_stats_cl(_abi.ptr(cur[n]), cur[n].numel() // cur.shape[4], cur.shape[4],
+                                                    _abi.ptr(stats[n]), stream), 'channel_stats_cl')
+            feats = []
+            for enc in self.encoders:
+                if enc.pooling is not None:
+                    _, D, H, W, Cc = cur.shape
+                    nxt = torch.empty((N, D // 2, H // 2, W // 2, Cc), dtype=torch.float32, device=dev)
+                    stats = torch.zeros((N, Cc, 2), dtype=torch.float64, device=dev)
+                    for n in range(N):
+                        _abi.check(L.vtaco_maxpool2_cl(_abi.ptr(cur[n]), _abi.ptr(nxt[n]), 1, D, H, W, Cc,
+                                                       _abi.ptr(stats[n]), stream), 'maxpool2_cl')
+                    cur = nxt
+                for sc in (enc.basic_module.SingleConv1, enc.basic_module.SingleConv2):
+                    cur, stats = self._conv(cur, None, sc.groupnorm, sc.conv, stats, True, True)
+                feats.insert(0, (cur, stats))
+            for dec, (skip, skip_stats) in zip(self.decoders, feats[1:]):
+                # cat(skip, nearest-upsample(cur)) is never materialised: its per-channel sums are the skip's
+                # and 8x the half-resolution tensor's (every voxel is replicated 2x2x2 times)
+                if tuple(skip.shape[1:4]) != tuple(2 * d for d in cur.shape[1:4]):
+                    raise NotImplementedError('fused UNet3D needs exact 2x upsampling')
+                cat_stats = torch.cat([skip_stats, 8.0 * stats], 1).contiguous()
+                sc1, sc2 = dec.basic_module.SingleConv1, dec.basic_module.SingleConv2
+                cur, stats = self._conv(skip, cur, sc1.groupnorm, sc1.conv, cat_stats, True, True)
+                cur, stats = self._conv(cur, None, sc2.groupnorm, sc2.conv, stats, True, True)
+            cur, _ = self._conv(cur, None, None, self.final_conv, None, False, False)
+        return cur.permute(0, 4, 1, 2, 3)       # (N,C,D,H,W) in channels_last_3d memory format
+
     def forward(self, x):
+        if self._fusable(x):
+            return self._forward_fused(x)
         feats = []
         for enc in self.encoders:
             x = enc(x)
