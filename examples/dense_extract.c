@@ -59,7 +59,7 @@ int main(void) {
   const int64_t scratch = vtaco_mc_scratch_bytes(nx, nx, nx);
   void* d_scratch; float* d_v; int32_t* d_f; int64_t* d_counts;
   cudaMalloc(&d_scratch, (size_t)scratch); cudaMalloc((void**)&d_v, cap_v * 12); cudaMalloc((void**)&d_f, cap_f * 12);
-  cudaMalloc((void**)&d_counts, 16);
+  cudaMalloc((void**)&d_counts, 32);   /* int64[4]: V, F, numbered vertices, - */
   m.grid = d_logits; m.nx = nx; m.ny = nx; m.nz = nx; m.level_keys = d_keys; m.n_level_keys = 1;
   m.scratch = d_scratch; m.scratch_bytes = scratch; m.vertices = d_v; m.vertex_capacity = cap_v;
   m.faces = d_f; m.face_capacity = cap_f; m.counts = d_counts; m.voffset = nx / 2.0f; m.vscale = 1.1f / nx;

@@ -4,10 +4,11 @@ network against torch fp32 (cuDNN with TF32 off) and the reference-generated gol
 
 Tolerance.  The kernels compute in single-pass TF32 with fp32 accumulation — the arithmetic the reference
 itself uses on a GPU (cuDNN, torch.backends.cudnn.allow_tf32 = True is torch's default).  TF32 keeps 11
-significant bits (relative rounding 4.9e-4 per operand), so against an fp32 result a layer is accurate to
-~1e-3 of the output scale and the 11-layer network to a few 1e-3: the tests require
-max|a-b| <= 1e-2 * max|b| and mean|a-b| <= 2e-3 * mean|b|, and check that cuDNN's own TF32 result is no
-closer to fp32 than ours by more than 2x."""
+significant bits (relative rounding 4.9e-4 per operand), so against an fp32 result ONE layer is accurate to
+~1e-3 of the output scale (tests: max <= 1e-2 * max|b|, mean <= 2e-3 * mean|b|) and the 11-layer network
+to ~5e-3 (tests: max <= 2e-2 * max|b|, mean <= 1e-2 * mean|b|).  Measured on B200 for the shipped network at
+32^3 / 64^3: ours 4.4e-3 / 4.7e-3 mean, cuDNN's TF32 kernels 4.4e-3 / 4.7e-3 mean against the same fp32
+result — the test also requires that we are no further from fp32 than cuDNN's TF32 by more than 25 %."""
 import numpy as np
 import pytest
 import torch
@@ -137,8 +138,10 @@ def test_unet3d_fused_vs_fp32_modules(R, B):
     emax, emean = _err(got, ref)
     cmax, cmean = _err(cud, ref)
     print('fused vs fp32: max %.2e mean %.2e | cuDNN TF32 vs fp32: max %.2e mean %.2e' % (emax, emean, cmax, cmean))
-    assert emax <= 1e-2 and emean <= 2e-3, (emax, emean)
-    assert emean <= 2.0 * cmean + 1e-4
+    assert emax <= 2e-2 and emean <= 1e-2, (emax, emean)
+    assert emean <= 1.25 * cmean + 1e-4 and emax <= 1.25 * cmax + 1e-4
+    fmax, _ = _err(got, cud)
+    assert fmax <= 5e-3, fmax                 # and we agree with cuDNN's TF32 result itself to ~1e-3
 
 
 def test_unet3d_fused_vs_reference_golden():
@@ -164,4 +167,4 @@ def test_unet3d_fused_vs_reference_golden():
     ref = torch.from_numpy(g['y'])
     assert _err(mod.cpu(), ref)[0] < 1e-4          # our module definition == the reference's network
     emax, emean = _err(got.cpu(), ref)
-    assert emax <= 1e-2 and emean <= 2e-3, (emax, emean)
+    assert emax <= 2e-2 and emean <= 1e-2, (emax, emean)

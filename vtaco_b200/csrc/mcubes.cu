@@ -7,19 +7,18 @@
 // are not available offline — parity with skimage is UNPINNED, parity with the oracle is
 // bit-exact on case indices / faces and to rounding on vertices).
 //
-// HBM-bound stream compaction in three launches (no scan kernel):
-//   classify : 1 thread / run of 8 consecutive z points — four rows of 9 samples as float4
-//              loads -> "above" bit rows -> per point 3-bit own-edge mask + triangle count;
-//              the 8 one-byte codes of a run are stored only by blocks that contain a cut edge
-//              or triangle; per-block totals + one 64-bit atomic per block into the totals of
-//              its super-block (256 blocks)
-//   vertices : blocks without a cut edge exit at once; an active block forms its own exclusive
-//              prefix from the super-block totals and the <= 255 block totals before it (two
-//              level, so no dependent scan launch), then intra-block scan -> vertex base id
-//              per point, vertices of the point's own cut edges (inverse-distance weighting in
-//              double, like Lewiner's code); one extra block writes the counters
-//   faces    : same for triangles; vertex ids looked up from the owners' base ids;
-//              output order = lattice order, then table order.
+// HBM-bound stream compaction in TWO kernels that read the grid once:
+//   mc_fused_kernel : 1 thread / run of 8 consecutive z points — four rows of 9 samples as float4
+//              loads -> "above" bit rows -> per point 3-bit own-edge mask + triangle count; block
+//              scan; the block's exclusive prefix comes from a DECOUPLED LOOK-BACK over the
+//              blocks before it (single pass, blocks take their index from a ticket so that
+//              every predecessor has started); with its vertex base known the thread emits the
+//              vertices of its own cut edges at once (inverse-distance weighting in double, like
+//              Lewiner's code), stores the run's codes + vertex base for the face pass and
+//              appends runs that own triangles to a work list (with their triangle base)
+//   mc_faces_kernel : grid-stride over the work list only (~5 % of the runs): vertex ids are looked
+//              up from the owners' codes / bases; output order = lattice order, then table order
+//              (the order of the WORK is arbitrary, every item carries its output position).
 // Slab mode (x_emit < nx; multi-GPU extraction, SURVEY 8e "gather of mesh pieces"): the volume
 // holds the rank's x-rows plus two halo rows; vertex ids are numbered over the whole volume (so a
 // halo-row vertex gets the id it has as the NEXT rank's first vertices), but only vertices owned
@@ -49,11 +48,12 @@ struct McParams {
   const int32_t* level_keys;
   int n_level_keys;
   const float* level_ptr;
-  uint8_t* code;                  // [nruns][8]: bits 0-2 own-edge mask (x,y,z), bits 3-5 triangle count
-  uint32_t* vbase;                // [nruns][8]: id of the first vertex owned by the point (active blocks only)
-  unsigned long long* block_sums; // [nblocks]: vertices | triangles << 32
-  unsigned long long* super_sums; // [nsuper], zeroed before classify
-  int nblocks, nsuper;
+  uint8_t* code;                  // [nruns][8]: bits 0-2 own-edge mask (x,y,z), bits 3-5 triangle count (active runs only)
+  uint32_t* vbase;                // [nruns]: id of the first vertex owned by the run (active runs only)
+  unsigned long long* state;      // [nblocks] look-back words: flag << 62 | triangles << 31 | vertices (zeroed per call)
+  uint2* work;                    // [nruns] (run, triangle base) of the runs that own triangles
+  unsigned* ctrl;                 // [0] block ticket, [1] work-list length (zeroed per call)
+  int nblocks, emit;
   long long* counts;
   float* verts;
   long long vcap;
@@ -104,35 +104,6 @@ __device__ __forceinline__ unsigned block_scan_excl(unsigned v, unsigned& total)
   __syncthreads();
   total = tot;
   return warp_excl[w] + inc - v;
-}
-
-// sum of a 64-bit value over the block (all threads get it)
-__device__ __forceinline__ unsigned long long block_sum64(unsigned long long v) {
-  constexpr int kWarps = kMcThreads / 32;
-  __shared__ unsigned long long part[kWarps];
-  __shared__ unsigned long long tot64;
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = v;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned long long s = 0;
-#pragma unroll
-    for (int w = 0; w < kWarps; ++w) s += part[w];
-    tot64 = s;
-  }
-  __syncthreads();
-  return tot64;
-}
-
-// exclusive prefix (vertices | triangles << 32) of block b: whole super-blocks before it + the
-// blocks of its own super-block before it
-__device__ __forceinline__ unsigned long long block_prefix(const McParams& P, int b) {
-  const int sb = b / kMcSuper, first = sb * kMcSuper;
-  unsigned long long acc = 0;
-  for (int i = threadIdx.x; i < sb; i += kMcThreads) acc += P.super_sums[i];
-  if (first + (int)threadIdx.x < b) acc += P.block_sums[first + threadIdx.x];
-  return block_sum64(acc);
 }
 
 // run -> lattice coordinates of its first point
@@ -206,150 +177,160 @@ __device__ __forceinline__ unsigned run_codes(const McParams& P, int i, int j, i
   return packed;
 }
 
-__global__ void __launch_bounds__(kMcThreads) mc_classify_kernel(const __grid_constant__ McParams P) {
-  const long long run = (long long)blockIdx.x * kMcThreads + threadIdx.x;
+constexpr unsigned long long kMcFlagAgg = 1ull << 62, kMcFlagPrefix = 2ull << 62, kMcValMask = (1ull << 62) - 1;
+
+__device__ __forceinline__ unsigned long long ld_state(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_state(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// point (i,j,k) -> run index / slot within the run
+__device__ __forceinline__ long long run_of(const McParams& P, int i, int j, int k) {
+  return ((long long)i * P.ny + j) * P.nzc + (k >> 3);
+}
+
+__global__ void __launch_bounds__(kMcThreads) mc_fused_kernel(const __grid_constant__ McParams P) {
+  __shared__ int s_bid;
+  __shared__ unsigned long long s_prefix;
+  if (threadIdx.x == 0) s_bid = (int)atomicAdd(P.ctrl, 1u);      // ticket: all blocks before this one have started
+  __syncthreads();
+  const int b = s_bid;
+  const long long run = (long long)b * kMcThreads + threadIdx.x;
+  const float level = mc_level(P);
   unsigned packed = 0;
   unsigned long long codes = 0;
+  int i = 0, j = 0, k0 = 0;
   if (run < P.nruns) {
-    int i, j, k0;
     run_coords(P, run, i, j, k0);
-    packed = run_codes(P, i, j, k0, mc_level(P), codes);
+    packed = run_codes(P, i, j, k0, level, codes);
   }
   unsigned total;
-  block_scan_excl(packed, total);
-  if (total != 0 && run < P.nruns) reinterpret_cast<unsigned long long*>(P.code)[run] = codes;   // inactive blocks are never read
-  if (threadIdx.x == 0) {
-    const unsigned long long s = (unsigned long long)(total & 0xffffu) | ((unsigned long long)(total >> 16) << 32);
-    P.block_sums[blockIdx.x] = s;
-    if (s) atomicAdd(P.super_sums + blockIdx.x / kMcSuper, s);
-  }
-}
-
-// the extra block of the vertices kernel: counts[0] = vertices owned by rows < x_emit,
-// counts[1] = triangles (halo cells were classified as empty), counts[2] = vertices of the whole
-// volume, halo rows included
-__device__ void mc_write_counts(const McParams& P) {
-  unsigned long long acc = 0;
-  for (int i = threadIdx.x; i < P.nsuper; i += kMcThreads) acc += P.super_sums[i];
-  const unsigned long long tot = block_sum64(acc);
-  unsigned long long v_emit = tot & 0xffffffffull;
-  if (P.x_emit < P.nx) {
-    const long long r_emit = (long long)P.x_emit * P.ny * P.nzc;     // first run of the first halo row
-    const int b = (int)(r_emit / kMcThreads), t_emit = (int)(r_emit % kMcThreads);
-    const unsigned long long pre = block_prefix(P, b) & 0xffffffffull;
-    unsigned long long part = 0;
-    if ((P.block_sums[b] & 0xffffffffull) != 0 && (int)threadIdx.x < t_emit) {
-      const unsigned long long codes = reinterpret_cast<const unsigned long long*>(P.code)[(long long)b * kMcThreads + threadIdx.x];
-#pragma unroll
-      for (int t = 0; t < kMcRun; ++t) part += __popc((unsigned)(codes >> (8 * t)) & 7u);
-    }
-    v_emit = pre + block_sum64(part);
-  }
-  if (threadIdx.x == 0) {
-    P.counts[0] = (long long)v_emit;
-    P.counts[1] = (long long)(tot >> 32);
-    P.counts[2] = (long long)(tot & 0xffffffffull);
-  }
-}
-
-// vertex base ids + vertices; blocks without any cut edge return at once.
-__global__ void __launch_bounds__(kMcThreads) mc_vertices_kernel(const __grid_constant__ McParams P) {
-  if ((int)blockIdx.x == P.nblocks) { mc_write_counts(P); return; }
-  if ((P.block_sums[blockIdx.x] & 0xffffffffull) == 0) return;
-  const long long run = (long long)blockIdx.x * kMcThreads + threadIdx.x;
-  unsigned long long codes = 0;
-  if (run < P.nruns) codes = reinterpret_cast<const unsigned long long*>(P.code)[run];
-  unsigned nv = 0;
-#pragma unroll
-  for (int t = 0; t < kMcRun; ++t) nv += __popc((unsigned)(codes >> (8 * t)) & 7u);
-  const unsigned long long pre = block_prefix(P, blockIdx.x) & 0xffffffffull;
-  unsigned total;
-  const unsigned excl = block_scan_excl(nv, total);
-  if (run >= P.nruns) return;
-  unsigned long long vb = pre + excl;
-  int i, j, k0;
-  run_coords(P, run, i, j, k0);
-  const bool emit = i < P.x_emit;
-  const double level = (double)mc_level(P);
-  const long long stride[3] = {(long long)P.ny * P.nz, (long long)P.nz, 1};
-  uint32_t vb_out[kMcRun];
-#pragma unroll
-  for (int t = 0; t < kMcRun; ++t) {
-    vb_out[t] = (uint32_t)vb;
-    const unsigned flags = (unsigned)(codes >> (8 * t)) & 7u;
-    if (flags && emit) {
-      const int k = k0 + t;
-      const long long p = ((long long)i * P.ny + j) * P.nz + k;
-      const double d0 = fabs((double)P.grid[p] - level);
-      const float base[3] = {(float)(i + P.x_origin), (float)j, (float)k};
-#pragma unroll
-      for (int a = 0; a < 3; ++a) {
-        if (flags & (1u << a)) {
-          if ((long long)vb < P.vcap) {      // capacity overflow: counted, not written (the caller re-runs the emit phase)
-            const double d1 = fabs((double)P.grid[p + stride[a]] - level);
-            const double w0 = 1.0 / ((double)FLT_EPSILON + d0), w1 = 1.0 / ((double)FLT_EPSILON + d1);
-            const double tt = w1 / (w0 + w1);
-            float pos[3] = {base[0], base[1], base[2]};
-            pos[a] = (float)((double)base[a] + tt);
-            float* o = P.verts + vb * 3;
-            o[0] = (pos[0] - P.voffset) * P.vscale;
-            o[1] = (pos[1] - P.voffset) * P.vscale;
-            o[2] = (pos[2] - P.voffset) * P.vscale;
-          }
-          ++vb;
+  const unsigned excl = block_scan_excl(packed, total);
+  // ---- decoupled look-back (warp 0): exclusive prefix of this block over all blocks before it ----
+  if (threadIdx.x < 32) {
+    const unsigned long long agg = (unsigned long long)(total & 0xffffu) | ((unsigned long long)(total >> 16) << 31);
+    unsigned long long prefix = 0;
+    if (b > 0) {
+      if (threadIdx.x == 0) st_state(P.state + b, kMcFlagAgg | agg);
+      int base = b - 1;
+      for (;;) {
+        const int idx = base - (int)threadIdx.x;
+        unsigned long long w = kMcFlagPrefix;                    // before block 0: an empty prefix
+        if (idx >= 0) {
+          do { w = ld_state(P.state + idx); } while ((w >> 62) == 0);
         }
+        const unsigned has_prefix = __ballot_sync(0xffffffffu, (w >> 62) == 2);
+        const int first = has_prefix ? (__ffs(has_prefix) - 1) : 32;     // nearest predecessor that knows its prefix
+        unsigned long long v = ((int)threadIdx.x <= first) ? (w & kMcValMask) : 0ull;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+        prefix += v;
+        if (has_prefix) break;
+        base -= 32;
       }
-    } else {
-      vb += __popc(flags);
+    }
+    if (threadIdx.x == 0) {
+      st_state(P.state + b, kMcFlagPrefix | (prefix + agg));
+      s_prefix = prefix;
+      if (b == P.nblocks - 1) {                                  // totals (slab mode: halo cells were classified empty)
+        const unsigned long long tot = prefix + agg;
+        P.counts[1] = (long long)(tot >> 31);
+        P.counts[2] = (long long)(tot & 0x7fffffffull);
+        if (P.x_emit >= P.nx) P.counts[0] = (long long)(tot & 0x7fffffffull);
+      }
     }
   }
-  uint4* dst = reinterpret_cast<uint4*>(P.vbase + run * kMcRun);
-  dst[0] = make_uint4(vb_out[0], vb_out[1], vb_out[2], vb_out[3]);
-  dst[1] = make_uint4(vb_out[4], vb_out[5], vb_out[6], vb_out[7]);
+  __syncthreads();
+  if (run >= P.nruns) return;
+  const unsigned long long pre = s_prefix;
+  unsigned long long vb = (pre & 0x7fffffffull) + (excl & 0xffffu);
+  const unsigned long long tb = (pre >> 31) + (excl >> 16);
+  if (P.x_emit < P.nx && run == (long long)P.x_emit * P.ny * P.nzc) P.counts[0] = (long long)vb;   // first halo run
+  if (!packed) return;
+  reinterpret_cast<unsigned long long*>(P.code)[run] = codes;
+  P.vbase[run] = (uint32_t)vb;
+  if (!P.emit) return;
+  if (packed >> 16) {                                            // the run owns triangles: face pass work item
+    const unsigned slot = atomicAdd(P.ctrl + 1, 1u);
+    P.work[slot] = make_uint2((unsigned)run, (unsigned)tb);
+  }
+  if (i >= P.x_emit) return;                                     // halo rows: numbered, not emitted
+  const double dlevel = (double)level;
+  const long long stride[3] = {(long long)P.ny * P.nz, (long long)P.nz, 1};
+#pragma unroll 1
+  for (int t = 0; t < kMcRun; ++t) {
+    const unsigned flags = (unsigned)(codes >> (8 * t)) & 7u;
+    if (!flags) continue;
+    const int k = k0 + t;
+    const long long p = ((long long)i * P.ny + j) * P.nz + k;
+    const double d0 = fabs((double)P.grid[p] - dlevel);
+    const float base[3] = {(float)(i + P.x_origin), (float)j, (float)k};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      if (flags & (1u << a)) {
+        if ((long long)vb < P.vcap) {      // capacity overflow: counted, not written (the caller re-runs with larger buffers)
+          const double d1 = fabs((double)P.grid[p + stride[a]] - dlevel);
+          const double w0 = 1.0 / ((double)FLT_EPSILON + d0), w1 = 1.0 / ((double)FLT_EPSILON + d1);
+          const double tt = w1 / (w0 + w1);
+          float pos[3] = {base[0], base[1], base[2]};
+          pos[a] = (float)((double)base[a] + tt);
+          float* o = P.verts + vb * 3;
+          o[0] = (pos[0] - P.voffset) * P.vscale;
+          o[1] = (pos[1] - P.voffset) * P.vscale;
+          o[2] = (pos[2] - P.voffset) * P.vscale;
+        }
+        ++vb;
+      }
+    }
+  }
 }
 
-// point (i,j,k) -> index into the run-major code / vbase arrays
-__device__ __forceinline__ long long run_slot(const McParams& P, int i, int j, int k) {
-  return (((long long)i * P.ny + j) * P.nzc + (k >> 3)) * kMcRun + (k & 7);
+// id of the vertex on axis `a` owned by point (i,j,k): the run's base + the vertices of the points before it
+// in the run + the lower axes of the point itself
+__device__ __forceinline__ int32_t vertex_id(const McParams& P, int i, int j, int k, int a) {
+  const long long r = run_of(P, i, j, k);
+  const unsigned long long codes = reinterpret_cast<const unsigned long long*>(P.code)[r];
+  const int t = k & 7;
+  const unsigned long long before = codes & ((1ull << (8 * t)) - 1ull) & 0x0707070707070707ull;
+  const unsigned own = (unsigned)(codes >> (8 * t)) & 7u;
+  return (int32_t)(P.vbase[r] + __popcll(before) + __popc(own & ((1u << a) - 1u)));
 }
 
 __global__ void __launch_bounds__(kMcThreads) mc_faces_kernel(const __grid_constant__ McParams P) {
-  if ((P.block_sums[blockIdx.x] >> 32) == 0) return;
-  const long long run = (long long)blockIdx.x * kMcThreads + threadIdx.x;
-  unsigned long long codes = 0;
-  if (run < P.nruns) codes = reinterpret_cast<const unsigned long long*>(P.code)[run];
-  unsigned nt_run = 0;
-#pragma unroll
-  for (int t = 0; t < kMcRun; ++t) nt_run += ((unsigned)(codes >> (8 * t)) & 0xffu) >> 3;
-  const unsigned long long pre = block_prefix(P, blockIdx.x) >> 32;
-  unsigned total;
-  const unsigned excl = block_scan_excl(nt_run, total);
-  if (run >= P.nruns || !nt_run) return;
-  unsigned long long tb = pre + excl;
-  int i, j, k0;
-  run_coords(P, run, i, j, k0);
+  const unsigned n_work = P.ctrl[1];
   const float level = mc_level(P);
-  const unsigned r00 = row_bits(P, i, j, k0, level), r01 = row_bits(P, i, j + 1, k0, level);
-  const unsigned r10 = row_bits(P, i + 1, j, k0, level), r11 = row_bits(P, i + 1, j + 1, k0, level);
-  for (int t = 0; t < kMcRun; ++t) {
-    const unsigned nt = ((unsigned)(codes >> (8 * t)) & 0xffu) >> 3;
-    if (!nt) continue;
-    const unsigned cs = ((r00 >> t) & 1u) | (((r10 >> t) & 1u) << 1) | (((r01 >> t) & 1u) << 2) |
-                        (((r11 >> t) & 1u) << 3) | (((r00 >> (t + 1)) & 1u) << 4) | (((r10 >> (t + 1)) & 1u) << 5) |
-                        (((r01 >> (t + 1)) & 1u) << 6) | (((r11 >> (t + 1)) & 1u) << 7);
-    const int k = k0 + t;
-    for (unsigned tr = 0; tr < nt; ++tr) {
-      if ((long long)(tb + tr) >= P.fcap) break;
-      int32_t* o = P.faces + (tb + tr) * 3;
+  for (unsigned wi = blockIdx.x * blockDim.x + threadIdx.x; wi < n_work; wi += gridDim.x * blockDim.x) {
+    const uint2 item = P.work[wi];
+    const long long run = item.x;
+    unsigned long long tb = item.y;
+    const unsigned long long codes = reinterpret_cast<const unsigned long long*>(P.code)[run];
+    int i, j, k0;
+    run_coords(P, run, i, j, k0);
+    const unsigned r00 = row_bits(P, i, j, k0, level), r01 = row_bits(P, i, j + 1, k0, level);
+    const unsigned r10 = row_bits(P, i + 1, j, k0, level), r11 = row_bits(P, i + 1, j + 1, k0, level);
+#pragma unroll 1
+    for (int t = 0; t < kMcRun; ++t) {
+      const unsigned nt = ((unsigned)(codes >> (8 * t)) & 0xffu) >> 3;
+      if (!nt) continue;
+      const unsigned cs = ((r00 >> t) & 1u) | (((r10 >> t) & 1u) << 1) | (((r01 >> t) & 1u) << 2) |
+                          (((r11 >> t) & 1u) << 3) | (((r00 >> (t + 1)) & 1u) << 4) | (((r10 >> (t + 1)) & 1u) << 5) |
+                          (((r01 >> (t + 1)) & 1u) << 6) | (((r11 >> (t + 1)) & 1u) << 7);
+      const int k = k0 + t;
+      for (unsigned tr = 0; tr < nt; ++tr) {
+        if ((long long)(tb + tr) >= P.fcap) break;
+        int32_t* o = P.faces + (tb + tr) * 3;
 #pragma unroll
-      for (int corner = 0; corner < 3; ++corner) {
-        const int e = kMcTriTable[cs][3 * tr + corner];
-        const int a = kMcEdge[e][0];
-        const long long q = run_slot(P, i + kMcEdge[e][1], j + kMcEdge[e][2], k + kMcEdge[e][3]);
-        o[corner] = (int32_t)(P.vbase[q] + __popc((P.code[q] & 7u) & ((1u << a) - 1u)));
+        for (int corner = 0; corner < 3; ++corner) {
+          const int e = kMcTriTable[cs][3 * tr + corner];
+          o[corner] = vertex_id(P, i + kMcEdge[e][1], j + kMcEdge[e][2], k + kMcEdge[e][3], kMcEdge[e][0]);
+        }
       }
+      tb += nt;
     }
-    tb += nt;
   }
 }
 
@@ -401,8 +382,8 @@ extern "C" int64_t vtaco_mc_scratch_bytes(int32_t nx, int32_t ny, int32_t nz) {
   if (nx < 1 || ny < 1 || nz < 1) return VTACO_ERR_INVALID_ARG;
   const long long nruns = (long long)nx * ny * ((nz + kMcRun - 1) / kMcRun);
   const long long nb = (nruns + kMcThreads - 1) / kMcThreads;
-  const long long nsuper = (nb + kMcSuper - 1) / kMcSuper;
-  return mc_align(nruns * kMcRun) + mc_align(4 * nruns * kMcRun) + mc_align(8 * nb) + mc_align(8 * nsuper);
+  // codes (8 B / run), vertex base (4 B / run), work list (8 B / run), look-back state (8 B / block) + control words
+  return mc_align(nruns * 8) + mc_align(4 * nruns) + mc_align(8 * nruns) + mc_align(8 * nb + 256);
 }
 
 extern "C" int vtaco_grid_minmax(const float* grid, int64_t n, int32_t* keys, void* stream) {
@@ -415,10 +396,6 @@ extern "C" int vtaco_grid_minmax(const float* grid, int64_t n, int32_t* keys, vo
   grid_minmax_kernel<<<(unsigned)blocks, 256, 0, st>>>(grid, n, keys);
   VTACO_LAUNCH_CHECK();
   return VTACO_OK;
-}
-
-__global__ void __launch_bounds__(kMcThreads) mc_counts_kernel(const __grid_constant__ vtaco::McParams P) {
-  vtaco::mc_write_counts(P);
 }
 
 extern "C" int vtaco_marching_cubes(const vtaco_mc_args* a, void* stream) {
@@ -441,24 +418,26 @@ extern "C" int vtaco_marching_cubes(const vtaco_mc_args* a, void* stream) {
   P.nzc = (a->nz + kMcRun - 1) / kMcRun;
   P.nruns = (long long)a->nx * a->ny * P.nzc;
   P.nblocks = (int)((P.nruns + kMcThreads - 1) / kMcThreads);
-  P.nsuper = (P.nblocks + kMcSuper - 1) / kMcSuper;
   char* s = reinterpret_cast<char*>(a->scratch);
-  P.code = reinterpret_cast<uint8_t*>(s); s += mc_align(P.nruns * kMcRun);
-  P.vbase = reinterpret_cast<uint32_t*>(s); s += mc_align(4 * P.nruns * kMcRun);
-  P.block_sums = reinterpret_cast<unsigned long long*>(s); s += mc_align(8ll * P.nblocks);
-  P.super_sums = reinterpret_cast<unsigned long long*>(s);
+  P.code = reinterpret_cast<uint8_t*>(s); s += mc_align(P.nruns * 8);
+  P.vbase = reinterpret_cast<uint32_t*>(s); s += mc_align(4 * P.nruns);
+  P.work = reinterpret_cast<uint2*>(s); s += mc_align(8 * P.nruns);
+  P.state = reinterpret_cast<unsigned long long*>(s);
+  P.ctrl = reinterpret_cast<unsigned*>(s + 8ll * P.nblocks);
   P.counts = reinterpret_cast<long long*>(a->counts);
   P.verts = a->vertices; P.vcap = a->vertex_capacity;
   P.faces = a->faces; P.fcap = a->face_capacity;
   P.voffset = a->voffset; P.vscale = a->vscale;
-  if (a->phase & 1) {
-    VTACO_CUDA_CHECK(cudaMemsetAsync(P.super_sums, 0, 8ll * P.nsuper, st));
-    mc_classify_kernel<<<P.nblocks, kMcThreads, 0, st>>>(P);
-    if (!(a->phase & 2)) mc_counts_kernel<<<1, kMcThreads, 0, st>>>(P);
-  }
-  if (a->phase & 2) {
-    mc_vertices_kernel<<<P.nblocks + 1, kMcThreads, 0, st>>>(P);   // + the counter block
-    mc_faces_kernel<<<P.nblocks, kMcThreads, 0, st>>>(P);
+  // phase 1 = count only (nothing is written to the outputs); 2 and 3 = the whole extraction (classification is
+  // part of the same pass, so "emit after a count" simply runs it again with the larger buffers)
+  P.emit = (a->phase & 2) ? 1 : 0;
+  if (!P.emit) P.vcap = 0;
+  VTACO_CUDA_CHECK(cudaMemsetAsync(P.state, 0, 8ll * P.nblocks + 16, st));
+  mc_fused_kernel<<<P.nblocks, kMcThreads, 0, st>>>(P);
+  if (P.emit) {
+    long long blocks = (long long)num_sms() * 4;
+    if (blocks > P.nblocks) blocks = P.nblocks;
+    mc_faces_kernel<<<(unsigned)blocks, kMcThreads, 0, st>>>(P);
   }
   VTACO_LAUNCH_CHECK();
   return VTACO_OK;
