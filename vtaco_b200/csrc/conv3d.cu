@@ -28,6 +28,7 @@ constexpr int kCvThreads = 256;
 constexpr int kCvKC = 16;                 // input channels per chunk (4 planes of 4)
 constexpr int kCvTileY = 16, kCvTileX = 8;
 constexpr int kCvMaxCin = 512;
+constexpr int kCvItems = (3 * 18 * 10 * 4 + kCvThreads - 1) / kCvThreads;   // brick float4s per thread (3x3x3 halo brick)
 constexpr uint32_t kCvIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (4u << 17) | (8u << 24);  // F32 acc, TF32 x TF32, K-major, N=32, M=128
 
 struct ConvParams {
@@ -82,7 +83,7 @@ __host__ __device__ inline CvSmem cv_layout(int ksize, int cin) {
   s.scale = s.w + taps * 2048;
   s.shift = s.scale + cin * 4;
   s.stat = s.shift + cin * 4;
-  s.bar = (s.stat + 64 * 4 + 15) / 16 * 16;
+  s.bar = (s.stat + 64 * 4 + 15) / 16 * 16;   // [0] MMA completion, [1] weights landed (TMA bulk copy)
   s.tmem = s.bar + 16;
   s.total = s.tmem + 16;
   return s;
@@ -135,6 +136,7 @@ __global__ void __launch_bounds__(kCvThreads, 2) conv3d_tc_kernel(const __grid_c
   if (tid < 64) sStat[tid] = 0.0f;
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(cv_smem_u32(sBar)) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(cv_smem_u32(sBar + 1)) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -146,47 +148,82 @@ __global__ void __launch_bounds__(kCvThreads, 2) conv3d_tc_kernel(const __grid_c
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = *sTmem;
-  const uint32_t bar = cv_smem_u32(sBar);
+  const uint32_t bar = cv_smem_u32(sBar), wbar = cv_smem_u32(sBar + 1);
+  uint32_t wphase = 0;
   const uint32_t brick_sm = cv_smem_u32(sm + L.brick), w_sm = cv_smem_u32(sm + L.w);
   uint32_t phase = 0;
+
+  // this thread's brick items (i = tid + u * 256 -> voxel i / 4, channel quad i % 4 == tid % 4): global voxel
+  // index in the full-resolution source and in the half-resolution one, or -1 outside the volume
+  const int total_items = L.bvox * 4;
+  int voxA[kCvItems], voxB[kCvItems];
+#pragma unroll
+  for (int u = 0; u < kCvItems; ++u) {
+    const int i = tid + u * kCvThreads;
+    const int v = i >> 2;
+    const int bxv = v % bx_ext, r = v / bx_ext;
+    const int byv = r % by_ext, bzv = r / by_ext;
+    const int gz = z + bzv - h, gy = y0 + byv - h, gx = x0 + bxv - h;
+    const bool inb = i < total_items && gz >= 0 && gz < P.D && gy >= 0 && gy < P.H && gx >= 0 && gx < P.W;
+    voxA[u] = inb ? (int)((((size_t)n * P.D + gz) * P.H + gy) * P.W + gx) : -1;
+    voxB[u] = -1;
+    if (inb && P.C2 > 0) {   // ATen nearest: src = min(floor(dst * in / out), in - 1)
+      const int sz = min(gz * P.D2 / P.D, P.D2 - 1), sy = min(gy * P.H2 / P.H, P.H2 - 1), sx = min(gx * P.W2 / P.W, P.W2 - 1);
+      voxB[u] = (int)((((size_t)n * P.D2 + sz) * P.H2 + sy) * P.W2 + sx);
+    }
+  }
 
   const int n_chunks = Cin / kCvKC;
   const float4* wsrc = reinterpret_cast<const float4*>(P.w) + (size_t)ntile * n_chunks * taps * 128;
   for (int ch = 0; ch < n_chunks; ++ch) {
-    // ---- weights of this (out-channel tile, chunk): taps x 2 KB, contiguous in the packed buffer ----
-    {
-      float4* dst = reinterpret_cast<float4*>(sm + L.w);
+    // ---- weights of this (out-channel tile, chunk): taps x 2 KB, contiguous in the packed buffer: ONE bulk
+    //      async copy (TMA engine, completion on an mbarrier) instead of 13 dependent loads per thread ----
+    if (tid == 0) {
+      const uint32_t bytes = (uint32_t)taps * 2048u;
       const float4* src = wsrc + (size_t)ch * taps * 128;
-      for (int i = tid; i < taps * 128; i += kCvThreads) dst[i] = __ldg(src + i);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(wbar), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(w_sm),
+                   "l"(src), "r"(bytes), "r"(wbar)
+                   : "memory");
     }
-    // ---- halo brick of 16 input channels: GroupNorm-apply, TF32 rounding, zero padding ----
+    // ---- halo brick of 16 input channels: GroupNorm-apply, TF32 rounding, zero padding.  The brick geometry
+    //      is the same for every chunk, so the voxel offsets of this thread's items were computed once (voxA /
+    //      voxB); the loads of a batch are all issued before the first is used. ----
     {
       const int c0 = ch * kCvKC;
       const bool second = c0 >= P.C1;                       // channels from the half-resolution tensor (upsample + concat)
       const float* src = second ? P.x2 : P.x;
       const int Cs = second ? P.C2 : P.C1, cs0 = second ? c0 - P.C1 : c0;
-      for (int i = tid; i < L.bvox * 4; i += kCvThreads) {
-        const int v = i >> 2, q = i & 3;
-        const int bxv = v % bx_ext, r = v / bx_ext;
-        const int byv = r % by_ext, bzv = r / by_ext;
-        const int gz = z + bzv - h, gy = y0 + byv - h, gx = x0 + bxv - h;
-        float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (gz >= 0 && gz < P.D && gy >= 0 && gy < P.H && gx >= 0 && gx < P.W) {
-          size_t vox;
-          if (second) {   // ATen nearest: src = min(floor(dst * in / out), in - 1)
-            const int sz = min(gz * P.D2 / P.D, P.D2 - 1), sy = min(gy * P.H2 / P.H, P.H2 - 1), sx = min(gx * P.W2 / P.W, P.W2 - 1);
-            vox = (((size_t)n * P.D2 + sz) * P.H2 + sy) * P.W2 + sx;
-          } else {
-            vox = (((size_t)n * P.D + gz) * P.H + gy) * P.W + gx;
+      const int q = tid & 3;
+      const float4 sc = *reinterpret_cast<const float4*>(sScale + c0 + 4 * q);
+      const float4 sh = *reinterpret_cast<const float4*>(sShift + c0 + 4 * q);
+#pragma unroll
+      for (int b0 = 0; b0 < kCvItems; b0 += 5) {
+        float4 val[5];
+#pragma unroll
+        for (int u = 0; u < 5; ++u) {
+          if (b0 + u < kCvItems) {
+            const int vox = second ? voxB[b0 + u] : voxA[b0 + u];
+            val[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (vox >= 0) val[u] = __ldg(reinterpret_cast<const float4*>(src + (size_t)vox * Cs + cs0) + q);
           }
-          const float4 a = __ldg(reinterpret_cast<const float4*>(src + vox * Cs + cs0) + q);
-          const int c = c0 + 4 * q;
-          val.x = cv_tf32(fmaf(a.x, sScale[c], sShift[c]));
-          val.y = cv_tf32(fmaf(a.y, sScale[c + 1], sShift[c + 1]));
-          val.z = cv_tf32(fmaf(a.z, sScale[c + 2], sShift[c + 2]));
-          val.w = cv_tf32(fmaf(a.w, sScale[c + 3], sShift[c + 3]));
         }
-        *reinterpret_cast<float4*>(sm + L.brick + q * L.plane_stride + v * 16) = val;
+#pragma unroll
+        for (int u = 0; u < 5; ++u) {
+          if (b0 + u < kCvItems) {
+            const int i = tid + (b0 + u) * kCvThreads;
+            if (i < total_items) {
+              float4 o = val[u];
+              if ((second ? voxB[b0 + u] : voxA[b0 + u]) >= 0) {
+                o.x = cv_tf32(fmaf(o.x, sc.x, sh.x));
+                o.y = cv_tf32(fmaf(o.y, sc.y, sh.y));
+                o.z = cv_tf32(fmaf(o.z, sc.z, sh.z));
+                o.w = cv_tf32(fmaf(o.w, sc.w, sh.w));
+              }
+              *reinterpret_cast<float4*>(sm + L.brick + q * L.plane_stride + (i >> 2) * 16) = o;
+            }
+          }
+        }
       }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy stores -> visible to the tensor core
@@ -196,6 +233,10 @@ __global__ void __launch_bounds__(kCvThreads, 2) conv3d_tc_kernel(const __grid_c
       uint32_t pred;
       asm volatile("{\n.reg .b32 rx;\n.reg .pred px;\nelect.sync rx|px, 0xffffffff;\nselp.u32 %0, 1, 0, px;\n}\n" : "=r"(pred));
       if (pred) {
+        asm volatile(   // the weights have landed
+            "{\n.reg .pred p;\nCW_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra CW_DONE;\nbra CW_WAIT;\nCW_DONE:\n}\n" ::"r"(wbar),
+            "r"(wphase)
+            : "memory");
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         for (int tap = 0; tap < taps; ++tap) {
           const int dx = tap % P.ksize, dy = (tap / P.ksize) % P.ksize, dz = tap / (P.ksize * P.ksize);
@@ -211,6 +252,7 @@ __global__ void __launch_bounds__(kCvThreads, 2) conv3d_tc_kernel(const __grid_c
       }
       __syncwarp();
     }
+    wphase ^= 1;
     // the MMAs read the brick and the weights: wait before the next chunk overwrites them
     asm volatile(
         "{\n.reg .pred p;\nCV_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra CV_DONE;\nbra CV_WAIT;\nCV_DONE:\n}\n" ::"r"(bar),
