@@ -143,7 +143,7 @@ __device__ __forceinline__ unsigned row_bits(const McParams& P, int i, int j, in
 // its 8 corner bits are neither all 0 nor all 1, so the ~95 % of runs that the surface does not
 // touch cost a handful of logic ops; only the set bits take the per-point path.
 __device__ __forceinline__ unsigned run_codes(const McParams& P, int i, int j, int k0, float level,
-                                               unsigned long long& codes) {
+                                               unsigned long long& codes, const uint8_t* __restrict__ tri_count) {
   const unsigned r00 = row_bits(P, i, j, k0, level), r01 = row_bits(P, i, j + 1, k0, level);
   const unsigned r10 = row_bits(P, i + 1, j, k0, level), r11 = row_bits(P, i + 1, j + 1, k0, level);
   const bool hx = i + 1 < P.nx, hy = j + 1 < P.ny;
@@ -169,7 +169,7 @@ __device__ __forceinline__ unsigned run_codes(const McParams& P, int i, int j, i
       const unsigned cs = ((r00 >> t) & 1u) | (((r10 >> t) & 1u) << 1) | (((r01 >> t) & 1u) << 2) |
                           (((r11 >> t) & 1u) << 3) | (((r00 >> (t + 1)) & 1u) << 4) | (((r10 >> (t + 1)) & 1u) << 5) |
                           (((r01 >> (t + 1)) & 1u) << 6) | (((r11 >> (t + 1)) & 1u) << 7);
-      nt = (unsigned)kMcTriCount[cs];
+      nt = (unsigned)tri_count[cs];     // shared-memory copy: a divergent __constant__ index is serialised per lane
     }
     codes |= (unsigned long long)(flags | (nt << 3)) << (8 * t);
     packed += nt << 16;
@@ -193,23 +193,37 @@ __device__ __forceinline__ long long run_of(const McParams& P, int i, int j, int
   return ((long long)i * P.ny + j) * P.nzc + (k >> 3);
 }
 
+constexpr int kMcSub = 4;                          // consecutive 256-run sub-blocks per CTA: 4x fewer look-back words
+constexpr int kMcBlockRuns = kMcThreads * kMcSub;
+
 __global__ void __launch_bounds__(kMcThreads) mc_fused_kernel(const __grid_constant__ McParams P) {
   __shared__ int s_bid;
   __shared__ unsigned long long s_prefix;
+  __shared__ uint8_t s_tricount[256];
   if (threadIdx.x == 0) s_bid = (int)atomicAdd(P.ctrl, 1u);      // ticket: all blocks before this one have started
+  s_tricount[threadIdx.x] = (uint8_t)kMcTriCount[threadIdx.x];
   __syncthreads();
   const int b = s_bid;
-  const long long run = (long long)b * kMcThreads + threadIdx.x;
   const float level = mc_level(P);
-  unsigned packed = 0;
-  unsigned long long codes = 0;
-  int i = 0, j = 0, k0 = 0;
-  if (run < P.nruns) {
-    run_coords(P, run, i, j, k0);
-    packed = run_codes(P, i, j, k0, level, codes);
+  // ---- classify kMcSub runs per thread (run = block base + s * 256 + thread: coalesced, lattice order = (s, thread)) ----
+  unsigned packed[kMcSub], excl[kMcSub];
+  unsigned long long codes[kMcSub];
+  unsigned sub_base = 0;                                         // packed totals of the sub-blocks before s
+#pragma unroll
+  for (int s = 0; s < kMcSub; ++s) {
+    const long long run = (long long)b * kMcBlockRuns + s * kMcThreads + threadIdx.x;
+    packed[s] = 0;
+    codes[s] = 0;
+    if (run < P.nruns) {
+      int i, j, k0;
+      run_coords(P, run, i, j, k0);
+      packed[s] = run_codes(P, i, j, k0, level, codes[s], s_tricount);
+    }
+    unsigned total;
+    excl[s] = sub_base + block_scan_excl(packed[s], total);
+    sub_base += total;                                           // fields: vertices < 2^16 (4 x 6144), triangles < 2^16 (4 x 10240)
   }
-  unsigned total;
-  const unsigned excl = block_scan_excl(packed, total);
+  const unsigned total = sub_base;
   // ---- decoupled look-back (warp 0): exclusive prefix of this block over all blocks before it ----
   if (threadIdx.x < 32) {
     const unsigned long long agg = (unsigned long long)(total & 0xffffu) | ((unsigned long long)(total >> 16) << 31);
@@ -218,19 +232,33 @@ __global__ void __launch_bounds__(kMcThreads) mc_fused_kernel(const __grid_const
       if (threadIdx.x == 0) st_state(P.state + b, kMcFlagAgg | agg);
       int base = b - 1;
       for (;;) {
-        const int idx = base - (int)threadIdx.x;
-        unsigned long long w = kMcFlagPrefix;                    // before block 0: an empty prefix
-        if (idx >= 0) {
-          do { w = ld_state(P.state + idx); } while ((w >> 62) == 0);
+        constexpr int kLb = 2;                                   // words per lane: 64 predecessors per round
+        unsigned long long w[kLb];
+#pragma unroll
+        for (int h = 0; h < kLb; ++h) {                          // lane l reads predecessors base - 32 h - l
+          const int idx = base - 32 * h - (int)threadIdx.x;
+          w[h] = kMcFlagPrefix;                                  // before block 0: an empty prefix
+          if (idx >= 0) w[h] = ld_state(P.state + idx);
         }
-        const unsigned has_prefix = __ballot_sync(0xffffffffu, (w >> 62) == 2);
-        const int first = has_prefix ? (__ffs(has_prefix) - 1) : 32;     // nearest predecessor that knows its prefix
-        unsigned long long v = ((int)threadIdx.x <= first) ? (w & kMcValMask) : 0ull;
+        // a word that is not published yet ends the usable range of this round: everything nearer than the
+        // nearest prefix word must be an aggregate, otherwise look again
+        int first = kLb * 32, hole = kLb * 32;
+#pragma unroll
+        for (int h = kLb - 1; h >= 0; --h) {
+          const unsigned pp = __ballot_sync(0xffffffffu, (w[h] >> 62) == 2), zz = __ballot_sync(0xffffffffu, (w[h] >> 62) == 0);
+          if (pp) first = 32 * h + (__ffs(pp) - 1);
+          if (zz) hole = 32 * h + (__ffs(zz) - 1);
+        }
+        if (hole < first) continue;                              // an unpublished predecessor nearer than the prefix: poll again
+        unsigned long long v = 0;
+#pragma unroll
+        for (int h = 0; h < kLb; ++h)
+          if (32 * h + (int)threadIdx.x <= first) v += w[h] & kMcValMask;
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
         prefix += v;
-        if (has_prefix) break;
-        base -= 32;
+        if (first < kLb * 32) break;
+        base -= kLb * 32;
       }
     }
     if (threadIdx.x == 0) {
@@ -245,45 +273,53 @@ __global__ void __launch_bounds__(kMcThreads) mc_fused_kernel(const __grid_const
     }
   }
   __syncthreads();
-  if (run >= P.nruns) return;
   const unsigned long long pre = s_prefix;
-  unsigned long long vb = (pre & 0x7fffffffull) + (excl & 0xffffu);
-  const unsigned long long tb = (pre >> 31) + (excl >> 16);
-  if (P.x_emit < P.nx && run == (long long)P.x_emit * P.ny * P.nzc) P.counts[0] = (long long)vb;   // first halo run
-  if (!packed) return;
-  reinterpret_cast<unsigned long long*>(P.code)[run] = codes;
-  P.vbase[run] = (uint32_t)vb;
-  if (!P.emit) return;
-  if (packed >> 16) {                                            // the run owns triangles: face pass work item
-    const unsigned slot = atomicAdd(P.ctrl + 1, 1u);
-    P.work[slot] = make_uint2((unsigned)run, (unsigned)tb);
-  }
-  if (i >= P.x_emit) return;                                     // halo rows: numbered, not emitted
   const double dlevel = (double)level;
   const long long stride[3] = {(long long)P.ny * P.nz, (long long)P.nz, 1};
-#pragma unroll 1
-  for (int t = 0; t < kMcRun; ++t) {
-    const unsigned flags = (unsigned)(codes >> (8 * t)) & 7u;
-    if (!flags) continue;
-    const int k = k0 + t;
-    const long long p = ((long long)i * P.ny + j) * P.nz + k;
-    const double d0 = fabs((double)P.grid[p] - dlevel);
-    const float base[3] = {(float)(i + P.x_origin), (float)j, (float)k};
 #pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      if (flags & (1u << a)) {
-        if ((long long)vb < P.vcap) {      // capacity overflow: counted, not written (the caller re-runs with larger buffers)
-          const double d1 = fabs((double)P.grid[p + stride[a]] - dlevel);
-          const double w0 = 1.0 / ((double)FLT_EPSILON + d0), w1 = 1.0 / ((double)FLT_EPSILON + d1);
-          const double tt = w1 / (w0 + w1);
-          float pos[3] = {base[0], base[1], base[2]};
-          pos[a] = (float)((double)base[a] + tt);
-          float* o = P.verts + vb * 3;
-          o[0] = (pos[0] - P.voffset) * P.vscale;
-          o[1] = (pos[1] - P.voffset) * P.vscale;
-          o[2] = (pos[2] - P.voffset) * P.vscale;
+  for (int s = 0; s < kMcSub; ++s) {
+    const long long run = (long long)b * kMcBlockRuns + s * kMcThreads + threadIdx.x;
+    if (run >= P.nruns) continue;
+    unsigned long long vb = (pre & 0x7fffffffull) + (excl[s] & 0xffffu);
+    const unsigned long long tb = (pre >> 31) + (excl[s] >> 16);
+    if (P.x_emit < P.nx && run == (long long)P.x_emit * P.ny * P.nzc) P.counts[0] = (long long)vb;   // first halo run
+    if (!packed[s]) continue;
+    reinterpret_cast<unsigned long long*>(P.code)[run] = codes[s];
+    P.vbase[run] = (uint32_t)vb;
+    if (!P.emit) continue;
+    if (packed[s] >> 16) {                                       // the run owns triangles: face pass work item
+      const unsigned slot = atomicAdd(P.ctrl + 1, 1u);
+      P.work[slot] = make_uint2((unsigned)run, (unsigned)tb);
+    }
+    int i, j, k0;
+    run_coords(P, run, i, j, k0);
+    if (i >= P.x_emit) continue;                                 // halo rows: numbered, not emitted
+#pragma unroll 1
+    for (int t = 0; t < kMcRun; ++t) {
+      const unsigned flags = (unsigned)(codes[s] >> (8 * t)) & 7u;
+      if (!flags) continue;
+      const int k = k0 + t;
+      const long long p = ((long long)i * P.ny + j) * P.nz + k;
+      const double d0 = fabs((double)P.grid[p] - dlevel);
+      const float base[3] = {(float)(i + P.x_origin), (float)j, (float)k};
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        if (flags & (1u << a)) {
+          if ((long long)vb < P.vcap) {    // capacity overflow: counted, not written (the caller re-runs with larger buffers)
+            const double d1 = fabs((double)P.grid[p + stride[a]] - dlevel);
+            // Lewiner's weights w = 1 / (eps + d): t = w1 / (w0 + w1) = (eps + d0) / ((eps + d0) + (eps + d1)), one
+            // division instead of three (equal to the last bit or two of the double, far below the float32 result)
+            const double e0 = (double)FLT_EPSILON + d0, e1 = (double)FLT_EPSILON + d1;
+            const double tt = e0 / (e0 + e1);
+            float pos[3] = {base[0], base[1], base[2]};
+            pos[a] = (float)((double)base[a] + tt);
+            float* o = P.verts + vb * 3;
+            o[0] = (pos[0] - P.voffset) * P.vscale;
+            o[1] = (pos[1] - P.voffset) * P.vscale;
+            o[2] = (pos[2] - P.voffset) * P.vscale;
+          }
+          ++vb;
         }
-        ++vb;
       }
     }
   }
@@ -301,6 +337,16 @@ __device__ __forceinline__ int32_t vertex_id(const McParams& P, int i, int j, in
 }
 
 __global__ void __launch_bounds__(kMcThreads) mc_faces_kernel(const __grid_constant__ McParams P) {
+  // case tables in shared memory: every lane indexes them with its own case (a divergent __constant__ index costs
+  // one replay per distinct address — it was the top stall of this kernel); a case row is one 16-byte load
+  __shared__ uint4 s_tri[256];
+  __shared__ int8_t s_edge[12][4];
+  {
+    int8_t* dst = reinterpret_cast<int8_t*>(s_tri);
+    for (int i = threadIdx.x; i < 256 * 16; i += blockDim.x) dst[i] = (i & 15) < 15 ? kMcTriTable[i >> 4][i & 15] : (int8_t)0;
+    if (threadIdx.x < 48) s_edge[threadIdx.x >> 2][threadIdx.x & 3] = kMcEdge[threadIdx.x >> 2][threadIdx.x & 3];
+  }
+  __syncthreads();
   const unsigned n_work = P.ctrl[1];
   const float level = mc_level(P);
   for (unsigned wi = blockIdx.x * blockDim.x + threadIdx.x; wi < n_work; wi += gridDim.x * blockDim.x) {
@@ -320,15 +366,19 @@ __global__ void __launch_bounds__(kMcThreads) mc_faces_kernel(const __grid_const
                           (((r11 >> t) & 1u) << 3) | (((r00 >> (t + 1)) & 1u) << 4) | (((r10 >> (t + 1)) & 1u) << 5) |
                           (((r01 >> (t + 1)) & 1u) << 6) | (((r11 >> (t + 1)) & 1u) << 7);
       const int k = k0 + t;
+      const uint4 row = s_tri[cs];
+      const int8_t* edges = reinterpret_cast<const int8_t*>(&row);
       for (unsigned tr = 0; tr < nt; ++tr) {
         if ((long long)(tb + tr) >= P.fcap) break;
         int32_t* o = P.faces + (tb + tr) * 3;
 #pragma unroll
         for (int corner = 0; corner < 3; ++corner) {
-          const int e = kMcTriTable[cs][3 * tr + corner];
-          o[corner] = vertex_id(P, i + kMcEdge[e][1], j + kMcEdge[e][2], k + kMcEdge[e][3], kMcEdge[e][0]);
+          const int e = (int)((reinterpret_cast<const unsigned*>(&row)[(3 * tr + corner) >> 2] >> (8 * ((3 * tr + corner) & 3))) & 0xffu);
+          const char4 ed = *reinterpret_cast<const char4*>(s_edge[e]);
+          o[corner] = vertex_id(P, i + ed.y, j + ed.z, k + ed.w, ed.x);
         }
       }
+      (void)edges;
       tb += nt;
     }
   }
@@ -417,7 +467,7 @@ extern "C" int vtaco_marching_cubes(const vtaco_mc_args* a, void* stream) {
   P.n_level_keys = a->n_level_keys > 1 ? a->n_level_keys : 1;
   P.nzc = (a->nz + kMcRun - 1) / kMcRun;
   P.nruns = (long long)a->nx * a->ny * P.nzc;
-  P.nblocks = (int)((P.nruns + kMcThreads - 1) / kMcThreads);
+  P.nblocks = (int)((P.nruns + kMcBlockRuns - 1) / kMcBlockRuns);
   char* s = reinterpret_cast<char*>(a->scratch);
   P.code = reinterpret_cast<uint8_t*>(s); s += mc_align(P.nruns * 8);
   P.vbase = reinterpret_cast<uint32_t*>(s); s += mc_align(4 * P.nruns);
@@ -436,7 +486,7 @@ extern "C" int vtaco_marching_cubes(const vtaco_mc_args* a, void* stream) {
   mc_fused_kernel<<<P.nblocks, kMcThreads, 0, st>>>(P);
   if (P.emit) {
     long long blocks = (long long)num_sms() * 4;
-    if (blocks > P.nblocks) blocks = P.nblocks;
+    if (blocks > (P.nruns + kMcThreads - 1) / kMcThreads) blocks = (P.nruns + kMcThreads - 1) / kMcThreads;
     mc_faces_kernel<<<(unsigned)blocks, kMcThreads, 0, st>>>(P);
   }
   VTACO_LAUNCH_CHECK();
