@@ -151,7 +151,8 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     structs = {'vtaco_decoder_args': _abi.DecoderArgs, 'vtaco_decoder_bwd_args': _abi.DecoderBwdArgs,
                'vtaco_encoder_args': EncoderArgs, 'vtaco_encoder_bwd_args': EncoderBwdArgs,
-               'vtaco_mc_args': _abi.McArgs}
+               'vtaco_mc_args': _abi.McArgs, 'vtaco_conv3d_args': _abi.Conv3dArgs, 'vtaco_exchange': _abi.Exchange,
+               'vtaco_mesh_piece': _abi.MeshPiece, 'vtaco_pack_desc': _abi.PackDesc}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "vtaco_b200.h"', 'int main(void) {']
     for cname, cls in structs.items():
         lines.append('  printf("%s sizeof %%zu\\n", sizeof(%s));' % (cname, cname))
