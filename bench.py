@@ -114,7 +114,7 @@ class ClockSampler(object):
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.004)   # the timed region is tens of ms: sample every 4 ms
+            self._stop.wait(0.001)   # the timed region is ~10-60 ms: sample every millisecond
 
     def __enter__(self):
         if self._h is not None:

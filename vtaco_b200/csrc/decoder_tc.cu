@@ -740,7 +740,9 @@ __host__ __device__ inline Tc2Smem tc2_smem_layout(int n_blocks) {
 
 template <bool DENSE, bool MIXED>
 __global__ void __launch_bounds__(kTc2Threads, 1) decoder_tc2_kernel(const __grid_constant__ DecParams P,
-                                                                     const float* __restrict__ wtc) {
+                                                                     const float* __restrict__ wtc,
+                                                                     long long* __restrict__ trace) {
+  int trace_n = 0;
   extern __shared__ __align__(1024) unsigned char tsm[];
   const Tc2Smem L = tc2_smem_layout(P.n_blocks);
   float* sWtc = reinterpret_cast<float*>(tsm + L.w);
@@ -849,6 +851,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) decoder_tc2_kernel(const __gri
       oidx = nn;
     }
     if (!valid) oidx = 0;
+    TC_STAMP(13);  // tile start: coordinates loaded
 
     // ---------------- gather: this thread's 16 channels of its query (+ of its c_img row): operands of step 0 ----------------
     if (P.has_c || cimg) {
@@ -938,6 +941,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) decoder_tc2_kernel(const __gri
         }
         __syncwarp();
       }
+      TC_STAMP(15);  // features of the thread's query in registers
       split_store16<MIXED>(tC, hv, cv);
      }
       if (cimg) {   // fc_p_img(cat[p, c_img]) = fc_p_img[:, :3] p + b + W_img c_img: the last term rides in step 0
@@ -1003,23 +1007,31 @@ __global__ void __launch_bounds__(kTc2Threads, 1) decoder_tc2_kernel(const __gri
 
     // ---------------- residual blocks ----------------
     for (int i = 0; i < nb; ++i) {
+      TC_STAMP(1);   // ALU phase starts (accumulator already read)
 #pragma unroll
       for (int j = 0; j < 16; ++j) x[j] = fmaxf(net[j], 0.f);
       split_store16<MIXED>(tX, hv, x);
+      TC_STAMP(2);   // operands computed, tcgen05.st issued
       tc_wait_st();
       tc_fence_before();
+      TC_STAMP(3);   // stores complete
       group_sync2();
+      TC_STAMP(4);   // group barrier passed
       if (wq == (step & 7) && elect_one()) {     // D = relu(net)*W0_i + ones*b0_i
         tc_fence_after();
         issue_product(mD, mX, wsm + (3 * i + 1) * 8192, 0, n_prod);
         tc_mma_ts(mD, mOnes, make_bdesc(bsm + (2 * i + 1) * 1024), 1);
         tc_commit(bar);
+        TC_STAMP(20);  // issuer only: 13 MMAs + commit issued
       }
       ++step;
+      TC_STAMP(5);   // (issuing warp: MMAs issued)
       mbar_wait(bar, ph); ph ^= 1;
+      TC_STAMP(6);   // MMAs complete
       tc_fence_after();
       tmem_ld16(tD + ch0, r);
       tc_wait_ld();
+      TC_STAMP(7);   // accumulator in registers
 #pragma unroll
       for (int j = 0; j < 16; ++j) x[j] = fmaxf(__uint_as_float(r[j]), 0.f);
       split_store16<MIXED>(tX, hv, x);
@@ -1042,6 +1054,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) decoder_tc2_kernel(const __gri
       for (int j = 0; j < 16; ++j) net[j] += __uint_as_float(r[j]);
     }
 
+    TC_STAMP(19);    // blocks done
     // ---------------- heads: partial dot products of the two halves, combined through shared memory ----------------
     {
       const float* Wo = sSmall + 128;
@@ -1102,7 +1115,7 @@ int launch_decoder_tc(DecParams P, bool dense, const float* wtc, cudaStream_t st
   if (P.tc_split == 2) {   // two threads per query
     const Tc2Smem L2 = tc2_smem_layout(P.n_blocks);
     if (L2.total > 227 * 1024) return VTACO_ERR_UNSUPPORTED;
-    using Kernel2 = void (*)(DecParams, const float*);
+    using Kernel2 = void (*)(DecParams, const float*, long long*);
     const Kernel2 k2 = dense ? (mixed ? (Kernel2)decoder_tc2_kernel<true, true> : (Kernel2)decoder_tc2_kernel<true, false>)
                              : (mixed ? (Kernel2)decoder_tc2_kernel<false, true> : (Kernel2)decoder_tc2_kernel<false, false>);
     static std::atomic<size_t> configured2[4][64];   // idempotent opt-in cache, safe across host threads
@@ -1115,8 +1128,31 @@ int launch_decoder_tc(DecParams P, bool dense, const float* wtc, cudaStream_t st
     }
     long long grid2 = (P.n_tiles + kTcGroups - 1) / kTcGroups;
     if (grid2 > num_sms()) grid2 = num_sms();
-    k2<<<(unsigned)grid2, kTc2Threads, L2.total, stream>>>(P, wtc);
+    long long* trace2 = nullptr;
+    static const bool want_trace2 = getenv("VTACO_TC_TRACE") != nullptr;
+    if (want_trace2) {
+      VTACO_CUDA_CHECK(cudaMalloc(&trace2, 4096 * sizeof(long long)));
+      VTACO_CUDA_CHECK(cudaMemsetAsync(trace2, 0, 4096 * sizeof(long long), stream));
+    }
+    k2<<<(unsigned)grid2, kTc2Threads, L2.total, stream>>>(P, wtc, trace2);
     VTACO_LAUNCH_CHECK();
+    if (trace2) {   // debug: average cycles between consecutive stamps of warp 0 / block 0, per (from -> to) slot pair
+      static long long h2[4096];
+      VTACO_CUDA_CHECK(cudaStreamSynchronize(stream));
+      VTACO_CUDA_CHECK(cudaMemcpy(h2, trace2, sizeof(h2), cudaMemcpyDeviceToHost));
+      cudaFree(trace2);
+      static double sum2[32][32];
+      static long long cnt2[32][32];
+      for (int a = 0; a < 32; ++a) for (int b = 0; b < 32; ++b) { sum2[a][b] = 0; cnt2[a][b] = 0; }
+      for (int i = 1; i < 4096 && h2[i]; ++i) {
+        const int a = (int)(h2[i - 1] >> 56) & 31, b = (int)(h2[i] >> 56) & 31;
+        const long long d = (h2[i] & 0x00ffffffffffffffll) - (h2[i - 1] & 0x00ffffffffffffffll);
+        if (d >= 0 && d < 1000000) { sum2[a][b] += (double)d; cnt2[a][b]++; }
+      }
+      for (int a = 0; a < 32; ++a)
+        for (int b = 0; b < 32; ++b)
+          if (cnt2[a][b]) fprintf(stderr, "[vtaco tc2 trace] %d -> %d : %8.0f cycles (n=%lld)\n", a, b, sum2[a][b] / cnt2[a][b], cnt2[a][b]);
+    }
     return VTACO_OK;
   }
   const TcSmem L = tc_smem_layout(P.n_blocks);

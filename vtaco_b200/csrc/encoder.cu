@@ -206,21 +206,35 @@ __global__ void __launch_bounds__(kET) enc_block_kernel(const __grid_constant__ 
       xcol[j * kES] = fmaf(Wp[128 + j], pz, fmaf(Wp[64 + j], py, fmaf(Wp[j], px, Wp[ENC_OFF_BPOS + j])));
   } else {
     const float* netin = P.net[net_in];
-    for (int i = 0; i < 32; ++i) {
-      const long long ni = nb0 + col0 + i;
-      if (ni >= P.n) break;
-      sX[lane * kES + col0 + i] = netin[ni * 32 + lane];
-      float s = 0.f;  // c_out = 0; c_out += fea  (key order xz, xy, yz, grid)
+    // 8 rows per batch: all global loads of a batch are in flight together (the row-at-a-time loop paid one
+    // L2 round trip per row and key — most of this kernel's time at the shipped T = 3 640)
+    for (int i0 = 0; i0 < 32; i0 += 8) {
+      float a[8], s[8];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (k < P.nkeys) {
-          const int sl = __shfl_sync(kFullMask, myslot[k], i);
-          float v = P.pool[r_read][k][(long long)sl * 32 + lane];
-          if (P.pool_mean) v = v / (float)P.count[k][sl];
-          s += v;
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + u;
+        const long long ni = nb0 + col0 + i;
+        const bool ok = ni < P.n;                       // warp-uniform
+        a[u] = ok ? netin[ni * 32 + lane] : 0.f;
+        s[u] = 0.f;  // c_out = 0; c_out += fea  (key order xz, xy, yz, grid)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (k < P.nkeys) {
+            const int sl = __shfl_sync(kFullMask, myslot[k], i);
+            float v = ok ? P.pool[r_read][k][(long long)sl * 32 + lane] : 0.f;
+            if (P.pool_mean && ok) v = v / (float)P.count[k][sl];
+            s[u] += v;
+          }
         }
       }
-      sX[(32 + lane) * kES + col0 + i] = s;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + u;
+        if (nb0 + col0 + i < P.n) {
+          sX[lane * kES + col0 + i] = a[u];
+          sX[(32 + lane) * kES + col0 + i] = s[u];
+        }
+      }
     }
   }
   __syncwarp();
@@ -270,10 +284,10 @@ __global__ void __launch_bounds__(kET) enc_final_kernel(const __grid_constant__ 
   int myslot[4] = {0, 0, 0, 0};
   for (int k = 0; k < P.nkeys; ++k) myslot[k] = valid ? P.slot[k][n] : 0;
   const float* netin = P.net[net_in];
+#pragma unroll 8
   for (int i = 0; i < 32; ++i) {
     const long long ni = nb0 + col0 + i;
-    if (ni >= P.n) break;
-    sX[lane * kES + col0 + i] = netin[ni * 32 + lane];
+    if (ni < P.n) sX[lane * kES + col0 + i] = netin[ni * 32 + lane];
   }
   __syncwarp();
   float* xcol = sX + tid;

@@ -208,12 +208,19 @@ class UNet3D(nn.Module):
         a.y = y.data_ptr()
         ys = None
         if want_stats:
-            ys = torch.zeros((N, conv.out_channels, 2), dtype=torch.float64, device=x.device)
+            ys = self._take_stats(N, conv.out_channels)
             a.out_stats = ys.data_ptr()
         with torch.cuda.device(x.device):
             st = _abi.lib().vtaco_conv3d_cl(C.byref(a), _abi.stream_ptr(x.device))
         _abi.check(st, 'conv3d_cl')
         return y, ys
+
+    def _take_stats(self, N, C):
+        """(N, C, 2) float64 slice of the forward's statistics arena (zeroed once per forward)."""
+        n = N * C * 2
+        out = self._arena[self._arena_pos:self._arena_pos + n].view(N, C, 2)
+        self._arena_pos += n
+        return out
 
     def _forward_fused(self, x):
         from .. import _abi
@@ -224,8 +231,12 @@ class UNet3D(nn.Module):
             cur = cur.contiguous()
         N = cur.shape[0]
         stream = _abi.stream_ptr(dev)
+        convs = [m for m in self.modules() if isinstance(m, nn.Conv3d)]
+        total = cur.shape[4] + sum(c.out_channels for c in convs) + sum(c.in_channels for c in convs)   # generous bound
+        self._arena = torch.zeros(N * 2 * total, dtype=torch.float64, device=dev)     # one fill instead of one per layer
+        self._arena_pos = 0
         with torch.cuda.device(dev):
-            stats = torch.zeros((N, cur.shape[4], 2), dtype=torch.float64, device=dev)
+            stats = self._take_stats(N, cur.shape[4])
             for n in range(N):
                 _abi.check(L.vtaco_channel_stats_cl(_abi.ptr(cur[n]), cur[n].numel() // cur.shape[4], cur.shape[4],
                                                     _abi.ptr(stats[n]), stream), 'channel_stats_cl')
@@ -234,7 +245,7 @@ class UNet3D(nn.Module):
                 if enc.pooling is not None:
                     _, D, H, W, Cc = cur.shape
                     nxt = torch.empty((N, D // 2, H // 2, W // 2, Cc), dtype=torch.float32, device=dev)
-                    stats = torch.zeros((N, Cc, 2), dtype=torch.float64, device=dev)
+                    stats = self._take_stats(N, Cc)
                     for n in range(N):
                         _abi.check(L.vtaco_maxpool2_cl(_abi.ptr(cur[n]), _abi.ptr(nxt[n]), 1, D, H, W, Cc,
                                                        _abi.ptr(stats[n]), stream), 'maxpool2_cl')
