@@ -108,8 +108,8 @@ int vtaco_relayout_cf(const float* src, float* dst, int B, int C, int64_t S, voi
 #define VTACO_DEC_PACKED_FLOATS(n_blocks) (VTACO_DEC_OFF_BLOCKS + VTACO_DEC_BLOCK_STRIDE * (n_blocks) + VTACO_DEC_TAIL)
 #define VTACO_MAX_TIPS 8
 #define VTACO_MAX_BLOCKS 8   /* n_blocks the shared-memory-resident kernels can hold */
-/* floats of the tcgen05 operand buffer `weights_tc` (layout below) */
-#define VTACO_DEC_TC_FLOATS(n_blocks) (3 * (n_blocks) * 2048 + (2 * (n_blocks) + 1) * 256 + 2048)
+/* floats of the tcgen05 operand buffer `weights_tc` (layouts below; sized for the largest, variant 7's) */
+#define VTACO_DEC_TC_FLOATS(n_blocks) ((3 * (n_blocks) + 1) * 2560 + (2 * (n_blocks) + 1) * 256)
 
 typedef struct vtaco_decoder_args {
   /* ---- queries ---- */
@@ -149,7 +149,9 @@ typedef struct vtaco_decoder_args {
                               atomicMin/atomicMax (caller initialises to INT32_MAX, INT32_MIN) */
   int32_t variant;         /* 0 = scalar-FFMA SIMT kernel; 1 = packed-FFMA2 SIMT kernel; 2 = tcgen05 3xTF32 kernel;
                             * 3 = single TF32 product (debug, ~1e-3); 4 = tcgen05 TF32 main product + BF16 corrections;
-                            * 5 / 6 = 2 / 4 with two threads per query (768-thread CTAs; fastest) */
+                            * 5 / 6 = 2 / 4 with two threads per query (768-thread CTAs, 3 tiles per SM);
+                            * 7 = four tiles per SM (1024-thread CTAs): TF32 hi products + BF16 residual product, biases
+                            *     on the CUDA cores (fastest; needs fewer than 2^31 outputs per call, else 5 is used) */
   /* variants 2-6: the 3*n_blocks hidden matrices (per block: fc_c[i], fc_0, fc_1) as TF32 hi / lo
    * pairs in the UMMA canonical K-major no-swizzle layout, 2048 floats per matrix:
    *   float index of element (n = out, k = in) = (k/4)*128 + (n/8)*32 + (n%8)*4 + (k%4),
@@ -159,8 +161,13 @@ typedef struct vtaco_decoder_args {
    * followed by 2*n_blocks+1 bias K-blocks of 256 floats in the same layout with k in [0,8): row k=0
    * = bias hi, k=1 = bias lo, for the steps bc_0 | b0_i, b1_i + bc_{i+1} (i = 0..n_blocks-1);
    * followed by one more 2048-float matrix block in the matrix layout: fc_p_img.weight[:, 3:]
-   * (the product with a per-query c_img tensor, decoder.py:83-85).  VTACO_DEC_TC_FLOATS floats in
-   * total; vtaco_decoder_pack_tc builds the buffer from `weights`. */
+   * (the product with a per-query c_img tensor, decoder.py:83-85).
+   *   variant 7 (pack mode 2): 2560 floats per matrix — hi block, lo block as above, then 1024 BF16
+   *   values bf16(W) with bf16 index (k/8)*256 + (n/8)*64 + (n%8)*8 + (k%8); the 3*n_blocks matrices are
+   *   followed by the fc_p_img.weight[:, 3:] block (same 2560-float layout) and then by 2*n_blocks+1
+   *   plain fp32 bias vectors [32] for the same steps.
+   * VTACO_DEC_TC_FLOATS floats are reserved for any layout; vtaco_decoder_pack_tc builds the buffer
+   * from `weights` (it writes every float its layout uses). */
   const float* weights_tc;
   /* dense mode, multi-GPU: when n_peers > 0 every logit of the slab is stored to
    * logits_peers[0..n_peers) instead of `logits` — the (nx,nx,nx) grids of all ranks (own one
@@ -250,7 +257,8 @@ int vtaco_tactile_point_map(const float* p, int64_t n, const float* axis, int32_
  * (bias vectors: in_dim = 1).  At most VTACO_PACK_MAX_DESCS descriptors per call; `dst` must be
  * zero-initialised where no descriptor writes (padding, absent fc_c when c_dim = 0).
  * vtaco_decoder_pack_tc derives the tcgen05 operand buffer (`weights_tc`, VTACO_DEC_TC_FLOATS
- * floats, every float written) from the packed decoder buffer; mixed = 1 for variants 4 / 6.
+ * floats) from the packed decoder buffer; mixed = 0 for variants 2 / 3 / 5, 1 for variants 4 / 6,
+ * 2 for variant 7.
  * ------------------------------------------------------------------------- */
 #define VTACO_PACK_MAX_DESCS 64
 typedef struct vtaco_pack_desc {

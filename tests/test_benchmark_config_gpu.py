@@ -30,7 +30,7 @@ def _scene(seed=0):
     return tips, tip_feat, touch
 
 
-@pytest.mark.parametrize('variant', [5, 6, 2])
+@pytest.mark.parametrize('variant', [7, 5, 6, 2])
 def test_dense_256_slabs_vs_oracle(variant):
     """forward_dense(nx=256, R=64, use_img, tips) on x-slabs (first, one through a touching
     fingertip, one through the untouched fingertip, last) == oracle.eval_points on the same rows
@@ -68,7 +68,7 @@ def test_dense_256_slabs_vs_oracle(variant):
     assert torch.isnan(out).sum().item() == (nx - len(covered)) * nx * nx   # slabs write nothing outside their rows
 
 
-@pytest.mark.parametrize('variant', [5, 6])
+@pytest.mark.parametrize('variant', [7, 5, 6])
 def test_dense_equals_flat_256_slab(variant):
     """dense mode == flat mode on 16 rows of the 256^3 lattice (R=64: the separable z-run gather's
     zmin/zmax arithmetic at the benchmarked size), and the same rows with a per-query c_img tensor."""
@@ -253,6 +253,21 @@ def test_pack_kernels_match_torch_packing():
             exp[b0 + 1] = lo
             off = 3 * nb * 2048 + s_ * 256
             assert torch.equal(got[off:off + 256], exp), (mixed, s_)
+    # variant 7 layout (pack mode 2): hi | lo | bf16(W) per matrix, W_img block after the matrices, fp32 bias vectors last
+    got = dec._packed_weights_tc(mixed=2)
+    k32 = torch.arange(32, device='cuda').view(1, 32)
+    idx16_32 = ((k32 // 8) * 256 + (n // 8) * 64 + (n % 8) * 8 + (k32 % 8)).reshape(-1)
+    for m, w in enumerate(mats):
+        w = w.detach().float().contiguous()
+        hi, lo = split(w)
+        exp = torch.zeros(2560, device='cuda')
+        exp[:1024][idx] = hi.reshape(-1)
+        exp[1024:2048][idx] = lo.reshape(-1)
+        exp[2048:].view(torch.bfloat16)[idx16_32] = w.to(torch.bfloat16).reshape(-1)
+        assert torch.equal(got[m * 2560:(m + 1) * 2560].view(torch.int32), exp.view(torch.int32)), m
+    for s_, b in enumerate(steps):
+        off = (3 * nb + 1) * 2560 + s_ * 32
+        assert torch.equal(got[off:off + 32], b.float()), s_
     # encoder buffer
     enc = encoder_dict['pointnet_local_pool'](dim=3, c_dim=32, hidden_dim=32, plane_type='grid', grid_resolution=16).cuda()
     with torch.no_grad():
@@ -275,7 +290,7 @@ def test_pack_kernels_match_torch_packing():
     assert torch.equal(enc._packed_weights(), ebuf)
 
 
-@pytest.mark.parametrize('variant', [2, 5, 6])
+@pytest.mark.parametrize('variant', [2, 5, 6, 7])
 def test_forward_img_tensor_on_tcgen05(variant):
     """forward_img with a per-query c_img tensor (the variant both shipped configs use,
     decoder.py:71-103, VTacO_YCB.yaml:18) stays on the tcgen05 kernel: 10^5 random queries

@@ -44,7 +44,7 @@ def run_case(g, tag, leaky, keys, mode, smode, variant=5, max_queries=None):
     return loss.item(), out
 
 
-@pytest.mark.parametrize('variant', [1, 5])
+@pytest.mark.parametrize('variant', [1, 5, 7])
 @pytest.mark.parametrize('case', GRAD_CASES, ids=[c[0] for c in GRAD_CASES])
 def test_backward_golden(case, variant):
     tag, leaky, keys, mode, smode = case

@@ -23,7 +23,7 @@ def make_decoder(W, leaky=False, contact=None, mode='bilinear', division='true')
     return dec
 
 
-@pytest.mark.parametrize('variant', [0, 1, 2, 4, 5, 6])
+@pytest.mark.parametrize('variant', [0, 1, 2, 4, 5, 6, 7])
 @pytest.mark.parametrize('tag', ['relu', 'leaky'])
 def test_decoder_golden(tag, variant):
     g = load('decoder_%s.npz' % tag)
@@ -54,7 +54,7 @@ def test_decoder_golden(tag, variant):
         assert close(dec.sample_plane_feature(p, feats['yz'], 'yz').cpu().numpy(), g['sample_yz']) < 1e-5
 
 
-@pytest.mark.parametrize('variant', [1, 2, 5])
+@pytest.mark.parametrize('variant', [1, 2, 5, 7])
 @pytest.mark.parametrize('B,N', [(1, 1), (1, 511), (3, 513), (2, 100000), (32, 2048)])
 def test_decoder_vs_oracle_shapes(B, N, variant):
     """ragged / tiny / training-shape batches against the oracle (CPU)."""
@@ -103,7 +103,7 @@ def test_channels_last_features_zero_copy():
     assert torch.equal(a, b)
 
 
-@pytest.mark.parametrize('variant', [1, 2, 5, 6])
+@pytest.mark.parametrize('variant', [1, 2, 5, 6, 7])
 def test_dense_matches_flat_and_golden(variant):
     """dense-lattice mode == flat mode on the same lattice; both == reference eval_points."""
     from vtaco_b200.common import make_3d_grid

@@ -62,7 +62,7 @@ def test_tactile_point_map_matches_oracle(nx):
     assert torch.equal(tactile.c_img_from_ids(m2[None], feat[None].cuda())[0].cpu(), ref) and int((m2 > 0).sum()) > 20
 
 
-@pytest.mark.parametrize('variant', [5, 2])
+@pytest.mark.parametrize('variant', [7, 5, 2])
 def test_decoder_byte_map_equals_dense_c_img(variant):
     """forward_img / forward_dense with the one-byte-per-query map == the reference's dense c_img_all."""
     from oracle import convonet as oc

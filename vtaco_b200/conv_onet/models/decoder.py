@@ -121,9 +121,10 @@ class LocalDecoder(nn.Module):
         self.division = 'cuda'
         # 0 scalar-FFMA SIMT, 1 packed-FFMA2 SIMT (exact fp32; per-query c_img tensors are routed here),
         # 2 tcgen05 3xTF32 (fp32-accurate to ~1.5e-6), 4 tcgen05 TF32 main product + BF16 corrections (3.6e-6),
-        # 5 / 6 = 2 / 4 with two threads per query (8 warps per 128-query tile; fastest, default 5),
-        # 3 single TF32 product (debug, ~1e-3)
-        self.kernel_variant = 5
+        # 5 / 6 = 2 / 4 with two threads per query (8 warps per 128-query tile, 3 tiles per SM),
+        # 7 = four tiles per SM (TF32 hi products + BF16 residual product; fastest, default; calls with
+        #     >= 2^31 outputs run variant 5), 3 single TF32 product (debug, ~1e-3)
+        self.kernel_variant = 7
         self._pack_cache = None
         self._pack_tc_cache = None
         self._cl_cache = {}
@@ -191,14 +192,15 @@ class LocalDecoder(nn.Module):
 
     def _packed_weights_tc(self, mixed=False):
         """The 3*n_blocks hidden matrices (+ fc_p_img.weight[:, 3:]) in the UMMA canonical K-major
-        layout expected by the tcgen05 kernel (include/vtaco_b200.h, `weights_tc`): per matrix 4 KB
-        of TF32 hi followed by 4 KB of either TF32 lo (3xTF32) or — `mixed`, variants 4 / 6 — the
-        BF16 correction operand with K = 64; then the bias K-blocks.  One launch
+        layout expected by the tcgen05 kernels (include/vtaco_b200.h, `weights_tc`): per matrix 4 KB
+        of TF32 hi followed by 4 KB of either TF32 lo (3xTF32; mixed = 0) or — mixed = 1, variants
+        4 / 6 — the BF16 correction operand with K = 64; then the bias K-blocks.  mixed = 2
+        (variant 7): hi, lo and a 2 KB bf16(W) block per matrix, biases as fp32 vectors.  One launch
         (vtaco_decoder_pack_tc) from the packed fp32 buffer."""
         w = self._packed_weights()
         if self._pack_tc_cache is None:
             self._pack_tc_cache = {}
-        mixed = bool(mixed)
+        mixed = int(mixed)
         if mixed in self._pack_tc_cache:
             return self._pack_tc_cache[mixed]
         out = torch.empty(_abi.dec_tc_floats(self.n_blocks), dtype=torch.float32, device=w.device)
@@ -243,7 +245,7 @@ class LocalDecoder(nn.Module):
             st = _abi.lib().vtaco_decoder_forward(C.byref(args), _abi.stream_ptr(device))
         _abi.check(st, 'decoder_forward')
 
-    def _base_args(self, c_plane, B):
+    def _base_args(self, c_plane, B, n_outputs=0):
         self._check_supported()
         a = _abi.DecoderArgs()
         cl = self._features_cl(c_plane) if self.c_dim != 0 else {}
@@ -272,9 +274,11 @@ class LocalDecoder(nn.Module):
         a.n_blocks = self.n_blocks
         a.leaky = int(self.leaky)
         a.variant = int(self.kernel_variant)
+        if a.variant == 7 and n_outputs >= 2 ** 31:
+            a.variant = 5      # the four-tile kernel indexes its outputs with 32 bits
         keep = [cl, w]
-        if a.variant in (2, 3, 4, 5, 6):
-            wtc = self._packed_weights_tc(mixed=(a.variant in (4, 6)))
+        if a.variant in (2, 3, 4, 5, 6, 7):
+            wtc = self._packed_weights_tc(mixed=2 if a.variant == 7 else int(a.variant in (4, 6)))
             a.weights_tc = wtc.data_ptr()
             keep.append(wtc)
         return a, keep
@@ -308,8 +312,8 @@ class LocalDecoder(nn.Module):
         _abi.require_cuda(feat, 'tip features')
         if feat.shape[0] > _abi.MAX_TIPS or feat.shape[1] != 32:
             raise ValueError('tip features must be (F <= %d, 32)' % _abi.MAX_TIPS)
-        if a.variant not in (2, 4, 5, 6):
-            raise NotImplementedError('the per-query tactile id map needs a tcgen05 kernel variant (2, 4, 5, 6)')
+        if a.variant not in (2, 4, 5, 6, 7):
+            raise NotImplementedError('the per-query tactile id map needs a tcgen05 kernel variant (2, 4, 5, 6, 7)')
         ids = ids.contiguous()
         a.tip_map, a.tip_feat, a.n_tips = ids.data_ptr(), feat.data_ptr(), feat.shape[0]
         keep += [ids, feat]
@@ -322,7 +326,7 @@ class LocalDecoder(nn.Module):
         out_c = torch.empty((B, N), dtype=torch.float32, device=p.device) if contact else None
         if N == 0 or B == 0:
             return out, out_c, None
-        a, keep = self._base_args(c_plane, B)
+        a, keep = self._base_args(c_plane, B, B * N)
         a.p = pc.data_ptr()
         a.N = N
         a.use_img = int(use_img)
@@ -493,7 +497,7 @@ class LocalDecoder(nn.Module):
             out = torch.empty((nx, nx, nx), dtype=torch.float32, device=dev)
         if tuple(out.shape) != (nx, nx, nx) or not out.is_contiguous():
             raise ValueError('out must be a contiguous (nx,nx,nx) tensor')
-        a, keep = self._base_args(c_plane, 1)
+        a, keep = self._base_args(c_plane, 1, nx ** 3)
         if axis is None:
             axis = dense_axis(nx, self.padding, dev)
         a.axis = axis.data_ptr()

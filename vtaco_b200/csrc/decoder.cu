@@ -23,6 +23,7 @@
 namespace vtaco {
 
 int launch_decoder_tc(DecParams P, bool dense, const float* wtc, cudaStream_t stream);  // decoder_tc.cu
+int launch_decoder_tc4(DecParams P, bool dense, const float* wtc, cudaStream_t stream);  // decoder_tc4.cu
 
 // acc[s][j] += sum_k W[k][j] * X[k][q_s]  for the thread's two queries.
 // W: shared, K-major [32][32] (broadcast LDS.128); X: shared column base.
@@ -424,7 +425,7 @@ extern "C" int vtaco_decoder_forward(const vtaco_decoder_args* a, void* stream) 
   P.p = a->p; P.axis = a->axis; P.grid = a->grid;
   for (int i = 0; i < 3; ++i) P.plane[i] = a->plane[i];
   P.weights = a->weights; P.c_img = a->c_img; P.tip_feat = a->tip_feat; P.tip_map = a->tip_map;
-  if (a->tip_map && !(a->variant >= 2 && a->variant <= 6)) return VTACO_ERR_UNSUPPORTED;   // byte map: tcgen05 kernels only
+  if (a->tip_map && !(a->variant >= 2 && a->variant <= 7)) return VTACO_ERR_UNSUPPORTED;   // byte map: tcgen05 kernels only
   P.logits = a->logits; P.contact = a->contact; P.minmax_key = a->minmax_key;
   P.B = a->B; P.Rg = a->reso_grid; P.Rp = a->reso_plane;
   P.n_blocks = a->n_blocks; P.leaky = a->leaky ? 1 : 0; P.use_img = a->use_img ? 1 : 0;
@@ -483,6 +484,7 @@ extern "C" int vtaco_decoder_forward(const vtaco_decoder_args* a, void* stream) 
   }
   P.tc_products = (a->variant == 3) ? 1 : (a->variant == 4 || a->variant == 6) ? 2 : 3;
   P.tc_split = (a->variant == 5 || a->variant == 6) ? 2 : 1;
+  if (a->variant == 7) return launch_decoder_tc4(P, dense, a->weights_tc, st);
   if (a->variant >= 2 && a->variant <= 6) return launch_decoder_tc(P, dense, a->weights_tc, st);
   const bool f2 = (a->variant == 1);
   if (dense) return f2 ? launch_decoder<true, true>(P, smem_bytes, st) : launch_decoder<true, false>(P, smem_bytes, st);

@@ -52,7 +52,11 @@ __global__ void __launch_bounds__(256) pack_tc_kernel(const __grid_constant__ Tc
       const float hi = tf32_rn(w);
       const int idx = (k >> 2) * 128 + (n >> 3) * 32 + (n & 7) * 4 + (k & 3);
       out[idx] = hi;
-      if (Pn.mixed) {   // K = 64 BF16 correction operand: rows k < 32 bf16(W), rows k >= 32 bf16(W - hi)
+      if (Pn.mixed == 2) {   // variant 7: TF32 hi | TF32 lo | bf16(W) (K = 32), 2560 floats per matrix
+        out[1024 + idx] = tf32_trunc(w - hi);
+        __nv_bfloat16* o16 = reinterpret_cast<__nv_bfloat16*>(out + 2048);
+        o16[(k >> 3) * 256 + (n >> 3) * 64 + (n & 7) * 8 + (k & 7)] = __float2bfloat16_rn(w);
+      } else if (Pn.mixed) {   // K = 64 BF16 correction operand: rows k < 32 bf16(W), rows k >= 32 bf16(W - hi)
         __nv_bfloat16* o16 = reinterpret_cast<__nv_bfloat16*>(out + 1024);
         const int k1 = k + 32;
         o16[(k >> 3) * 256 + (n >> 3) * 64 + (n & 7) * 8 + (k & 7)] = __float2bfloat16_rn(w);
@@ -63,6 +67,15 @@ __global__ void __launch_bounds__(256) pack_tc_kernel(const __grid_constant__ Tc
     }
   } else {
     const int s = b - Pn.n_mats;
+    if (Pn.mixed == 2) {   // variant 7 adds the biases on the CUDA cores: plain fp32 vectors
+      if (threadIdx.x < 32) {
+        float bsum = 0.f;
+        if (Pn.bias_src0[s] >= 0) bsum = __ldg(packed + Pn.bias_src0[s] + threadIdx.x);
+        if (Pn.bias_src1[s] >= 0) bsum = bsum + __ldg(packed + Pn.bias_src1[s] + threadIdx.x);
+        dst[Pn.bias_dst + s * 32 + threadIdx.x] = bsum;
+      }
+      return;
+    }
     float* out = dst + Pn.bias_dst + s * 256;
     for (int i = threadIdx.x; i < 256; i += blockDim.x) {
       // layout (k/4)*128 + (n/8)*32 + (n%8)*4 + (k%4) with k in [0,8): i -> (k, n)
@@ -107,22 +120,25 @@ extern "C" int64_t vtaco_decoder_tc_floats(int32_t n_blocks) {
 
 extern "C" int vtaco_decoder_pack_tc(const float* packed, int32_t n_blocks, int32_t mixed, float* dst, void* stream) {
   if (!packed || !dst || n_blocks < 0 || n_blocks > VTACO_MAX_BLOCKS) return VTACO_ERR_INVALID_ARG;
+  if (mixed < 0 || mixed > 2) return VTACO_ERR_INVALID_ARG;
   TcPackPlan Pn = {};
-  Pn.mixed = mixed ? 1 : 0;
+  Pn.mixed = mixed;
   const int nb = n_blocks;
+  const int mat_floats = (mixed == 2) ? 2560 : 2048;
   for (int i = 0; i < nb; ++i) {
     const int o = VTACO_DEC_OFF_BLOCKS + i * VTACO_DEC_BLOCK_STRIDE;
     const int srcs[3] = {o, o + 1056, o + 2112};   // fc_c[i], fc_0, fc_1
     for (int j = 0; j < 3; ++j) {
       Pn.mat_src[3 * i + j] = srcs[j];
-      Pn.mat_dst[3 * i + j] = (3 * i + j) * 2048;
+      Pn.mat_dst[3 * i + j] = (3 * i + j) * mat_floats;
     }
   }
   Pn.mat_src[3 * nb] = VTACO_DEC_OFF_WIMG;                       // fc_p_img.weight[:, 3:]
-  Pn.mat_dst[3 * nb] = 3 * nb * 2048 + (2 * nb + 1) * 256;       // after the bias blocks
+  // layouts 0 / 1: the W_img block follows the bias K-blocks; layout 2: it follows the matrices, the bias vectors come last
+  Pn.mat_dst[3 * nb] = (mixed == 2) ? 3 * nb * mat_floats : 3 * nb * 2048 + (2 * nb + 1) * 256;
   Pn.n_mats = 3 * nb + 1;
   // bias steps: bc_0 | b0_i, b1_i + bc_{i+1}
-  Pn.bias_dst = 3 * nb * 2048;
+  Pn.bias_dst = (mixed == 2) ? (3 * nb + 1) * mat_floats : 3 * nb * 2048;
   Pn.n_bias = 2 * nb + 1;
   Pn.bias_src0[0] = nb > 0 ? VTACO_DEC_OFF_BLOCKS + 1024 : -1;
   Pn.bias_src1[0] = -1;
