@@ -109,7 +109,7 @@ int vtaco_relayout_cf(const float* src, float* dst, int B, int C, int64_t S, voi
 #define VTACO_MAX_TIPS 8
 #define VTACO_MAX_BLOCKS 8   /* n_blocks the shared-memory-resident kernels can hold */
 /* floats of the tcgen05 operand buffer `weights_tc` (layouts below; sized for the largest, variant 7's) */
-#define VTACO_DEC_TC_FLOATS(n_blocks) ((3 * (n_blocks) + 1) * 2560 + (2 * (n_blocks) + 1) * 256)
+#define VTACO_DEC_TC_FLOATS(n_blocks) ((3 * (n_blocks) + 1) * 2560 + (2 * (n_blocks) + 1) * 256 + 1024)
 
 typedef struct vtaco_decoder_args {
   /* ---- queries ---- */
@@ -165,7 +165,10 @@ typedef struct vtaco_decoder_args {
    *   variant 7 (pack mode 2): 2560 floats per matrix — hi block, lo block as above, then 1024 BF16
    *   values bf16(W) with bf16 index (k/8)*256 + (n/8)*64 + (n%8)*8 + (k%8); the 3*n_blocks matrices are
    *   followed by the fc_p_img.weight[:, 3:] block (same 2560-float layout) and then by 2*n_blocks+1
-   *   plain fp32 bias vectors [32] for the same steps.
+   *   plain fp32 bias vectors [32] for the same steps, and by four K = 8 blocks of 256 floats (K-block layout
+   *   above) that put the 3-wide input layer on the tensor core as well: for fc_p, then for
+   *   fc_p_img[:, :3], B1 = rows (W_hi[:,0..2], (b + bc_0)_hi, W_hi[:,0..2], 0) and B2 = rows
+   *   (W_lo[:,0..2], (b + bc_0)_lo, 0, 0, 0, 0), multiplied by A = (px, py, pz, 1, px_lo, py_lo, pz_lo, 0).
    * VTACO_DEC_TC_FLOATS floats are reserved for any layout; vtaco_decoder_pack_tc builds the buffer
    * from `weights` (it writes every float its layout uses). */
   const float* weights_tc;

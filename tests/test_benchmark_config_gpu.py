@@ -268,6 +268,21 @@ def test_pack_kernels_match_torch_packing():
     for s_, b in enumerate(steps):
         off = (3 * nb + 1) * 2560 + s_ * 32
         assert torch.equal(got[off:off + 32], b.float()), s_
+    # ... and the 3-wide input layer as K = 8 blocks: A = (px, py, pz, 1, px_lo, py_lo, pz_lo, 0)
+    kb = torch.arange(8, device='cuda').view(1, 8)
+    idx8 = ((kb // 4) * 128 + (n // 8) * 32 + (n % 8) * 4 + (kb % 4))          # (n, k) -> float index
+    pw0 = (3 * nb + 1) * 2560 + (2 * nb + 1) * 32
+    for q, lin in enumerate((dec.fc_p, dec.fc_p_img)):
+        wb = torch.cat([lin.weight.detach()[:, :3].float(), (lin.bias.detach() + dec.fc_c[0].bias.detach()).view(32, 1)], 1)
+        hi, lo = split(wb.contiguous())
+        b1 = torch.zeros(256, device='cuda')
+        b2 = torch.zeros(256, device='cuda')
+        b1[idx8[:, 0:4].reshape(-1)] = hi.reshape(-1)
+        b1[idx8[:, 4:7].reshape(-1)] = hi[:, :3].reshape(-1)
+        b2[idx8[:, 0:4].reshape(-1)] = lo.reshape(-1)
+        off = pw0 + q * 512
+        assert torch.equal(got[off:off + 256], b1), q
+        assert torch.equal(got[off + 256:off + 512], b2), q
     # encoder buffer
     enc = encoder_dict['pointnet_local_pool'](dim=3, c_dim=32, hidden_dim=32, plane_type='grid', grid_resolution=16).cuda()
     with torch.no_grad():

@@ -103,7 +103,7 @@ PACK_MAX_DESCS = 64
 
 def dec_tc_floats(n_blocks):
     """VTACO_DEC_TC_FLOATS: floats reserved for any tcgen05 operand layout (variant 7's is the largest)."""
-    return (3 * n_blocks + 1) * 2560 + (2 * n_blocks + 1) * 256
+    return (3 * n_blocks + 1) * 2560 + (2 * n_blocks + 1) * 256 + 1024
 
 
 def pack_linear(entries, dst):

@@ -29,12 +29,13 @@ constexpr int kT4StageRows = 24;          // staged z-rows per warp (separable g
 constexpr int kT4MatBytes = 10240;        // W_hi 4 KB | W_lo 4 KB | bf16(W) 2 KB
 constexpr int kT4MaxAxis = 2048;
 
-struct Tc4Smem { int w, bias, small, tips, stage, head, axis, mm, bars, tmem_ptr, total; };
+struct Tc4Smem { int w, bias, pw, small, tips, stage, head, axis, mm, bars, tmem_ptr, total; };
 __host__ __device__ inline Tc4Smem tc4_smem_layout(int n_blocks) {
   Tc4Smem s;
   s.w = 0;                                                   // 3*nb matrices, then fc_p_img.weight[:, 3:]
   s.bias = s.w + (3 * n_blocks + 1) * kT4MatBytes;           // (2*nb+1) fp32 bias vectors
-  s.small = s.bias + (2 * n_blocks + 1) * 128;
+  s.pw = (s.bias + (2 * n_blocks + 1) * 128 + 127) / 128 * 128;   // fc_p | fc_p_img[:, :3] as two K = 8 operand blocks (1 KB each)
+  s.small = s.pw + 2048;
   s.tips = s.small + (128 + 68) * 4;
   s.stage = s.tips + VTACO_MAX_TIPS * 32 * 4;
   s.stage = (s.stage + 15) / 16 * 16;
@@ -51,37 +52,33 @@ __host__ __device__ inline Tc4Smem tc4_smem_layout(int n_blocks) {
 // XOR-swizzled with the row pair so that lanes reading rows r and r+2 hit different banks
 __device__ __forceinline__ int stage_idx(int r, int j) { return r * 16 + ((j ^ (r >> 1)) & 3) * 4; }
 
-// channels [16*hv, 16*hv+16) of x -> hi (tf32 container) at tblk + 16*hv, lo (bf16 pairs) at tblk + 32 + 8*hv;
-// four channels at a time, so that few registers are live next to the residual stream
+// Eight channels [16*hv + 8*h, +8) of x (already activated) -> operand columns of the block at `tblk`:
+// hi (tf32 container: x with the 13 low mantissa bits cleared) at tblk + 16*hv + 8*h, lo = bf16(x - hi),
+// two per column, at tblk + 32 + 8*hv + 4*h.  x - hi is formed as fma(hi, -1, x) on register pairs
+// (FFMA2: one instruction per two channels).
+__device__ __forceinline__ void split_store8(uint32_t tblk, int hv, int h, const float (&x)[8]) {
+  uint32_t hi[8], lo[4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) hi[j] = trunc_tf32(x[j]);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const float2 d = __ffma2_rn(make_float2(__uint_as_float(hi[2 * c]), __uint_as_float(hi[2 * c + 1])),
+                                make_float2(-1.0f, -1.0f), make_float2(x[2 * c], x[2 * c + 1]));
+    lo[c] = pack_bf16(d.x, d.y);
+  }
+  tmem_st8(tblk + 16 * hv + 8 * h, hi);
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%4], {%0,%1,%2,%3};" ::"r"(lo[0]), "r"(lo[1]), "r"(lo[2]),
+               "r"(lo[3]), "r"(tblk + 32 + 8 * hv + 4 * h)
+               : "memory");
+}
 __device__ __forceinline__ void split_store_t4(uint32_t tblk, int hv, const float (&x)[16]) {
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    uint32_t hi[4], lo[2];
+  for (int h = 0; h < 2; ++h) {
+    float y[8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) hi[j] = trunc_tf32(x[4 * q + j]);
-#pragma unroll
-    for (int c = 0; c < 2; ++c)
-      lo[c] = pack_bf16(x[4 * q + 2 * c] - __uint_as_float(hi[2 * c]), x[4 * q + 2 * c + 1] - __uint_as_float(hi[2 * c + 1]));
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%4], {%0,%1,%2,%3};" ::"r"(hi[0]), "r"(hi[1]), "r"(hi[2]),
-                 "r"(hi[3]), "r"(tblk + 16 * hv + 4 * q)
-                 : "memory");
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%2], {%0,%1};" ::"r"(lo[0]), "r"(lo[1]),
-                 "r"(tblk + 32 + 8 * hv + 2 * q)
-                 : "memory");
+    for (int j = 0; j < 8; ++j) y[j] = x[8 * h + j];
+    split_store8(tblk, hv, h, y);
   }
-}
-
-// four channels [16*hv + 4*q, +4) of relu(v + bias) -> operand columns (as split_store_t4)
-__device__ __forceinline__ void relu_split_store4(uint32_t tblk, int hv, int q, float v0, float v1, float v2, float v3) {
-  v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f);
-  const uint32_t h0 = trunc_tf32(v0), h1 = trunc_tf32(v1), h2 = trunc_tf32(v2), h3 = trunc_tf32(v3);
-  const uint32_t l0 = pack_bf16(v0 - __uint_as_float(h0), v1 - __uint_as_float(h1));
-  const uint32_t l1 = pack_bf16(v2 - __uint_as_float(h2), v3 - __uint_as_float(h3));
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%4], {%0,%1,%2,%3};" ::"r"(h0), "r"(h1), "r"(h2), "r"(h3),
-               "r"(tblk + 16 * hv + 4 * q)
-               : "memory");
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%2], {%0,%1};" ::"r"(l0), "r"(l1), "r"(tblk + 32 + 8 * hv + 2 * q)
-               : "memory");
 }
 
 // Shared-memory descriptor of a B block `units` 16-byte units after the block described by `lo`:
@@ -123,6 +120,7 @@ __global__ void __launch_bounds__(kT4Threads, 1) decoder_tc4_kernel(const __grid
   float* sWtc = reinterpret_cast<float*>(tsm + L.w);
   float* sBias = reinterpret_cast<float*>(tsm + L.bias);
   float* sSmall = reinterpret_cast<float*>(tsm + L.small);
+  float* sPw = reinterpret_cast<float*>(tsm + L.pw);
   float* sTip = reinterpret_cast<float*>(tsm + L.tips);
   float* sStage = reinterpret_cast<float*>(tsm + L.stage);
   float* sHead = reinterpret_cast<float*>(tsm + L.head);
@@ -144,6 +142,8 @@ __global__ void __launch_bounds__(kT4Threads, 1) decoder_tc4_kernel(const __grid
   const int wtc_floats = (3 * nb + 1) * (kT4MatBytes / 4) + (2 * nb + 1) * 32;
   for (int i = tid; i < wtc_floats / 4; i += kT4Threads)
     reinterpret_cast<float4*>(sWtc)[i] = __ldg(reinterpret_cast<const float4*>(wtc) + i);
+  // the fc_p operand blocks follow the bias vectors in wtc: [fc_p B1 | B2 | fc_p_img B1 | B2], 256 floats each
+  for (int i = tid; i < 512; i += kT4Threads) sPw[i] = __ldg(wtc + wtc_floats + (P.use_img ? 512 : 0) + i);
   for (int i = tid; i < 128; i += kT4Threads) {
     float v = P.weights[(P.use_img ? VTACO_DEC_OFF_WPI : VTACO_DEC_OFF_WP) + i];
     // bc_0 joins the fc_p bias: net = (W p + (bp + bc_0)) + Wc_0 c
@@ -186,6 +186,7 @@ __global__ void __launch_bounds__(kT4Threads, 1) decoder_tc4_kernel(const __grid
   // descriptor low word of matrix 0 (start address >> 4 | K-chunk stride 512 B); matrix m is m * 640 units further
   const uint32_t wlo0 = ((smem_u32(sWtc) >> 4) & 0x3fffu) | ((512u >> 4) << 16);
   constexpr uint32_t kMatUnits = kT4MatBytes / 16;
+  const uint32_t pwlo = ((smem_u32(sPw) >> 4) & 0x3fffu) | ((512u >> 4) << 16);
   const int gsync_id = g + 1;
   auto group_sync = [&]() { asm volatile("bar.sync %0, 256;" ::"r"(gsync_id) : "memory"); };
   float* stage = sStage + warp * kT4StageRows * 16;
@@ -227,7 +228,7 @@ __global__ void __launch_bounds__(kT4Threads, 1) decoder_tc4_kernel(const __grid
     T4_STAMP(13);  // tile start: coordinates loaded
 
     // ---------------- gather: this thread's 16 channels of its query (+ of its c_img row): operands of step 0 ----------------
-    if (P.has_c || cimg) {
+    {
       if (P.has_c) {
         float cv[16];
         bool sep_done = false;
@@ -334,18 +335,35 @@ __global__ void __launch_bounds__(kT4Threads, 1) decoder_tc4_kernel(const __grid
           xv[4 * j] = v.x; xv[4 * j + 1] = v.y; xv[4 * j + 2] = v.z; xv[4 * j + 3] = v.w;
         }
         split_store_t4(tX, hv, xv);
+      } else if (hv == 0) {
+        // fc_p on the tensor core as well: A = (px, py, pz, 1, px_lo, py_lo, pz_lo, 0) in the first 8 X columns
+        // (the tensor core reads the top 19 bits of px, i.e. px_hi), B1 = rows (Wp_hi x3, b_hi, Wp_hi x3, 0),
+        // B2 = rows (Wp_lo x3, b_lo, 0...) — 3xTF32 for the 3-wide layer with two K = 8 MMAs
+        uint32_t a[8];
+        a[0] = __float_as_uint(px); a[1] = __float_as_uint(py); a[2] = __float_as_uint(pz);
+        a[3] = __float_as_uint(1.0f);
+        a[4] = __float_as_uint(px - __uint_as_float(trunc_tf32(px)));
+        a[5] = __float_as_uint(py - __uint_as_float(trunc_tf32(py)));
+        a[6] = __float_as_uint(pz - __uint_as_float(trunc_tf32(pz)));
+        a[7] = 0u;
+        tmem_st8(tX, a);
       }
       tc_wait_st();
       tc_fence_before();
       group_sync();
-      if (wq == (step & 7) && elect_one()) {     // step 0: D = C*Wc_0 [+ c_img*W_img]   (bc_0 sits in the fc_p bias)
+      if (wq == (step & 7) && elect_one()) {     // step 0: D = C*Wc_0 + (c_img*W_img | fc_p(p) + bc_0)
         tc_fence_after();
         uint32_t acc = 0;
         if (P.has_c) {
           issue_product_t4(mD, mC, wlo0, 0);
           acc = 1;
         }
-        if (cimg) issue_product_t4(mD, mX, wlo0 + (uint32_t)(3 * nb) * kMatUnits, acc);
+        if (cimg) {
+          issue_product_t4(mD, mX, wlo0 + (uint32_t)(3 * nb) * kMatUnits, acc);
+        } else {
+          tc_mma_ts(mD, mX, bdesc_at(pwlo, 64), acc);
+          tc_mma_ts(mD, mX, bdesc_at(pwlo, 0), 1);
+        }
         tc_commit(bar);
       }
       ++step;
@@ -356,7 +374,16 @@ __global__ void __launch_bounds__(kT4Threads, 1) decoder_tc4_kernel(const __grid
     int tipf = -1;
     if (P.use_img && P.n_tips > 0) tipf = tip_of_query(P, max(oidx, 0), px, py, pz);
     float net[16];
-    {
+    {  // net = fc_c[0](c) + (W_img c_img | fc_p(p) + bc_0)
+      uint32_t r[16];
+      mbar_wait(bar, (uint32_t)(step - 1) & 1u);
+      tc_fence_after();
+      tmem_ld16(tD + ch0, r);
+      tc_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) net[j] = __uint_as_float(r[j]);
+    }
+    if (cimg) {   // c_img occupies the X columns: the 3-wide layer runs on the CUDA cores
       const float4* w0 = reinterpret_cast<const float4*>(sSmall + ch0);
       const float4* w1 = reinterpret_cast<const float4*>(sSmall + 32 + ch0);
       const float4* w2 = reinterpret_cast<const float4*>(sSmall + 64 + ch0);
@@ -364,31 +391,28 @@ __global__ void __launch_bounds__(kT4Threads, 1) decoder_tc4_kernel(const __grid
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float4 a0 = w0[j], a1 = w1[j], a2 = w2[j], bb = bp[j];
-        net[4 * j + 0] = fmaf(a2.x, pz, fmaf(a1.x, py, fmaf(a0.x, px, bb.x)));
-        net[4 * j + 1] = fmaf(a2.y, pz, fmaf(a1.y, py, fmaf(a0.y, px, bb.y)));
-        net[4 * j + 2] = fmaf(a2.z, pz, fmaf(a1.z, py, fmaf(a0.z, px, bb.z)));
-        net[4 * j + 3] = fmaf(a2.w, pz, fmaf(a1.w, py, fmaf(a0.w, px, bb.w)));
+        net[4 * j + 0] += fmaf(a2.x, pz, fmaf(a1.x, py, fmaf(a0.x, px, bb.x)));
+        net[4 * j + 1] += fmaf(a2.y, pz, fmaf(a1.y, py, fmaf(a0.y, px, bb.y)));
+        net[4 * j + 2] += fmaf(a2.z, pz, fmaf(a1.z, py, fmaf(a0.z, px, bb.z)));
+        net[4 * j + 3] += fmaf(a2.w, pz, fmaf(a1.w, py, fmaf(a0.w, px, bb.w)));
       }
     }
     if (tipf >= 0) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) net[j] += sTip[tipf * 32 + ch0 + j];
     }
-    uint32_t r[16];
-    if (P.has_c || cimg) {  // net += fc_c[0](c) [+ W_img c_img]
-      mbar_wait(bar, (uint32_t)(step - 1) & 1u);
-      tc_fence_after();
-      tmem_ld16(tD + ch0, r);
-      tc_wait_ld();
-#pragma unroll
-      for (int j = 0; j < 16; ++j) net[j] += __uint_as_float(r[j]);
-    }
 
     // ---------------- residual blocks: 2 accumulation steps each ----------------
+    uint32_t r[16];
     for (int i = 0; i < nb; ++i) {
       T4_STAMP(1);   // ALU phase starts (accumulator already read)
 #pragma unroll
-      for (int q = 0; q < 4; ++q) relu_split_store4(tX, hv, q, net[4 * q], net[4 * q + 1], net[4 * q + 2], net[4 * q + 3]);
+      for (int h = 0; h < 2; ++h) {
+        float y[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) y[j] = fmaxf(net[8 * h + j], 0.f);
+        split_store8(tX, hv, h, y);
+      }
       T4_STAMP(2);   // operands computed, tcgen05.st issued
       tc_wait_st();
       tc_fence_before();
@@ -411,10 +435,19 @@ __global__ void __launch_bounds__(kT4Threads, 1) decoder_tc4_kernel(const __grid
       tc_wait_ld();
       T4_STAMP(7);   // accumulator in registers
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {               // h = relu(D + b0_i)
-        const float4 bb = b0[j];
-        relu_split_store4(tX, hv, j, __uint_as_float(r[4 * j + 0]) + bb.x, __uint_as_float(r[4 * j + 1]) + bb.y,
-                          __uint_as_float(r[4 * j + 2]) + bb.z, __uint_as_float(r[4 * j + 3]) + bb.w);
+      for (int h = 0; h < 2; ++h) {               // h = relu(D + b0_i), packed adds
+        float y[8];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const float4 bb = b0[2 * h + j];
+          const float2 s0 = __fadd2_rn(make_float2(__uint_as_float(r[8 * h + 4 * j]), __uint_as_float(r[8 * h + 4 * j + 1])),
+                                       make_float2(bb.x, bb.y));
+          const float2 s1 = __fadd2_rn(make_float2(__uint_as_float(r[8 * h + 4 * j + 2]), __uint_as_float(r[8 * h + 4 * j + 3])),
+                                       make_float2(bb.z, bb.w));
+          y[4 * j] = fmaxf(s0.x, 0.f); y[4 * j + 1] = fmaxf(s0.y, 0.f);
+          y[4 * j + 2] = fmaxf(s1.x, 0.f); y[4 * j + 3] = fmaxf(s1.y, 0.f);
+        }
+        split_store8(tX, hv, h, y);
       }
       tc_wait_st();
       tc_fence_before();
@@ -432,12 +465,13 @@ __global__ void __launch_bounds__(kT4Threads, 1) decoder_tc4_kernel(const __grid
       tmem_ld16(tD + ch0, r);
       tc_wait_ld();
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {               // net += D + (b1_i + bc_{i+1})
+      for (int j = 0; j < 4; ++j) {               // net += D + (b1_i + bc_{i+1}), packed adds
         const float4 bb = b1[j];
-        net[4 * j + 0] += __uint_as_float(r[4 * j + 0]) + bb.x;
-        net[4 * j + 1] += __uint_as_float(r[4 * j + 1]) + bb.y;
-        net[4 * j + 2] += __uint_as_float(r[4 * j + 2]) + bb.z;
-        net[4 * j + 3] += __uint_as_float(r[4 * j + 3]) + bb.w;
+        const float2 s0 = __fadd2_rn(make_float2(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1])), make_float2(bb.x, bb.y));
+        const float2 s1 = __fadd2_rn(make_float2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), make_float2(bb.z, bb.w));
+        const float2 n0 = __fadd2_rn(make_float2(net[4 * j], net[4 * j + 1]), s0);
+        const float2 n1 = __fadd2_rn(make_float2(net[4 * j + 2], net[4 * j + 3]), s1);
+        net[4 * j] = n0.x; net[4 * j + 1] = n0.y; net[4 * j + 2] = n1.x; net[4 * j + 3] = n1.y;
       }
     }
 

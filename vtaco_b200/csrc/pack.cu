@@ -38,6 +38,7 @@ struct TcPackPlan {
   int bias_src0[2 * VTACO_MAX_BLOCKS + 1];  // -1 = zero
   int bias_src1[2 * VTACO_MAX_BLOCKS + 1];
   int bias_dst;
+  int pw_dst;
 };
 
 __global__ void __launch_bounds__(256) pack_tc_kernel(const __grid_constant__ TcPackPlan Pn,
@@ -65,6 +66,28 @@ __global__ void __launch_bounds__(256) pack_tc_kernel(const __grid_constant__ Tc
         out[1024 + idx] = tf32_trunc(w - hi);
       }
     }
+  } else if (b >= Pn.n_mats + Pn.n_bias) {
+    // variant 7: fc_p / fc_p_img[:, :3] (+ their bias + bc_0) as K = 8 operand blocks for the 3xTF32 product
+    // with A = (px, py, pz, 1, px_lo, py_lo, pz_lo, 0):  B1 rows (W_hi x3, b_hi, W_hi x3, 0), B2 rows (W_lo x3, b_lo, 0 x4)
+    const int q = b - Pn.n_mats - Pn.n_bias;          // 0: fc_p B1, 1: fc_p B2, 2: fc_p_img B1, 3: fc_p_img B2
+    const int wsrc = (q >> 1) ? VTACO_DEC_OFF_WPI : VTACO_DEC_OFF_WP;
+    const int bsrc = (q >> 1) ? VTACO_DEC_OFF_BPI : VTACO_DEC_OFF_BP;
+    float* out = dst + Pn.pw_dst + q * 256;
+    const int i = threadIdx.x;                        // 256 threads == 256 floats
+    const int k = (i >> 7) * 4 + (i & 3), n = ((i >> 5) & 3) * 8 + ((i >> 2) & 7);
+    const int kk = k & 3;
+    float v;
+    if (kk < 3) {
+      v = __ldg(packed + wsrc + kk * 32 + n);
+    } else {
+      v = __ldg(packed + bsrc + n);
+      if (Pn.bias_src0[0] >= 0) v = v + __ldg(packed + Pn.bias_src0[0] + n);   // + bc_0
+    }
+    const float hi = tf32_rn(v);
+    float o;
+    if ((q & 1) == 0) o = (k == 7) ? 0.f : hi;                          // B1
+    else o = (k < 4) ? tf32_trunc(v - hi) : 0.f;                       // B2
+    out[i] = o;
   } else {
     const int s = b - Pn.n_mats;
     if (Pn.mixed == 2) {   // variant 7 adds the biases on the CUDA cores: plain fp32 vectors
@@ -149,7 +172,8 @@ extern "C" int vtaco_decoder_pack_tc(const float* packed, int32_t n_blocks, int3
     Pn.bias_src0[2 * i + 2] = o + 3136;
     Pn.bias_src1[2 * i + 2] = (i + 1 < nb) ? o + VTACO_DEC_BLOCK_STRIDE + 1024 : -1;
   }
-  pack_tc_kernel<<<Pn.n_mats + Pn.n_bias, 256, 0, (cudaStream_t)stream>>>(Pn, packed, dst);
+  Pn.pw_dst = Pn.bias_dst + (2 * nb + 1) * 32;     // layout 2 only
+  pack_tc_kernel<<<Pn.n_mats + Pn.n_bias + (mixed == 2 ? 4 : 0), 256, 0, (cudaStream_t)stream>>>(Pn, packed, dst);
   VTACO_LAUNCH_CHECK();
   return VTACO_OK;
 }
