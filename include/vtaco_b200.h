@@ -162,7 +162,8 @@ typedef struct vtaco_decoder_args {
    * = bias hi, k=1 = bias lo, for the steps bc_0 | b0_i, b1_i + bc_{i+1} (i = 0..n_blocks-1);
    * followed by one more 2048-float matrix block in the matrix layout: fc_p_img.weight[:, 3:]
    * (the product with a per-query c_img tensor, decoder.py:83-85).
-   *   variant 7 (pack mode 2): 2560 floats per matrix — hi block, lo block as above, then 1024 BF16
+   *   variant 7 (pack mode 2): fc_0 / fc_1 are stored times 0.5 (the kernel feeds them 2*relu(x) = x + |x|);
+   *   2560 floats per matrix — hi block, lo block as above, then 1024 BF16
    *   values bf16(W) with bf16 index (k/8)*256 + (n/8)*64 + (n%8)*8 + (k%8); the 3*n_blocks matrices are
    *   followed by the fc_p_img.weight[:, 3:] block (same 2560-float layout) and then by 2*n_blocks+1
    *   plain fp32 bias vectors [32] for the same steps, and by four K = 8 blocks of 256 floats (K-block layout

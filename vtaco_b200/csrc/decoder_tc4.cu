@@ -52,6 +52,11 @@ __host__ __device__ inline Tc4Smem tc4_smem_layout(int n_blocks) {
 // XOR-swizzled with the row pair so that lanes reading rows r and r+2 hit different banks
 __device__ __forceinline__ int stage_idx(int r, int j) { return r * 16 + ((j ^ (r >> 1)) & 3) * 4; }
 
+// 2 * relu(x) = x + |x| (exact): one FADD on the FMA pipe instead of an FMNMX on the ALU pipe, which the
+// truncation (LOP3) and the BF16 pack (F2FP) already load (ncu: ALU pipe 47 %, FMA pipe 16 %).  The factor 2
+// is undone by the weights: fc_0 / fc_1 are packed times 0.5 (a power of two: every product is unchanged).
+__device__ __forceinline__ float relu2(float x) { return x + fabsf(x); }
+
 // Eight channels [16*hv + 8*h, +8) of x (already activated) -> operand columns of the block at `tblk`:
 // hi (tf32 container: x with the 13 low mantissa bits cleared) at tblk + 16*hv + 8*h, lo = bf16(x - hi),
 // two per column, at tblk + 32 + 8*hv + 4*h.  x - hi is formed as fma(hi, -1, x) on register pairs
@@ -198,16 +203,27 @@ __global__ void __launch_bounds__(kT4Threads, 1) decoder_tc4_kernel(const __grid
   const bool sep_cfg = DENSE && P.has_c && P.grid && !P.nearest && !(P.plane[0] || P.plane[1] || P.plane[2]);
 
   const int n_tiles = (int)P.n_tiles;   // < 2^31 (checked at launch)
+  // dense mode: brick coordinates of the group's tile, advanced by the (decomposed) grid stride with carries
+  // instead of three integer divisions per tile
+  int bz = 0, by = 0, bx = 0, bq = 0, sz = 0, sy = 0, sx = 0, sq = 0;
+  if (DENSE) {
+    unsigned t = (unsigned)(blockIdx.x * kT4Groups + g);
+    bz = (int)(t % (unsigned)P.t_nbz); t /= (unsigned)P.t_nbz;
+    by = (int)(t % (unsigned)P.t_nby); t /= (unsigned)P.t_nby;
+    bx = (int)(t % (unsigned)P.t_nbx);
+    bq = (int)(t / (unsigned)P.t_nbx);
+    unsigned u = (unsigned)(gridDim.x * kT4Groups);
+    sz = (int)(u % (unsigned)P.t_nbz); u /= (unsigned)P.t_nbz;
+    sy = (int)(u % (unsigned)P.t_nby); u /= (unsigned)P.t_nby;
+    sx = (int)(u % (unsigned)P.t_nbx);
+    sq = (int)(u / (unsigned)P.t_nbx);
+  }
   for (int tile = blockIdx.x * kT4Groups + g; tile < n_tiles; tile += gridDim.x * kT4Groups) {
     float px, py, pz;
     int oidx;      // output index, < 2^31 (checked at launch); -1 = padding query
     int qb;
     if (DENSE) {
-      unsigned t = (unsigned)tile;
-      const int bz = (int)(t % (unsigned)P.t_nbz); t /= (unsigned)P.t_nbz;
-      const int by = (int)(t % (unsigned)P.t_nby); t /= (unsigned)P.t_nby;
-      const int bx = (int)(t % (unsigned)P.t_nbx);
-      qb = (int)(t / (unsigned)P.t_nbx);
+      qb = bq;
       const int ix = P.x0 + bx * 2 + (tq >> 6), iy = by * 2 + ((tq >> 5) & 1), iz = bz * 32 + (tq & 31);
       const bool valid = (ix < P.t_xend) && (iy < nx) && (iz < nx);
       const int cx = min(ix, nx - 1), cy = min(iy, nx - 1), cz = min(iz, nx - 1);
@@ -215,6 +231,10 @@ __global__ void __launch_bounds__(kT4Threads, 1) decoder_tc4_kernel(const __grid
       py = axis_sm ? sAxis[cy] : __ldg(P.axis + cy);
       pz = axis_sm ? sAxis[cz] : __ldg(P.axis + cz);
       oidx = valid ? ((qb * nx + ix) * nx + iy) * nx + iz : -1;
+      bz += sz; if (bz >= P.t_nbz) { bz -= P.t_nbz; ++by; }     // next tile of this group
+      by += sy; if (by >= P.t_nby) { by -= P.t_nby; ++bx; }
+      bx += sx; if (bx >= P.t_nbx) { bx -= P.t_nbx; ++bq; }
+      bq += sq;
     } else {
       const int n = tile * kTcTile + tq;
       const bool valid = n < (int)P.total;
@@ -372,7 +392,23 @@ __global__ void __launch_bounds__(kT4Threads, 1) decoder_tc4_kernel(const __grid
     // ---------------- net = fc_p(p) | fc_p_img(p, tip feature): this thread's 16 channels ----------------
     // (the fingertip test runs in float64: evaluate it before the residual stream occupies registers)
     int tipf = -1;
-    if (P.use_img && P.n_tips > 0) tipf = tip_of_query(P, max(oidx, 0), px, py, pz);
+    if (P.use_img && P.n_tips > 0) {
+      bool any_near = true;
+      if (DENSE && !P.tip_map) {
+        // the warp is one z-run at fixed (x, y): lane f tests fingertip f against the whole segment (fp32,
+        // padded threshold); almost every run is far from every fingertip and skips the per-query test
+        const float z_lo = __shfl_sync(kFull, pz, 0), z_hi = __shfl_sync(kFull, pz, 31);
+        bool near = false;
+        if (lane < P.n_tips) {
+          const float dx = px - P.tipsf[lane][0], dy = py - P.tipsf[lane][1];
+          const float tz = P.tipsf[lane][2];
+          const float dz = fmaxf(fmaxf(z_lo - tz, tz - z_hi), 0.f);
+          near = dx * dx + dy * dy + dz * dz < P.tip_r2_hi;
+        }
+        any_near = __any_sync(kFull, near);
+      }
+      if (any_near) tipf = tip_of_query(P, max(oidx, 0), px, py, pz);
+    }
     float net[16];
     {  // net = fc_c[0](c) + (W_img c_img | fc_p(p) + bc_0)
       uint32_t r[16];
@@ -410,7 +446,7 @@ __global__ void __launch_bounds__(kT4Threads, 1) decoder_tc4_kernel(const __grid
       for (int h = 0; h < 2; ++h) {
         float y[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) y[j] = fmaxf(net[8 * h + j], 0.f);
+        for (int j = 0; j < 8; ++j) y[j] = relu2(net[8 * h + j]);
         split_store8(tX, hv, h, y);
       }
       T4_STAMP(2);   // operands computed, tcgen05.st issued
@@ -444,8 +480,8 @@ __global__ void __launch_bounds__(kT4Threads, 1) decoder_tc4_kernel(const __grid
                                        make_float2(bb.x, bb.y));
           const float2 s1 = __fadd2_rn(make_float2(__uint_as_float(r[8 * h + 4 * j + 2]), __uint_as_float(r[8 * h + 4 * j + 3])),
                                        make_float2(bb.z, bb.w));
-          y[4 * j] = fmaxf(s0.x, 0.f); y[4 * j + 1] = fmaxf(s0.y, 0.f);
-          y[4 * j + 2] = fmaxf(s1.x, 0.f); y[4 * j + 3] = fmaxf(s1.y, 0.f);
+          y[4 * j] = relu2(s0.x); y[4 * j + 1] = relu2(s0.y);
+          y[4 * j + 2] = relu2(s1.x); y[4 * j + 3] = relu2(s1.y);
         }
         split_store8(tX, hv, h, y);
       }
@@ -479,13 +515,16 @@ __global__ void __launch_bounds__(kT4Threads, 1) decoder_tc4_kernel(const __grid
     // ---------------- heads: partial dot products of the two halves, combined through shared memory ----------------
     {
       const float* Wo = sSmall + 128;
-      const float slope = P.leaky ? 0.2f : 0.0f;
       float o = 0.f, oc = 0.f;
+      if (P.leaky) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        net[j] = net[j] > 0.f ? net[j] : net[j] * slope;
-        o = fmaf(Wo[ch0 + j], net[j], o);
+        for (int j = 0; j < 16; ++j) net[j] = net[j] > 0.f ? net[j] : net[j] * 0.2f;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) net[j] = fmaxf(net[j], 0.f);
       }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) o = fmaf(Wo[ch0 + j], net[j], o);
       if (P.contact) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) oc = fmaf(Wo[32 + ch0 + j], net[j], oc);

@@ -49,7 +49,8 @@ __global__ void __launch_bounds__(256) pack_tc_kernel(const __grid_constant__ Tc
     float* out = dst + Pn.mat_dst[b];
     for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
       const int k = i >> 5, n = i & 31;
-      const float w = __ldg(src + i);                      // W[n][k] (nn.Linear weight[out=n][in=k])
+      float w = __ldg(src + i);                            // W[n][k] (nn.Linear weight[out=n][in=k])
+      if (Pn.mixed == 2 && b < 3 * ((Pn.n_mats - 1) / 3) && (b % 3) != 0) w *= 0.5f;   // variant 7: fc_0 / fc_1 take 2*relu(x)
       const float hi = tf32_rn(w);
       const int idx = (k >> 2) * 128 + (n >> 3) * 32 + (n & 7) * 4 + (k & 3);
       out[idx] = hi;
