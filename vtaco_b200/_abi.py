@@ -140,11 +140,11 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    if not os.path.exists(os.environ.get('VTACO_B200_LIB', LIB_PATH)):
         raise RuntimeError(
             'vtaco_b200: %s not found. Build it with `python -m vtaco_b200.build` '
             '(nvcc, sm_100a). There is no CPU / PyTorch fallback.' % LIB_PATH)
-    L = C.CDLL(LIB_PATH)
+    L = C.CDLL(os.environ.get('VTACO_B200_LIB', LIB_PATH))   # (override: A/B runs of two builds in one process tree)
     L.vtaco_abi_version.restype = C.c_int
     L.vtaco_status_string.restype = C.c_char_p
     L.vtaco_status_string.argtypes = [C.c_int]

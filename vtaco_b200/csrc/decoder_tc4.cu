@@ -55,7 +55,9 @@ __device__ __forceinline__ int stage_idx(int r, int j) { return r * 16 + ((j ^ (
 // 2 * relu(x) = x + |x| (exact): one FADD on the FMA pipe instead of an FMNMX on the ALU pipe, which the
 // truncation (LOP3) and the BF16 pack (F2FP) already load (ncu: ALU pipe 47 %, FMA pipe 16 %).  The factor 2
 // is undone by the weights: fc_0 / fc_1 are packed times 0.5 (a power of two: every product is unchanged).
-__device__ __forceinline__ float relu2(float x) { return x + fabsf(x); }
+__device__ __forceinline__ float2 relu2(float2 x) {   // FADD2 with an |.| operand modifier: two channels per instruction
+  return __fadd2_rn(x, make_float2(fabsf(x.x), fabsf(x.y)));
+}
 
 // Eight channels [16*hv + 8*h, +8) of x (already activated) -> operand columns of the block at `tblk`:
 // hi (tf32 container: x with the 13 low mantissa bits cleared) at tblk + 16*hv + 8*h, lo = bf16(x - hi),
@@ -77,13 +79,17 @@ __device__ __forceinline__ void split_store8(uint32_t tblk, int hv, int h, const
                : "memory");
 }
 __device__ __forceinline__ void split_store_t4(uint32_t tblk, int hv, const float (&x)[16]) {
+  uint32_t hi[16], lo[8];
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    float y[8];
+  for (int j = 0; j < 16; ++j) hi[j] = trunc_tf32(x[j]);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) y[j] = x[8 * h + j];
-    split_store8(tblk, hv, h, y);
+  for (int c = 0; c < 8; ++c) {
+    const float2 d = __ffma2_rn(make_float2(__uint_as_float(hi[2 * c]), __uint_as_float(hi[2 * c + 1])),
+                                make_float2(-1.0f, -1.0f), make_float2(x[2 * c], x[2 * c + 1]));
+    lo[c] = pack_bf16(d.x, d.y);
   }
+  tmem_st16(tblk + 16 * hv, hi);
+  tmem_st8(tblk + 32 + 8 * hv, lo);
 }
 
 // Shared-memory descriptor of a B block `units` 16-byte units after the block described by `lo`:
@@ -193,13 +199,25 @@ __global__ void __launch_bounds__(kT4Threads, 1) decoder_tc4_kernel(const __grid
   constexpr uint32_t kMatUnits = kT4MatBytes / 16;
   const uint32_t pwlo = ((smem_u32(sPw) >> 4) & 0x3fffu) | ((512u >> 4) << 16);
   const int gsync_id = g + 1;
+  int step = 0;   // accumulation steps issued so far by this group: rotates the issuing warp, its parity is the mbarrier phase
   auto group_sync = [&]() { asm volatile("bar.sync %0, 256;" ::"r"(gsync_id) : "memory"); };
+  // Wait for the MMAs of the step issued last (step counts them; its parity is the mbarrier phase).  Only the
+  // warp that issued them polls the mbarrier; the other seven sleep in the group's hardware barrier, which
+  // costs no issue slots (ncu: with all eight warps polling, a quarter of all issued instructions were the
+  // try_wait loop, taken from the warps that had work).
+  auto mma_wait = [&]() {
+    if (wq == ((step - 1) & 7)) {
+      mbar_wait(bar, (uint32_t)(step - 1) & 1u);
+      tc_fence_after();
+      tc_fence_before();
+    }
+    asm volatile("bar.sync %0, 256;" ::"r"(gsync_id) : "memory");
+  };
   float* stage = sStage + warp * kT4StageRows * 16;
   float* head = sHead + g * 256;
   const int sub = lane & 3;          // float4 within the 16-channel half
   const int zr = lane >> 2;          // 8 rows / queries per load step
   const int ch0 = 16 * hv;           // first channel of this thread
-  int step = 0;   // accumulation steps issued so far by this group: rotates the issuing warp, its parity is the mbarrier phase
   const bool sep_cfg = DENSE && P.has_c && P.grid && !P.nearest && !(P.plane[0] || P.plane[1] || P.plane[2]);
 
   const int n_tiles = (int)P.n_tiles;   // < 2^31 (checked at launch)
@@ -250,7 +268,6 @@ __global__ void __launch_bounds__(kT4Threads, 1) decoder_tc4_kernel(const __grid
     // ---------------- gather: this thread's 16 channels of its query (+ of its c_img row): operands of step 0 ----------------
     {
       if (P.has_c) {
-        float cv[16];
         bool sep_done = false;
         if (sep_cfg) {
           // separable dense gather (see decoder_tc.cu): the warp is one z-run at fixed (x, y); the 4
@@ -277,30 +294,38 @@ __global__ void __launch_bounds__(kT4Threads, 1) decoder_tc4_kernel(const __grid
               if (zrow < nz) {
                 const float4* p = col + (size_t)(zmin + zrow) * R * R * 8;
                 const float4 v00 = __ldg(p), v01 = __ldg(p + dx), v10 = __ldg(p + dy), v11 = __ldg(p + dy + dx);
-                float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-                a = f4_fma(w00, v00, a);
-                a = f4_fma(w01, v01, a);
-                a = f4_fma(w10, v10, a);
-                a = f4_fma(w11, v11, a);
-                *reinterpret_cast<float4*>(stage + stage_idx(zrow, sub)) = a;
+                // (same operation order as f4_fma from 0: fma(v00, w00, 0) == v00 * w00, then three FMAs; two lanes per FFMA2)
+                float2 lo2 = __fmul2_rn(make_float2(v00.x, v00.y), make_float2(w00, w00));
+                float2 hi2 = __fmul2_rn(make_float2(v00.z, v00.w), make_float2(w00, w00));
+                lo2 = __ffma2_rn(make_float2(v01.x, v01.y), make_float2(w01, w01), lo2);
+                hi2 = __ffma2_rn(make_float2(v01.z, v01.w), make_float2(w01, w01), hi2);
+                lo2 = __ffma2_rn(make_float2(v10.x, v10.y), make_float2(w10, w10), lo2);
+                hi2 = __ffma2_rn(make_float2(v10.z, v10.w), make_float2(w10, w10), hi2);
+                lo2 = __ffma2_rn(make_float2(v11.x, v11.y), make_float2(w11, w11), lo2);
+                hi2 = __ffma2_rn(make_float2(v11.z, v11.w), make_float2(w11, w11), hi2);
+                *reinterpret_cast<float4*>(stage + stage_idx(zrow, sub)) = make_float4(lo2.x, lo2.y, hi2.x, hi2.y);
               }
             }
             __syncwarp();
             const int ra = z0 - zmin, rb = min(z0 + 1, R - 1) - zmin;
+            float cv[16];   // (its own array: the generic path's cv lives in local memory)
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const float4 a = *reinterpret_cast<const float4*>(stage + stage_idx(ra, j));
               const float4 b = *reinterpret_cast<const float4*>(stage + stage_idx(rb, j));
-              cv[4 * j + 0] = fmaf(b.x, fz1, a.x * fz0);
-              cv[4 * j + 1] = fmaf(b.y, fz1, a.y * fz0);
-              cv[4 * j + 2] = fmaf(b.z, fz1, a.z * fz0);
-              cv[4 * j + 3] = fmaf(b.w, fz1, a.w * fz0);
+              const float2 f0 = make_float2(fz0, fz0), f1 = make_float2(fz1, fz1);
+              const float2 c0 = __ffma2_rn(make_float2(b.x, b.y), f1, __fmul2_rn(make_float2(a.x, a.y), f0));
+              const float2 c1 = __ffma2_rn(make_float2(b.z, b.w), f1, __fmul2_rn(make_float2(a.z, a.w), f0));
+              cv[4 * j + 0] = c0.x; cv[4 * j + 1] = c0.y; cv[4 * j + 2] = c1.x; cv[4 * j + 3] = c1.y;
             }
             __syncwarp();
+            T4_STAMP(15);  // features of the thread's query in registers
+            split_store_t4(tC, hv, cv);
             sep_done = true;
           }
         }
         if (!sep_done) {   // generic gather: the owner computes the taps, 4 lanes fetch a query's 16 channels
+          float cv[16];
           TapInfo tv, tp0, tp1, tp2;
           if (P.grid) tv = tap_volume(norm3d(px, P.nc), norm3d(py, P.nc), norm3d(pz, P.nc), P.Rg, P.nearest);
           const bool planes = P.plane[0] || P.plane[1] || P.plane[2];
@@ -342,9 +367,8 @@ __global__ void __launch_bounds__(kT4Threads, 1) decoder_tc4_kernel(const __grid
             }
             __syncwarp();
           }
+          split_store_t4(tC, hv, cv);
         }
-        T4_STAMP(15);  // features of the thread's query in registers
-        split_store_t4(tC, hv, cv);
       }
       if (cimg) {   // fc_p_img(cat[p, c_img]) = fc_p_img[:, :3] p + b + W_img c_img: the last term rides in step 0
         float xv[16];
@@ -412,7 +436,7 @@ __global__ void __launch_bounds__(kT4Threads, 1) decoder_tc4_kernel(const __grid
     float net[16];
     {  // net = fc_c[0](c) + (W_img c_img | fc_p(p) + bc_0)
       uint32_t r[16];
-      mbar_wait(bar, (uint32_t)(step - 1) & 1u);
+      mma_wait();
       tc_fence_after();
       tmem_ld16(tD + ch0, r);
       tc_wait_ld();
@@ -442,12 +466,14 @@ __global__ void __launch_bounds__(kT4Threads, 1) decoder_tc4_kernel(const __grid
     uint32_t r[16];
     for (int i = 0; i < nb; ++i) {
       T4_STAMP(1);   // ALU phase starts (accumulator already read)
+      {
+        float y[16];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        float y[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) y[j] = relu2(net[8 * h + j]);
-        split_store8(tX, hv, h, y);
+        for (int j = 0; j < 8; ++j) {
+          const float2 v = relu2(make_float2(net[2 * j], net[2 * j + 1]));
+          y[2 * j] = v.x; y[2 * j + 1] = v.y;
+        }
+        split_store_t4(tX, hv, y);
       }
       T4_STAMP(2);   // operands computed, tcgen05.st issued
       tc_wait_st();
@@ -464,26 +490,23 @@ __global__ void __launch_bounds__(kT4Threads, 1) decoder_tc4_kernel(const __grid
       ++step;
       T4_STAMP(5);
       const float4* b0 = reinterpret_cast<const float4*>(sBias + (2 * i + 1) * 32 + ch0);
-      mbar_wait(bar, (uint32_t)(step - 1) & 1u);
+      mma_wait();
       T4_STAMP(6);   // MMAs complete
       tc_fence_after();
       tmem_ld16(tD + ch0, r);
       tc_wait_ld();
       T4_STAMP(7);   // accumulator in registers
+      {                                           // h = relu(D + b0_i), packed adds
+        float y[16];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {               // h = relu(D + b0_i), packed adds
-        float y[8];
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const float4 bb = b0[2 * h + j];
-          const float2 s0 = __fadd2_rn(make_float2(__uint_as_float(r[8 * h + 4 * j]), __uint_as_float(r[8 * h + 4 * j + 1])),
-                                       make_float2(bb.x, bb.y));
-          const float2 s1 = __fadd2_rn(make_float2(__uint_as_float(r[8 * h + 4 * j + 2]), __uint_as_float(r[8 * h + 4 * j + 3])),
-                                       make_float2(bb.z, bb.w));
-          y[4 * j] = relu2(s0.x); y[4 * j + 1] = relu2(s0.y);
-          y[4 * j + 2] = relu2(s1.x); y[4 * j + 3] = relu2(s1.y);
+        for (int j = 0; j < 4; ++j) {
+          const float4 bb = b0[j];
+          const float2 s0 = __fadd2_rn(make_float2(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1])), make_float2(bb.x, bb.y));
+          const float2 s1 = __fadd2_rn(make_float2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), make_float2(bb.z, bb.w));
+          const float2 v0 = relu2(s0), v1 = relu2(s1);
+          y[4 * j] = v0.x; y[4 * j + 1] = v0.y; y[4 * j + 2] = v1.x; y[4 * j + 3] = v1.y;
         }
-        split_store8(tX, hv, h, y);
+        split_store_t4(tX, hv, y);
       }
       tc_wait_st();
       tc_fence_before();
@@ -496,7 +519,7 @@ __global__ void __launch_bounds__(kT4Threads, 1) decoder_tc4_kernel(const __grid
       }
       ++step;
       const float4* b1 = reinterpret_cast<const float4*>(sBias + (2 * i + 2) * 32 + ch0);
-      mbar_wait(bar, (uint32_t)(step - 1) & 1u);
+      mma_wait();
       tc_fence_after();
       tmem_ld16(tD + ch0, r);
       tc_wait_ld();
@@ -523,8 +546,13 @@ __global__ void __launch_bounds__(kT4Threads, 1) decoder_tc4_kernel(const __grid
 #pragma unroll
         for (int j = 0; j < 16; ++j) net[j] = fmaxf(net[j], 0.f);
       }
+      {   // 16-term dot product as two 8-term chains on register pairs
+        float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) o = fmaf(Wo[ch0 + j], net[j], o);
+        for (int j = 0; j < 8; ++j)
+          acc = __ffma2_rn(make_float2(Wo[ch0 + 2 * j], Wo[ch0 + 2 * j + 1]), make_float2(net[2 * j], net[2 * j + 1]), acc);
+        o = acc.x + acc.y;
+      }
       if (P.contact) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) oc = fmaf(Wo[32 + ch0 + j], net[j], oc);

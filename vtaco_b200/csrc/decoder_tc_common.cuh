@@ -25,13 +25,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "{\n"
       ".reg .pred p;\n"
       "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
       "@p bra DONE;\n"
       "bra LAB_WAIT;\n"
       "DONE:\n"
-      "}\n" ::"r"(bar), "r"(parity), "r"(0x989680u)   // suspend-time hint: the warp sleeps in hardware until the
-      : "memory");                                     // phase completes instead of re-issuing the probe (ncu: 16 % of
-                                                       // all issued instructions were this spin before the hint)
+      "}\n" ::"r"(bar), "r"(parity)
+      : "memory");
 }
 // exactly one lane of a converged warp; unlike `lane == 0` the compiler knows a single lane is
 // active, so tcgen05.mma sequences compile to back-to-back UTCHMMA without per-instruction
