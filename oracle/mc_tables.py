@@ -202,13 +202,16 @@ def write_header(path):
     lines = ['// GENERATED by oracle/mc_tables.py — do not edit.  See that file for the rule.',
              '#pragma once', '#include <stdint.h>', 'namespace vtaco {',
              'constexpr int kMcMaxTris = %d;' % MAX_TRIS,
-             '__device__ __constant__ int8_t kMcTriCount[256] = {%s};' % ','.join(str(int(v)) for v in TRI_COUNT),
-             '__device__ __constant__ int8_t kMcTriTable[256][%d] = {' % (MAX_TRIS * 3)]
+             '// global memory (not __constant__): the kernels stage the tables in shared memory with coalesced loads;',
+             '// every lane indexes them with its own case, which a constant bank would serialise per distinct address',
+             '__device__ const int8_t kMcTriCount[256] = {%s};' % ','.join(str(int(v)) for v in TRI_COUNT),
+             '// rows padded to 16 bytes: a case row is one aligned 16-byte load',
+             'alignas(16) __device__ const int8_t kMcTriTable[256][16] = {']
     for c in range(256):
-        lines.append('  {%s},' % ','.join(str(int(v)) for v in TRI_TABLE[c]))
+        lines.append('  {%s,0},' % ','.join(str(int(v)) for v in TRI_TABLE[c]))
     lines.append('};')
     lines.append('// edge e: axis, owner offset (x,y,z)')
-    lines.append('__device__ __constant__ int8_t kMcEdge[12][4] = {')
+    lines.append('alignas(16) __device__ const int8_t kMcEdge[12][4] = {')
     for e in range(12):
         lines.append('  {%d,%d,%d,%d},' % (int(EDGE_AXIS[e]), *[int(v) for v in EDGE_OFF[e]]))
     lines.append('};')

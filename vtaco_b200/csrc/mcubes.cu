@@ -7,18 +7,21 @@
 // are not available offline — parity with skimage is UNPINNED, parity with the oracle is
 // bit-exact on case indices / faces and to rounding on vertices).
 //
-// HBM-bound stream compaction in TWO kernels that read the grid once:
-//   mc_fused_kernel : 1 thread / run of 8 consecutive z points — four rows of 9 samples as float4
-//              loads -> "above" bit rows -> per point 3-bit own-edge mask + triangle count; block
-//              scan; the block's exclusive prefix comes from a DECOUPLED LOOK-BACK over the
-//              blocks before it (single pass, blocks take their index from a ticket so that
-//              every predecessor has started); with its vertex base known the thread emits the
-//              vertices of its own cut edges at once (inverse-distance weighting in double, like
-//              Lewiner's code), stores the run's codes + vertex base for the face pass and
-//              appends runs that own triangles to a work list (with their triangle base)
-//   mc_faces_kernel : grid-stride over the work list only (~5 % of the runs): vertex ids are looked
-//              up from the owners' codes / bases; output order = lattice order, then table order
-//              (the order of the WORK is arbitrary, every item carries its output position).
+// HBM-bound stream compaction in TWO kernels; only the first streams the grid:
+//   mc_fused_kernel : 1 thread / 4 runs of 8 consecutive z points — four rows of 9 samples as float4
+//              loads -> "above" bit rows -> per point 3-bit own-edge mask + triangle count; the four
+//              runs are classified back to back (all loads in flight) and scanned together (two
+//              block barriers); the block's exclusive prefix comes from a DECOUPLED LOOK-BACK over
+//              the blocks before it (single pass, blocks take their index from a ticket so that
+//              every predecessor has started); the kernel stores codes + vertex base of the active
+//              runs and appends them, with their triangle base, to a work list.  No emission here:
+//              a warp is one z-row of the lattice, and rows that the surface crosses in one or two
+//              places ran the 8 x 3 double-precision emission loop for one or two lanes.
+//   mc_emit_kernel : grid-stride over the work list only (~6 % of the runs, every lane busy): the
+//              vertices of the run's own cut edges (inverse-distance weighting in double, like
+//              Lewiner's code) and the faces of its cut cells; vertex ids are looked up from the
+//              owners' codes / bases; output order = lattice order, then table order (the order
+//              of the WORK is arbitrary, every item carries its output positions).
 // Slab mode (x_emit < nx; multi-GPU extraction, SURVEY 8e "gather of mesh pieces"): the volume
 // holds the rank's x-rows plus two halo rows; vertex ids are numbered over the whole volume (so a
 // halo-row vertex gets the id it has as the NEXT rank's first vertices), but only vertices owned
@@ -41,6 +44,7 @@ constexpr int kMcSuper = 256;     // blocks per super-block of the two-level pre
 struct McParams {
   const float* grid;
   int nx, ny, nz, nzc;            // nzc = ceil(nz / kMcRun) runs per (x,y) row
+  int nzc_shift, ny_shift;        // log2 when the extent is a power of two (run -> coordinates by shifts), else -1
   int x_emit;                     // rows [0, x_emit) emit vertices / faces (== nx: whole volume)
   int x_origin;                   // lattice row of the sub-volume's row 0 (vertex coordinates are global)
   long long npts, nruns;
@@ -75,43 +79,12 @@ __device__ __forceinline__ float mc_level(const McParams& P) {
   return P.level;
 }
 
-// exclusive scan of a packed (hi16 | lo16) value across the block; returns the exclusive
-// prefix and the block total (all threads).
-__device__ __forceinline__ unsigned block_scan_excl(unsigned v, unsigned& total) {
-  constexpr int kWarps = kMcThreads / 32;
-  __shared__ unsigned warp_excl[kWarps];
-  __shared__ unsigned tot;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  unsigned inc = v;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const unsigned t = __shfl_up_sync(0xffffffffu, inc, d);
-    if (lane >= d) inc += t;
-  }
-  if (lane == 31) warp_excl[w] = inc;  // warp totals
-  __syncthreads();
-  if (w == 0) {
-    const unsigned s = lane < kWarps ? warp_excl[lane] : 0u;
-    unsigned si = s;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const unsigned t = __shfl_up_sync(0xffffffffu, si, d);
-      if (lane >= d) si += t;
-    }
-    if (lane < kWarps) warp_excl[lane] = si - s;
-    if (lane == kWarps - 1) tot = si;
-  }
-  __syncthreads();
-  total = tot;
-  return warp_excl[w] + inc - v;
-}
-
 // run -> lattice coordinates of its first point
 __device__ __forceinline__ void run_coords(const McParams& P, long long run, int& i, int& j, int& k0) {
   const unsigned ru = (unsigned)run;           // nruns < 2^31 (checked by the host wrapper)
-  const unsigned r = ru / (unsigned)P.nzc;
+  const unsigned r = P.nzc_shift >= 0 ? ru >> P.nzc_shift : ru / (unsigned)P.nzc;
   const int kc = (int)(ru - r * (unsigned)P.nzc);
-  i = (int)(r / (unsigned)P.ny);
+  i = (int)(P.ny_shift >= 0 ? r >> P.ny_shift : r / (unsigned)P.ny);
   j = (int)(r - (unsigned)i * (unsigned)P.ny);
   k0 = kc * kMcRun;
 }
@@ -128,9 +101,17 @@ __device__ __forceinline__ unsigned row_bits(const McParams& P, int i, int j, in
     const float4 a = __ldg(reinterpret_cast<const float4*>(row + k0));
     const float4 b = __ldg(reinterpret_cast<const float4*>(row + k0 + 4));
     const float c = __ldg(row + min(k0 + 8, P.nz - 1));
-    bits = (unsigned)(a.x > level) | ((unsigned)(a.y > level) << 1) | ((unsigned)(a.z > level) << 2) |
-           ((unsigned)(a.w > level) << 3) | ((unsigned)(b.x > level) << 4) | ((unsigned)(b.y > level) << 5) |
-           ((unsigned)(b.z > level) << 6) | ((unsigned)(b.w > level) << 7) | ((unsigned)(c > level) << 8);
+    // sample > level  <=>  level - sample is negative (no flush-to-zero in this build: a difference of distinct
+    // floats is never zero); the sign bits are collected by funnel shifts, highest sample first
+    bits = __funnelshift_l(__float_as_uint(level - c), bits, 1);
+    bits = __funnelshift_l(__float_as_uint(level - b.w), bits, 1);
+    bits = __funnelshift_l(__float_as_uint(level - b.z), bits, 1);
+    bits = __funnelshift_l(__float_as_uint(level - b.y), bits, 1);
+    bits = __funnelshift_l(__float_as_uint(level - b.x), bits, 1);
+    bits = __funnelshift_l(__float_as_uint(level - a.w), bits, 1);
+    bits = __funnelshift_l(__float_as_uint(level - a.z), bits, 1);
+    bits = __funnelshift_l(__float_as_uint(level - a.y), bits, 1);
+    bits = __funnelshift_l(__float_as_uint(level - a.x), bits, 1);
   } else {
 #pragma unroll
     for (int t = 0; t <= kMcRun; ++t) bits |= (unsigned)(__ldg(row + min(k0 + t, P.nz - 1)) > level) << t;
@@ -142,10 +123,9 @@ __device__ __forceinline__ unsigned row_bits(const McParams& P, int i, int j, in
 // Bit-parallel over the run: own-edge masks are XORs of the "above" rows and a cell is cut iff
 // its 8 corner bits are neither all 0 nor all 1, so the ~95 % of runs that the surface does not
 // touch cost a handful of logic ops; only the set bits take the per-point path.
-__device__ __forceinline__ unsigned run_codes(const McParams& P, int i, int j, int k0, float level,
-                                               unsigned long long& codes, const uint8_t* __restrict__ tri_count) {
-  const unsigned r00 = row_bits(P, i, j, k0, level), r01 = row_bits(P, i, j + 1, k0, level);
-  const unsigned r10 = row_bits(P, i + 1, j, k0, level), r11 = row_bits(P, i + 1, j + 1, k0, level);
+__device__ __forceinline__ unsigned run_codes(const McParams& P, int i, int j, int k0, unsigned r00, unsigned r10,
+                                               unsigned r01, unsigned r11, unsigned long long& codes,
+                                               const uint8_t* __restrict__ tri_count) {
   const bool hx = i + 1 < P.nx, hy = j + 1 < P.ny;
   const int left = P.nz - k0;                                     // points of this run inside the lattice
   const unsigned m8 = left >= kMcRun ? 0xffu : ((1u << left) - 1u);
@@ -197,33 +177,86 @@ constexpr int kMcSub = 4;                          // consecutive 256-run sub-bl
 constexpr int kMcBlockRuns = kMcThreads * kMcSub;
 
 __global__ void __launch_bounds__(kMcThreads) mc_fused_kernel(const __grid_constant__ McParams P) {
+  constexpr int kWarps = kMcThreads / 32;
   __shared__ int s_bid;
   __shared__ unsigned long long s_prefix;
   __shared__ uint8_t s_tricount[256];
+  __shared__ unsigned s_wexcl[kMcSub * kWarps];
+  __shared__ unsigned s_rows[kMcBlockRuns];
+  __shared__ unsigned s_total;
   if (threadIdx.x == 0) s_bid = (int)atomicAdd(P.ctrl, 1u);      // ticket: all blocks before this one have started
-  s_tricount[threadIdx.x] = (uint8_t)kMcTriCount[threadIdx.x];
+  s_tricount[threadIdx.x] = (uint8_t)__ldg(kMcTriCount + threadIdx.x);
   __syncthreads();
   const int b = s_bid;
   const float level = mc_level(P);
-  // ---- classify kMcSub runs per thread (run = block base + s * 256 + thread: coalesced, lattice order = (s, thread)) ----
-  unsigned packed[kMcSub], excl[kMcSub];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  // ---- classify kMcSub runs per thread (run = block base + s * 256 + thread: coalesced, lattice order = (s, thread));
+  //      no barrier between them, so the loads of all four runs are in flight together ----
+  //      A run needs the "above" bits of rows (i,j), (i+1,j), (i,j+1), (i+1,j+1); the last two are the first two of
+  //      run + nzc, which is a run of this block for all but its last nzc runs: every thread classifies its own two
+  //      rows and takes the other two from shared memory (half the loads and compares).
+  unsigned packed[kMcSub], inc[kMcSub];
   unsigned long long codes[kMcSub];
-  unsigned sub_base = 0;                                         // packed totals of the sub-blocks before s
+  unsigned own[kMcSub];                                          // r00 | r10 << 16
 #pragma unroll
   for (int s = 0; s < kMcSub; ++s) {
     const long long run = (long long)b * kMcBlockRuns + s * kMcThreads + threadIdx.x;
+    own[s] = 0;
+    if (run < P.nruns) {
+      int i, j, k0;
+      run_coords(P, run, i, j, k0);
+      own[s] = row_bits(P, i, j, k0, level) | (row_bits(P, i + 1, j, k0, level) << 16);
+    }
+    s_rows[s * kMcThreads + threadIdx.x] = own[s];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int s = 0; s < kMcSub; ++s) {
+    const int local = s * kMcThreads + threadIdx.x;
+    const long long run = (long long)b * kMcBlockRuns + local;
     packed[s] = 0;
     codes[s] = 0;
     if (run < P.nruns) {
       int i, j, k0;
       run_coords(P, run, i, j, k0);
-      packed[s] = run_codes(P, i, j, k0, level, codes[s], s_tricount);
+      unsigned nxt;
+      if (j + 1 >= P.ny) nxt = own[s];                           // replicated row: its cells / edges are masked out
+      else if (local + P.nzc < kMcBlockRuns) nxt = s_rows[local + P.nzc];
+      else nxt = row_bits(P, i, j + 1, k0, level) | (row_bits(P, i + 1, j + 1, k0, level) << 16);
+      packed[s] = run_codes(P, i, j, k0, own[s] & 0xffffu, own[s] >> 16, nxt & 0xffffu, nxt >> 16, codes[s], s_tricount);
     }
-    unsigned total;
-    excl[s] = sub_base + block_scan_excl(packed[s], total);
-    sub_base += total;                                           // fields: vertices < 2^16 (4 x 6144), triangles < 2^16 (4 x 10240)
   }
-  const unsigned total = sub_base;
+  // ---- one scan over the (s, thread) order: four independent warp scans, then the 32 warp totals in warp 0.
+  //      fields: vertices < 2^16 (4 x 6144), triangles < 2^16 (4 x 10240) ----
+#pragma unroll
+  for (int s = 0; s < kMcSub; ++s) inc[s] = packed[s];
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+#pragma unroll
+    for (int s = 0; s < kMcSub; ++s) {
+      const unsigned t = __shfl_up_sync(0xffffffffu, inc[s], d);
+      if (lane >= d) inc[s] += t;
+    }
+  }
+  if (lane == 31) {
+#pragma unroll
+    for (int s = 0; s < kMcSub; ++s) s_wexcl[s * kWarps + w] = inc[s];
+  }
+  __syncthreads();
+  unsigned total = 0;
+  if (w == 0) {
+    static_assert(kMcSub * kWarps == 32, "one lane per (sub-block, warp) total");
+    const unsigned v = s_wexcl[lane];
+    unsigned si = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned t = __shfl_up_sync(0xffffffffu, si, d);
+      if (lane >= d) si += t;
+    }
+    s_wexcl[lane] = si - v;
+    total = __shfl_sync(0xffffffffu, si, 31);
+    if (lane == 0) s_total = total;
+  }
   // ---- decoupled look-back (warp 0): exclusive prefix of this block over all blocks before it ----
   if (threadIdx.x < 32) {
     const unsigned long long agg = (unsigned long long)(total & 0xffffu) | ((unsigned long long)(total >> 16) << 31);
@@ -233,19 +266,19 @@ __global__ void __launch_bounds__(kMcThreads) mc_fused_kernel(const __grid_const
       int base = b - 1;
       for (;;) {
         constexpr int kLb = 2;                                   // words per lane: 64 predecessors per round
-        unsigned long long w[kLb];
+        unsigned long long wd[kLb];
 #pragma unroll
         for (int h = 0; h < kLb; ++h) {                          // lane l reads predecessors base - 32 h - l
           const int idx = base - 32 * h - (int)threadIdx.x;
-          w[h] = kMcFlagPrefix;                                  // before block 0: an empty prefix
-          if (idx >= 0) w[h] = ld_state(P.state + idx);
+          wd[h] = kMcFlagPrefix;                                 // before block 0: an empty prefix
+          if (idx >= 0) wd[h] = ld_state(P.state + idx);
         }
         // a word that is not published yet ends the usable range of this round: everything nearer than the
         // nearest prefix word must be an aggregate, otherwise look again
         int first = kLb * 32, hole = kLb * 32;
 #pragma unroll
         for (int h = kLb - 1; h >= 0; --h) {
-          const unsigned pp = __ballot_sync(0xffffffffu, (w[h] >> 62) == 2), zz = __ballot_sync(0xffffffffu, (w[h] >> 62) == 0);
+          const unsigned pp = __ballot_sync(0xffffffffu, (wd[h] >> 62) == 2), zz = __ballot_sync(0xffffffffu, (wd[h] >> 62) == 0);
           if (pp) first = 32 * h + (__ffs(pp) - 1);
           if (zz) hole = 32 * h + (__ffs(zz) - 1);
         }
@@ -253,7 +286,7 @@ __global__ void __launch_bounds__(kMcThreads) mc_fused_kernel(const __grid_const
         unsigned long long v = 0;
 #pragma unroll
         for (int h = 0; h < kLb; ++h)
-          if (32 * h + (int)threadIdx.x <= first) v += w[h] & kMcValMask;
+          if (32 * h + (int)threadIdx.x <= first) v += wd[h] & kMcValMask;
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
         prefix += v;
@@ -274,54 +307,21 @@ __global__ void __launch_bounds__(kMcThreads) mc_fused_kernel(const __grid_const
   }
   __syncthreads();
   const unsigned long long pre = s_prefix;
-  const double dlevel = (double)level;
-  const long long stride[3] = {(long long)P.ny * P.nz, (long long)P.nz, 1};
+  // ---- codes + vertex base of the active runs; every active run becomes one work item of the emit pass ----
 #pragma unroll
   for (int s = 0; s < kMcSub; ++s) {
     const long long run = (long long)b * kMcBlockRuns + s * kMcThreads + threadIdx.x;
     if (run >= P.nruns) continue;
-    unsigned long long vb = (pre & 0x7fffffffull) + (excl[s] & 0xffffu);
-    const unsigned long long tb = (pre >> 31) + (excl[s] >> 16);
+    const unsigned excl = s_wexcl[s * kWarps + w] + inc[s] - packed[s];
+    const unsigned long long vb = (pre & 0x7fffffffull) + (excl & 0xffffu);
+    const unsigned long long tb = (pre >> 31) + (excl >> 16);
     if (P.x_emit < P.nx && run == (long long)P.x_emit * P.ny * P.nzc) P.counts[0] = (long long)vb;   // first halo run
     if (!packed[s]) continue;
     reinterpret_cast<unsigned long long*>(P.code)[run] = codes[s];
     P.vbase[run] = (uint32_t)vb;
     if (!P.emit) continue;
-    if (packed[s] >> 16) {                                       // the run owns triangles: face pass work item
-      const unsigned slot = atomicAdd(P.ctrl + 1, 1u);
-      P.work[slot] = make_uint2((unsigned)run, (unsigned)tb);
-    }
-    int i, j, k0;
-    run_coords(P, run, i, j, k0);
-    if (i >= P.x_emit) continue;                                 // halo rows: numbered, not emitted
-#pragma unroll 1
-    for (int t = 0; t < kMcRun; ++t) {
-      const unsigned flags = (unsigned)(codes[s] >> (8 * t)) & 7u;
-      if (!flags) continue;
-      const int k = k0 + t;
-      const long long p = ((long long)i * P.ny + j) * P.nz + k;
-      const double d0 = fabs((double)P.grid[p] - dlevel);
-      const float base[3] = {(float)(i + P.x_origin), (float)j, (float)k};
-#pragma unroll
-      for (int a = 0; a < 3; ++a) {
-        if (flags & (1u << a)) {
-          if ((long long)vb < P.vcap) {    // capacity overflow: counted, not written (the caller re-runs with larger buffers)
-            const double d1 = fabs((double)P.grid[p + stride[a]] - dlevel);
-            // Lewiner's weights w = 1 / (eps + d): t = w1 / (w0 + w1) = (eps + d0) / ((eps + d0) + (eps + d1)), one
-            // division instead of three (equal to the last bit or two of the double, far below the float32 result)
-            const double e0 = (double)FLT_EPSILON + d0, e1 = (double)FLT_EPSILON + d1;
-            const double tt = e0 / (e0 + e1);
-            float pos[3] = {base[0], base[1], base[2]};
-            pos[a] = (float)((double)base[a] + tt);
-            float* o = P.verts + vb * 3;
-            o[0] = (pos[0] - P.voffset) * P.vscale;
-            o[1] = (pos[1] - P.voffset) * P.vscale;
-            o[2] = (pos[2] - P.voffset) * P.vscale;
-          }
-          ++vb;
-        }
-      }
-    }
+    const unsigned slot = atomicAdd(P.ctrl + 1, 1u);
+    P.work[slot] = make_uint2((unsigned)run, (unsigned)tb);
   }
 }
 
@@ -336,38 +336,90 @@ __device__ __forceinline__ int32_t vertex_id(const McParams& P, int i, int j, in
   return (int32_t)(P.vbase[r] + __popcll(before) + __popc(own & ((1u << a) - 1u)));
 }
 
-__global__ void __launch_bounds__(kMcThreads) mc_faces_kernel(const __grid_constant__ McParams P) {
+// Emit pass: EIGHT lanes per work item, lane t owns point t of the run — its (up to 3) vertices and the
+// (up to 5) triangles of its cell.  One thread per run walked the 8 points serially through ~25 dependent
+// global loads (59 us for the 6 % active runs of a 256^3 grid); here a lane's chain is work item -> codes ->
+// grid samples -> neighbour codes / bases, and the samples of the run double as the vertex weights.
+__global__ void __launch_bounds__(kMcThreads) mc_emit_kernel(const __grid_constant__ McParams P) {
   // case tables in shared memory: every lane indexes them with its own case (a divergent __constant__ index costs
-  // one replay per distinct address — it was the top stall of this kernel); a case row is one 16-byte load
+  // one replay per distinct address); a case row is one 16-byte load
   __shared__ uint4 s_tri[256];
   __shared__ int8_t s_edge[12][4];
   {
-    int8_t* dst = reinterpret_cast<int8_t*>(s_tri);
-    for (int i = threadIdx.x; i < 256 * 16; i += blockDim.x) dst[i] = (i & 15) < 15 ? kMcTriTable[i >> 4][i & 15] : (int8_t)0;
-    if (threadIdx.x < 48) s_edge[threadIdx.x >> 2][threadIdx.x & 3] = kMcEdge[threadIdx.x >> 2][threadIdx.x & 3];
+    static_assert(kMcThreads == 256 && kMcMaxTris * 3 == 15, "one 16-byte case row per thread");
+    s_tri[threadIdx.x] = __ldg(reinterpret_cast<const uint4*>(kMcTriTable) + threadIdx.x);
+    if (threadIdx.x < 12) *reinterpret_cast<int*>(s_edge[threadIdx.x]) = __ldg(reinterpret_cast<const int*>(kMcEdge) + threadIdx.x);
   }
   __syncthreads();
   const unsigned n_work = P.ctrl[1];
   const float level = mc_level(P);
-  for (unsigned wi = blockIdx.x * blockDim.x + threadIdx.x; wi < n_work; wi += gridDim.x * blockDim.x) {
-    const uint2 item = P.work[wi];
+  const double dlevel = (double)level;
+  const int lane = threadIdx.x & 31, t = lane & 7;
+  const unsigned warps_total = gridDim.x * (kMcThreads / 32);
+  const unsigned warp_global = blockIdx.x * (kMcThreads / 32) + (threadIdx.x >> 5);
+  for (unsigned base = warp_global * 4; base < n_work; base += warps_total * 4) {   // warp-uniform trip count
+    const unsigned wi = base + (lane >> 3);
+    const bool live = wi < n_work;
+    const uint2 item = live ? P.work[wi] : make_uint2(0u, 0u);
     const long long run = item.x;
-    unsigned long long tb = item.y;
-    const unsigned long long codes = reinterpret_cast<const unsigned long long*>(P.code)[run];
+    const unsigned long long codes = live ? reinterpret_cast<const unsigned long long*>(P.code)[run] : 0ull;
     int i, j, k0;
     run_coords(P, run, i, j, k0);
-    const unsigned r00 = row_bits(P, i, j, k0, level), r01 = row_bits(P, i, j + 1, k0, level);
-    const unsigned r10 = row_bits(P, i + 1, j, k0, level), r11 = row_bits(P, i + 1, j + 1, k0, level);
-#pragma unroll 1
-    for (int t = 0; t < kMcRun; ++t) {
-      const unsigned nt = ((unsigned)(codes >> (8 * t)) & 0xffu) >> 3;
-      if (!nt) continue;
-      const unsigned cs = ((r00 >> t) & 1u) | (((r10 >> t) & 1u) << 1) | (((r01 >> t) & 1u) << 2) |
-                          (((r11 >> t) & 1u) << 3) | (((r00 >> (t + 1)) & 1u) << 4) | (((r10 >> (t + 1)) & 1u) << 5) |
-                          (((r01 >> (t + 1)) & 1u) << 6) | (((r11 >> (t + 1)) & 1u) << 7);
-      const int k = k0 + t;
+    const int k = k0 + t;
+    // samples of the four z-rows at this point (rows / samples outside the lattice replicate the last valid one,
+    // as in row_bits: their cells / edges carry no flags)
+    const int i1 = min(i + 1, P.nx - 1), j1 = min(j + 1, P.ny - 1), kc = min(k, P.nz - 1);
+    const float* r00 = P.grid + ((long long)i * P.ny + j) * P.nz;
+    const float* r10 = P.grid + ((long long)i1 * P.ny + j) * P.nz;
+    const float* r01 = P.grid + ((long long)i * P.ny + j1) * P.nz;
+    const float* r11 = P.grid + ((long long)i1 * P.ny + j1) * P.nz;
+    const float g00 = __ldg(r00 + kc), g10 = __ldg(r10 + kc), g01 = __ldg(r01 + kc), g11 = __ldg(r11 + kc);
+    // the samples one step up in z: the next lane's, except for the run's last point
+    float n00 = __shfl_down_sync(0xffffffffu, g00, 1, 8), n10 = __shfl_down_sync(0xffffffffu, g10, 1, 8);
+    float n01 = __shfl_down_sync(0xffffffffu, g01, 1, 8), n11 = __shfl_down_sync(0xffffffffu, g11, 1, 8);
+    if (t == 7) {
+      const int kn = min(k + 1, P.nz - 1);
+      n00 = __ldg(r00 + kn); n10 = __ldg(r10 + kn); n01 = __ldg(r01 + kn); n11 = __ldg(r11 + kn);
+    }
+    const unsigned code = (unsigned)(codes >> (8 * t)) & 0xffu;
+    const unsigned flags = code & 7u, nt = code >> 3;
+    const unsigned long long below = codes & ((1ull << (8 * t)) - 1ull);
+    // ---- vertices on the point's own cut edges (halo rows are numbered, not emitted) ----
+    if (flags && i < P.x_emit) {
+      unsigned long long vb = (unsigned long long)P.vbase[run] + (unsigned)__popcll(below & 0x0707070707070707ull);
+      const double d0 = fabs((double)g00 - dlevel);
+      const float pbase[3] = {(float)(i + P.x_origin), (float)j, (float)k};
+      const float nb[3] = {g10, g01, n00};                       // the neighbour along x, y, z
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        if (flags & (1u << a)) {
+          if ((long long)vb < P.vcap) {    // capacity overflow: counted, not written (the caller re-runs with larger buffers)
+            const double d1 = fabs((double)nb[a] - dlevel);
+            // Lewiner's weights w = 1 / (eps + d): t = w1 / (w0 + w1) = (eps + d0) / ((eps + d0) + (eps + d1)), one
+            // division instead of three (equal to the last bit or two of the double, far below the float32 result)
+            const double e0 = (double)FLT_EPSILON + d0, e1 = (double)FLT_EPSILON + d1;
+            const double tt = e0 / (e0 + e1);
+            float pos[3] = {pbase[0], pbase[1], pbase[2]};
+            pos[a] = (float)((double)pbase[a] + tt);
+            float* o = P.verts + vb * 3;
+            o[0] = (pos[0] - P.voffset) * P.vscale;
+            o[1] = (pos[1] - P.voffset) * P.vscale;
+            o[2] = (pos[2] - P.voffset) * P.vscale;
+          }
+          ++vb;
+        }
+      }
+    }
+    // ---- triangles of the point's cell ----
+    if (nt) {
+      // corner c = x | y<<1 | z<<2
+      const unsigned cs = (unsigned)(g00 > level) | ((unsigned)(g10 > level) << 1) | ((unsigned)(g01 > level) << 2) |
+                          ((unsigned)(g11 > level) << 3) | ((unsigned)(n00 > level) << 4) | ((unsigned)(n10 > level) << 5) |
+                          ((unsigned)(n01 > level) << 6) | ((unsigned)(n11 > level) << 7);
+      // triangle base of the cell: the run's + the triangle counts of the points before it (byte sum by multiplication)
+      const unsigned long long tb = (unsigned long long)item.y +
+          ((((below >> 3) & 0x1f1f1f1f1f1f1f1full) * 0x0101010101010101ull) >> 56);
       const uint4 row = s_tri[cs];
-      const int8_t* edges = reinterpret_cast<const int8_t*>(&row);
       for (unsigned tr = 0; tr < nt; ++tr) {
         if ((long long)(tb + tr) >= P.fcap) break;
         int32_t* o = P.faces + (tb + tr) * 3;
@@ -378,8 +430,6 @@ __global__ void __launch_bounds__(kMcThreads) mc_faces_kernel(const __grid_const
           o[corner] = vertex_id(P, i + ed.y, j + ed.z, k + ed.w, ed.x);
         }
       }
-      (void)edges;
-      tb += nt;
     }
   }
 }
@@ -466,6 +516,11 @@ extern "C" int vtaco_marching_cubes(const vtaco_mc_args* a, void* stream) {
   P.level = a->level; P.level_keys = a->level_keys; P.level_ptr = a->level_ptr;
   P.n_level_keys = a->n_level_keys > 1 ? a->n_level_keys : 1;
   P.nzc = (a->nz + kMcRun - 1) / kMcRun;
+  P.nzc_shift = P.ny_shift = -1;
+  for (int sh = 0; sh < 31; ++sh) {
+    if (P.nzc == (1 << sh)) P.nzc_shift = sh;
+    if (P.ny == (1 << sh)) P.ny_shift = sh;
+  }
   P.nruns = (long long)a->nx * a->ny * P.nzc;
   P.nblocks = (int)((P.nruns + kMcBlockRuns - 1) / kMcBlockRuns);
   char* s = reinterpret_cast<char*>(a->scratch);
@@ -485,9 +540,9 @@ extern "C" int vtaco_marching_cubes(const vtaco_mc_args* a, void* stream) {
   VTACO_CUDA_CHECK(cudaMemsetAsync(P.state, 0, 8ll * P.nblocks + 16, st));
   mc_fused_kernel<<<P.nblocks, kMcThreads, 0, st>>>(P);
   if (P.emit) {
-    long long blocks = (long long)num_sms() * 4;
-    if (blocks > (P.nruns + kMcThreads - 1) / kMcThreads) blocks = (P.nruns + kMcThreads - 1) / kMcThreads;
-    mc_faces_kernel<<<(unsigned)blocks, kMcThreads, 0, st>>>(P);
+    long long blocks = (long long)num_sms() * 8;   // 8 lanes per work item; the kernel strides over the list
+    if (blocks > (P.nruns * 8 + kMcThreads - 1) / kMcThreads) blocks = (P.nruns * 8 + kMcThreads - 1) / kMcThreads;
+    mc_emit_kernel<<<(unsigned)blocks, kMcThreads, 0, st>>>(P);
   }
   VTACO_LAUNCH_CHECK();
   return VTACO_OK;
