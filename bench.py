@@ -268,7 +268,8 @@ def workload_config(nx, args):
                             'mesh': 'never leave their rank: marching cubes runs per slab (+2 halo rows) and only mesh '
                                     'pieces are gathered on rank 0 (device-side signalling over NVLink peer memory)'}[
                                 getattr(args, 'exchange', 'mesh')]),
-            'l2': 'flushed between timed steps (256 MiB write outside the step events)',
+            'l2': 'flushed between timed steps (256 MiB write outside the step events; N>1: followed by an untimed '
+                  'device-side rendezvous so that every rank\'s step event starts aligned)',
             'kernel_variant': args.variant,
             'unet3d_conv_math': 'e2e only: UNet3D runs on our tcgen05 implicit-GEMM kernels (csrc/conv3d.cu) in single-pass TF32 '
                                 'with fp32 accumulation - the arithmetic of the reference on a GPU (cuDNN, '
@@ -453,10 +454,20 @@ def run_ours(args, rank, local_rank, world):
     barrier()
     if world > 1 and graph is not None:
         graph.replay()          # untimed: the step's own device-side waits align the ranks after the host barrier
+    # N>1, mesh exchange: the L2 flush between the steps (a measurement artefact, outside the step events) takes a
+    # different time on every GPU, and the first rendezvous of the next step would charge the difference to the
+    # ranks that flushed faster.  An untimed device-side rendezvous (the 16-byte level exchange with neutral
+    # keys) after the flush starts every rank's step event aligned, like the barrier before the timed region.
+    align_keys = None
+    if world > 1 and graph is not None and args.exchange == 'mesh' and gen._mesh_ex is not None:
+        from vtaco_b200.conv_onet.generation import new_minmax_key
+        align_keys = new_minmax_key(dev)
     wall0 = time.perf_counter()
     with ClockSampler(local_rank) as clocks:
         for s in range(args.steps):
             flush.fill_(float(s))
+            if align_keys is not None:
+                gen._mesh_ex.level(align_keys)
             e0, e_dec, e1 = ev[s]
             e0.record()
             if graph is not None:

@@ -106,6 +106,10 @@ def test_library_exports_every_declared_symbol():
     for n in sorted(names):
         assert hasattr(L, n), 'missing export %s' % n
     assert L.vtaco_abi_version() == 1
+    # host-only size helpers: the Python mirror of the header macros must agree with the library
+    L.vtaco_decoder_tc_floats.restype = ctypes.c_int64
+    for nb in range(0, 9):
+        assert L.vtaco_decoder_tc_floats(nb) == _abi.dec_tc_floats(nb), nb
 
 
 def test_make_3d_grid_matches_reference():
