@@ -499,8 +499,8 @@ def run_ours(args, rank, local_rank, world):
     _vd = __import__('vtaco_b200.dist', fromlist=['slab'])
     x0, x1 = (_vd.slab_root(nx, rank, world, gen.root_rows) if (world > 1 and args.exchange == 'root')
               else _vd.slab(nx, rank, world))
-    if world > 1 and args.exchange == 'mesh':
-        x1 = min(x1 + 2, nx)              # the two halo rows every rank decodes in addition
+    if world > 1 and args.exchange == 'mesh' and not (gen.halo_from_peer and rank + 1 < world):
+        x1 = min(x1 + 2, nx)              # the two halo rows a rank decodes in addition when it does not read them from its neighbour
     if x1 <= x0:
         x0, x1 = 0, 2
     kq = (x1 - x0) * nx * nx

@@ -390,7 +390,8 @@ int vtaco_scatter_mean(const float* c, const int32_t* idx32, int32_t B, int64_t 
  * faces of cells in rows < x_emit are emitted / counted (V_numbered also counts the halo rows'),
  * so that a face may name a vertex id >= V: it is the (id - V)-th vertex of the NEXT slab.
  * Concatenating the pieces of consecutive slabs (ids + sum of the previous slabs' V) gives
- * exactly the mesh of the whole volume.  x_emit = 0 or nx: whole volume.
+ * exactly the mesh of the whole volume.  x_emit = 0 or nx: whole volume.  The halo rows may be read in place from
+ * another buffer (halo_grid / halo_rows) instead of being part of `grid`.
  * ------------------------------------------------------------------------- */
 typedef struct vtaco_mc_args {
   const float* grid;
@@ -410,6 +411,11 @@ typedef struct vtaco_mc_args {
   int32_t x_emit;              /* slab mode: rows [0, x_emit) are owned; 0 = all */
   int32_t x_origin;            /* slab mode: lattice row of grid row 0 (vertex x = local row + x_origin) */
   const float* level_ptr;      /* optional device float: the level (takes precedence; written by vtaco_exchange_level) */
+  /* slab mode, optional: the halo rows live somewhere else — rows [nx - halo_rows, nx) of the sub-volume are read
+   * from halo_grid ([halo_rows][ny][nz]; e.g. the NEXT rank's first owned rows, peer-mapped over NVLink) and `grid`
+   * holds only the first nx - halo_rows rows.  A rank then decodes its own rows only. */
+  const float* halo_grid;
+  int32_t halo_rows;
 } vtaco_mc_args;
 
 int64_t vtaco_mc_scratch_bytes(int32_t nx, int32_t ny, int32_t nz);

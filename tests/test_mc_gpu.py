@@ -122,20 +122,28 @@ def test_cuda_graph_paths_match_eager():
     assert similar(f2, f3)
 
 
-def _mc_pieces(vol_t, level, slabs):
+def _mc_pieces(vol_t, level, slabs, separate_halo=False):
     """slab-mode marching cubes on each x-slab (+ 2 halo rows), pieces concatenated with their bases —
-    the single-GPU emulation of the sharded extraction (csrc/mcubes.cu slab mode + exchange.cu's rebase)."""
+    the single-GPU emulation of the sharded extraction (csrc/mcubes.cu slab mode + exchange.cu's rebase).
+    separate_halo: the halo rows are a copy in another buffer, passed by address (vtaco_mc_args.halo_grid) —
+    what a rank does with the next rank's peer-mapped grid."""
     from vtaco_b200.mcubes import MarchingCubes
     ex = MarchingCubes('cuda')
     nx = vol_t.shape[0]
     vs, fs, base = [], [], 0
     for x0, x1 in slabs:
         xh = min(x1 + 2, nx)
-        v, f, counts = ex(vol_t[x0:xh], level, x_emit=x1 - x0, x_origin=x0, sync=False)
+        kw = {}
+        vol = vol_t[x0:xh]
+        if separate_halo and xh > x1:
+            other = vol_t[x1:xh].clone()
+            vol = vol_t[x0:x1].clone()          # nothing behind the slab's own rows
+            kw = {'halo': (other.data_ptr(), xh - x1)}
+        v, f, counts = ex(vol, level, x_emit=x1 - x0, x_origin=x0, sync=False, **kw)
         V, F, Vnum = [int(x) for x in counts[:3].cpu()]
         if V > v.shape[0] or F > f.shape[0]:
             ex._ensure(0, V + 16, F + 16)
-            v, f, counts = ex(vol_t[x0:xh], level, x_emit=x1 - x0, x_origin=x0, sync=False)
+            v, f, counts = ex(vol, level, x_emit=x1 - x0, x_origin=x0, sync=False, **kw)
         assert Vnum >= V
         vs.append(v[:V].clone())
         fs.append(f[:F].clone() + base)
@@ -157,9 +165,10 @@ def test_slab_pieces_concatenate_to_the_whole_mesh(name, slabs):
     vol = torch.from_numpy(fields()[name]).cuda()
     level = 0.0 if name != 'tiny' else 3.5
     v, f = marching_cubes(vol, level)
-    pv, pf = _mc_pieces(vol, level, slabs)
-    assert pv.shape == v.shape and pf.shape == f.shape
-    assert torch.equal(pf, f) and torch.equal(pv, v)
+    for separate_halo in (False, True):
+        pv, pf = _mc_pieces(vol, level, slabs, separate_halo)
+        assert pv.shape == v.shape and pf.shape == f.shape
+        assert torch.equal(pf, f) and torch.equal(pv, v)
 
 
 def test_slab_pieces_256_lattice():
@@ -177,8 +186,9 @@ def test_slab_pieces_256_lattice():
     grid, keys = gen.eval_lattice({'grid': torch.randn(1, 32, 64, 64, 64, device='cuda')})
     level = keys_to_level(keys)
     v, f = marching_cubes(grid, level)
-    pv, pf = _mc_pieces(grid, level, [(32 * r, 32 * r + 32) for r in range(8)])
-    assert f.shape[0] > 1000 and torch.equal(pf, f) and torch.equal(pv, v)
+    for separate_halo in (False, True):
+        pv, pf = _mc_pieces(grid, level, [(32 * r, 32 * r + 32) for r in range(8)], separate_halo)
+        assert f.shape[0] > 1000 and torch.equal(pf, f) and torch.equal(pv, v)
 
 
 def test_exchange_kernels_world_1():

@@ -68,6 +68,7 @@ class McArgs(C.Structure):
         ('counts', C.c_void_p),
         ('voffset', C.c_float), ('vscale', C.c_float), ('phase', C.c_int32),
         ('x_emit', C.c_int32), ('x_origin', C.c_int32), ('level_ptr', C.c_void_p),
+        ('halo_grid', C.c_void_p), ('halo_rows', C.c_int32),
     ]
 
 

@@ -106,6 +106,8 @@ class Generator3D(object):
                                       '(SURVEY.md §2 row 9)')
         self._mc = None
         self._grid = None
+        self._shared_grid = None
+        self.halo_from_peer = True    # sharded extraction: read the two halo rows from the next rank instead of decoding them
         self._keys = None
         self._keys_init = None
         self._pin = None
@@ -302,25 +304,34 @@ class Generator3D(object):
         dev = self.device
         dec = self.model.decoder
         rank, world = vdist.rank_world(group)
-        if self._grid is None or self._grid.shape[0] != nx:
-            self._grid = torch.empty((nx, nx, nx), dtype=torch.float32, device=dev)
-            self._axis = dense_axis(nx, self.padding, dev)
-        if self._keys is None:
-            self._keys_init = new_minmax_key(dev)
-            self._keys = self._keys_init.clone()
         if self._mesh_ex is None or self._mesh_ex.gather != self.mesh_gather:
             cap = max(1024, 12 * nx * nx)
             self._mesh_ex = vdist.MeshExchange(dev, group, cap, 2 * cap, gather=self.mesh_gather)
         ex = self._mesh_ex
+        if self._shared_grid is None or self._shared_grid[0].shape[0] != nx:
+            # the lattice grid lives in symmetric memory: the halo rows of a slab are the next rank's first rows and
+            # are read in place over NVLink by marching cubes instead of being decoded a second time
+            self._shared_grid = ex.shared_grid(nx)
+            self._axis = dense_axis(nx, self.padding, dev)
+        grid, grid_ptrs = self._shared_grid
+        self._grid = grid
+        if self._keys is None:
+            self._keys_init = new_minmax_key(dev)
+            self._keys = self._keys_init.clone()
         x0, x1 = vdist.slab(nx, rank, world)
         xh = min(x1 + 2, nx)          # two halo rows: the next slab's first row and the row that numbers its vertices
+        # ... which the next rank decodes anyway, if it owns them both (always, unless there are about as many ranks as rows)
+        peer_halo = self.halo_from_peer and rank + 1 < world and xh > x1 and vdist.slab(nx, rank + 1, world)[1] >= xh
+        x_dec = x1 if peer_halo else xh
         with torch.no_grad():
             if x1 > x0:
-                dec.forward_dense(c, nx, x0=x0, x1=xh, use_img=self.with_img, c_img=c_img_all, tips=tips,
-                                  out=self._grid, minmax_key=self._keys, axis=self._axis)
-            ex.level(self._keys)          # publishes (min,max), waits for every rank's, resets the keys
+                dec.forward_dense(c, nx, x0=x0, x1=x_dec, use_img=self.with_img, c_img=c_img_all, tips=tips,
+                                  out=grid, minmax_key=self._keys, axis=self._axis)
+            # publishes (min,max), waits for every rank's — i.e. for every rank's decode of this step — and resets the keys
+            ex.level(self._keys)
             if x1 > x0:
-                v, f, counts = self.mc(self._grid[x0:xh], level_ptr=ex.level_ptr, x_emit=x1 - x0, x_origin=x0,
+                halo = (grid_ptrs[rank + 1] + x1 * nx * nx * 4, xh - x1) if peer_halo else None
+                v, f, counts = self.mc(grid[x0:x_dec], level_ptr=ex.level_ptr, x_emit=x1 - x0, x_origin=x0, halo=halo,
                                        voffset=np.float32(nx / 2), vscale=np.float32((1 + self.padding) / nx), sync=False)
             else:                         # more ranks than row pairs: an empty piece
                 self.mc._ensure(0, 16, 16)

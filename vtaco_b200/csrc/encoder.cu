@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(kET) enc_block_kernel(const __grid_constant__ 
   if (FIRST)
     for (int i = threadIdx.x; i < 256 / 4; i += kET)
       reinterpret_cast<float4*>(sW + ENC_BLOCK_STRIDE)[i] = __ldg(reinterpret_cast<const float4*>(P.W) + i);
-  __syncthreads();
+  if (FIRST) __syncthreads();   // fc_pos is read right away; otherwise the weight fill overlaps the input gather below
 
   const int tid = threadIdx.x, lane = tid & 31, col0 = tid & ~31;
   const long long nb0 = (long long)blockIdx.x * kET;
@@ -206,12 +206,14 @@ __global__ void __launch_bounds__(kET) enc_block_kernel(const __grid_constant__ 
       xcol[j * kES] = fmaf(Wp[128 + j], pz, fmaf(Wp[64 + j], py, fmaf(Wp[j], px, Wp[ENC_OFF_BPOS + j])));
   } else {
     const float* netin = P.net[net_in];
-    // 8 rows per batch: all global loads of a batch are in flight together (the row-at-a-time loop paid one
-    // L2 round trip per row and key — most of this kernel's time at the shipped T = 3 640)
-    for (int i0 = 0; i0 < 32; i0 += 8) {
-      float a[8], s[8];
+    // 16 rows per batch: all global loads of a batch are in flight together (the row-at-a-time loop paid one
+    // L2 round trip per row and key; ncu at the shipped T = 3 640: with 8 rows per batch the four dependent
+    // round trips were still ~40 % of the kernel's warp samples, one warp per scheduler has nothing to hide them)
+    constexpr int kRows = 16;
+    for (int i0 = 0; i0 < 32; i0 += kRows) {
+      float a[kRows], s[kRows];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
+      for (int u = 0; u < kRows; ++u) {
         const int i = i0 + u;
         const long long ni = nb0 + col0 + i;
         const bool ok = ni < P.n;                       // warp-uniform
@@ -228,7 +230,7 @@ __global__ void __launch_bounds__(kET) enc_block_kernel(const __grid_constant__ 
         }
       }
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
+      for (int u = 0; u < kRows; ++u) {
         const int i = i0 + u;
         if (nb0 + col0 + i < P.n) {
           sX[lane * kES + col0 + i] = a[u];
@@ -237,7 +239,8 @@ __global__ void __launch_bounds__(kET) enc_block_kernel(const __grid_constant__ 
       }
     }
   }
-  __syncwarp();
+  if (!FIRST) __syncthreads();   // weights in shared memory (and the warp's input columns)
+  else __syncwarp();
 
   float h[32], o[32];
 #pragma unroll

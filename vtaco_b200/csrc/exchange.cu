@@ -27,6 +27,7 @@ struct ExCtrl {
   float pad_;
   long long base[2];     // vertex / face base of this rank's piece
   long long total[2];    // mesh totals
+  uint32_t ticket;       // blocks of the mesh-exchange kernel that have finished (the last one signals, then resets it)
 };
 static_assert(sizeof(ExCtrl) <= VTACO_EXCHANGE_CTRL_BYTES, "control block too large");
 static_assert(offsetof(ExCtrl, level) == VTACO_EXCHANGE_LEVEL_OFFSET, "level offset");
@@ -97,105 +98,128 @@ __global__ void __launch_bounds__(32) exchange_level_kernel(ExPeers X, int32_t* 
   }
 }
 
-// (2) publish (V,F), wait for everyone's, exclusive scan -> this rank's bases and the totals.
-__global__ void __launch_bounds__(32) exchange_counts_kernel(ExPeers X, const long long* counts) {
+struct ExDest { float* v[8]; int32_t* f[8]; long long vcap, fcap; };
+
+// ---- (2)+(3) in ONE kernel: count exchange, copy of the piece with BULK stores, completion signal ----
+// A mesh piece is ~1-4 MB.  Fine-grained stores from the SMs sustain only ~140 GB/s of NVLink ingress per GPU
+// (measured, round 1), i.e. ~45 us for the seven pieces that arrive at rank 0 on an 8-GPU node — as long as a
+// slab's marching cubes.  Here a block stages 16 KB of the piece in shared memory (faces are rebased on the way)
+// and one thread sends it with a TMA bulk store (cp.async.bulk.global.shared::cta), the access size the copy
+// engines use; three launches and their dependency latency become one.
+constexpr int kPushChunk = 4096;               // 4-byte elements per bulk store (16 KB)
+
+__device__ __forceinline__ void bulk_store(void* dst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
+               "r"((uint32_t)__cvta_generic_to_shared(smem_src)), "r"(bytes)
+               : "memory");
+}
+
+// elements [0, n) of src -> dst (+ add) at every destination d[r] + off (element offsets); block-cooperative.
+template <typename T, bool ADD>
+__device__ __forceinline__ void push_bulk(T* const* dsts, int n_dst, long long off, const T* __restrict__ src,
+                                          long long n, T add, T* sbuf) {
+  if (n <= 0) return;
+  auto put = [&](T v) { return ADD ? (T)(v + add) : v; };      // vertices are copied bit for bit (no "+ 0.0f": -0.0f)
+  // all destinations share the alignment of `off` (their bases are allocation-aligned): scalar head up to 16 bytes
+  long long head = (long long)((16 - ((reinterpret_cast<uintptr_t>(dsts[0] + off)) & 15)) & 15) / 4;
+  if (head > n) head = n;
+  const long long body = (n - head) / 4 * 4;
+  if (blockIdx.x == 0) {
+    for (int r = 0; r < n_dst; ++r) {
+      T* d = dsts[r] + off;
+      for (long long i = threadIdx.x; i < head; i += blockDim.x) d[i] = put(src[i]);
+      for (long long i = head + body + threadIdx.x; i < n; i += blockDim.x) d[i] = put(src[i]);
+    }
+  }
+  for (long long c0 = (long long)blockIdx.x * kPushChunk; c0 < body; c0 += (long long)gridDim.x * kPushChunk) {
+    const int len = (int)min((long long)kPushChunk, body - c0);            // multiple of 4 elements
+    for (int i = threadIdx.x; i < len; i += blockDim.x) sbuf[i] = put(src[head + c0 + i]);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");           // generic-proxy writes -> visible to the bulk copy
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int r = 0; r < n_dst; ++r) bulk_store(dsts[r] + off + head + c0, sbuf, (uint32_t)len * 4u);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");       // the staging buffer may be overwritten
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) exchange_mesh_kernel(ExPeers X, ExDest D, const long long* counts,
+                                                            const float* __restrict__ verts,
+                                                            const int32_t* __restrict__ faces, long long* total_out) {
+  __shared__ __align__(128) int32_t sbuf[kPushChunk];
+  __shared__ long long s_base[4];
+  __shared__ int s_ok, s_last;
   ExCtrl* me = X.c[X.rank];
-  const int lane = threadIdx.x;
-  const uint32_t seq = me->seq_cnt + 1;
+  const int lane = threadIdx.x & 31;
+  const uint32_t seq = me->seq_cnt + 1;        // local state: advanced by the last block only, after every block has read it
   const int par = seq & 1;
-  const long long v = counts[0], f = counts[1];
-  if (lane < X.world) {
-    ExCtrl* peer = X.c[lane];
-    volatile long long* c = peer->cnt[par][X.rank];
-    c[0] = v;
-    c[1] = f;
-    __threadfence_system();
-    st_release_sys(&peer->cnt_flag[par][X.rank], seq);
+  // ---- (2) publish (V,F) (block 0), wait for everyone's (every block, on its own copy of the table), exclusive scan ----
+  if (threadIdx.x < 32) {
+    const long long v = counts[0], f = counts[1];
+    if (blockIdx.x == 0 && lane < X.world) {
+      ExCtrl* peer = X.c[lane];
+      volatile long long* c = peer->cnt[par][X.rank];
+      c[0] = v;
+      c[1] = f;
+      __threadfence_system();
+      st_release_sys(&peer->cnt_flag[par][X.rank], seq);
+    }
+    bool ok = true;
+    long long pv = 0, pf = 0;
+    if (lane < X.world) {
+      ok = wait_flag(&me->cnt_flag[par][lane], seq);
+      const volatile long long* c = me->cnt[par][lane];
+      pv = c[0];
+      pf = c[1];
+    }
+    long long bv = 0, bf = 0, tv = 0, tf = 0;
+    for (int r = 0; r < X.world; ++r) {
+      const long long rv = __shfl_sync(0xffffffffu, pv, r), rf = __shfl_sync(0xffffffffu, pf, r);
+      if (r < X.rank) { bv += rv; bf += rf; }
+      tv += rv; tf += rf;
+    }
+    const bool all_ok = __all_sync(0xffffffffu, ok);
+    if (lane == 0) { s_base[0] = bv; s_base[1] = bf; s_base[2] = tv; s_base[3] = tf; s_ok = all_ok ? 1 : 0; }
   }
+  __syncthreads();
+  const long long bv = s_base[0], bf = s_base[1];
+  // ---- (3a) the piece -> every destination at its base (capacity overflow: truncated, the totals tell) ----
+  float* dv[8];
+  int32_t* df[8];
+  int n_dst = 0;
+  for (int r = 0; r < X.world; ++r)
+    if (D.v[r] && D.f[r]) { dv[n_dst] = D.v[r]; df[n_dst] = D.f[r]; ++n_dst; }
+  long long nv3 = counts[0] * 3, nf3 = counts[1] * 3;
+  if (nv3 > (D.vcap - bv) * 3) nv3 = (D.vcap - bv) * 3;
+  if (nf3 > (D.fcap - bf) * 3) nf3 = (D.fcap - bf) * 3;
+  push_bulk<float, false>(dv, n_dst, bv * 3, verts, nv3, 0.0f, reinterpret_cast<float*>(sbuf));
+  push_bulk<int32_t, true>(df, n_dst, bf * 3, faces, nf3, (int32_t)bv, sbuf);
+  if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // this block's bulk stores have been performed
+  __threadfence_system();
+  __syncthreads();
+  // ---- (3b) the last block tells every destination that the piece has landed; a destination waits for all pieces ----
+  if (threadIdx.x == 0) {
+    const unsigned done = atomicAdd(&me->ticket, 1u);
+    s_last = (done == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last || threadIdx.x >= 32) return;
+  __threadfence_system();
+  const uint32_t dseq = me->seq_done + 1;
+  if (lane < X.world && D.v[lane]) st_release_sys(&X.c[lane]->done_flag[X.rank], dseq);
   bool ok = true;
-  long long pv = 0, pf = 0;
-  if (lane < X.world) {
-    ok = wait_flag(&me->cnt_flag[par][lane], seq);
-    const volatile long long* c = me->cnt[par][lane];
-    pv = c[0];
-    pf = c[1];
-  }
-  long long bv = 0, bf = 0, tv = 0, tf = 0;
-  for (int r = 0; r < X.world; ++r) {
-    const long long rv = __shfl_sync(0xffffffffu, pv, r), rf = __shfl_sync(0xffffffffu, pf, r);
-    if (r < X.rank) { bv += rv; bf += rf; }
-    tv += rv; tf += rf;
-  }
+  if (D.v[X.rank] && lane < X.world) ok = wait_flag(&me->done_flag[lane], dseq);
   const bool all_ok = __all_sync(0xffffffffu, ok);
   if (lane == 0) {
     me->base[0] = bv; me->base[1] = bf;
-    me->total[0] = tv; me->total[1] = tf;
+    me->total[0] = s_base[2]; me->total[1] = s_base[3];
     me->seq_cnt = seq;
-    if (!all_ok) me->err = 1;
-  }
-}
-
-struct ExDest { float* v[8]; int32_t* f[8]; long long vcap, fcap; };
-
-// (3a) copy this rank's piece into every destination at its base; faces are rebased.  Remote stores are
-// 16 bytes wide (fine-grained 4-byte stores sustain only ~40 GB/s over NVLink): the destination is aligned up
-// to 16 B with a scalar head, the local source is read with scalar loads (it is misaligned by then).
-template <typename T, bool ADD>
-__device__ __forceinline__ void push_range(T* __restrict__ dst, const T* __restrict__ src, long long n, T add_,
-                                           long long t0, long long stride) {
-  if (n <= 0) return;
-  const T add = ADD ? add_ : T(0);
-  auto put = [&](T v) { return ADD ? (T)(v + add) : v; };      // vertices are copied bit for bit (no "+ 0.0f": -0.0f)
-  long long head = (long long)((16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15) / 4;
-  if (head > n) head = n;
-  const long long n4 = (n - head) / 4;
-  for (long long i = t0; i < head; i += stride) dst[i] = put(src[i]);
-  struct alignas(16) V4 { T a, b, c, d; };
-  V4* d4 = reinterpret_cast<V4*>(dst + head);
-  for (long long i = t0; i < n4; i += stride) {
-    const T* q = src + head + 4 * i;
-    V4 v;
-    v.a = put(q[0]); v.b = put(q[1]); v.c = put(q[2]); v.d = put(q[3]);
-    d4[i] = v;
-  }
-  for (long long i = head + 4 * n4 + t0; i < n; i += stride) dst[i] = put(src[i]);
-}
-
-__global__ void __launch_bounds__(256) exchange_push_kernel(ExPeers X, ExDest D, const long long* counts,
-                                                            const float* __restrict__ verts,
-                                                            const int32_t* __restrict__ faces) {
-  const ExCtrl* me = X.c[X.rank];
-  const long long bv = me->base[0], bf = me->base[1];
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  for (int r = 0; r < X.world; ++r) {
-    float* dv = D.v[r];
-    int32_t* df = D.f[r];
-    if (!dv || !df) continue;
-    // capacity overflow: truncated, the totals tell
-    long long nv3 = counts[0] * 3, nf3 = counts[1] * 3;
-    if (nv3 > (D.vcap - bv) * 3) nv3 = (D.vcap - bv) * 3;
-    if (nf3 > (D.fcap - bf) * 3) nf3 = (D.fcap - bf) * 3;
-    push_range<float, false>(dv + bv * 3, verts, nv3, 0.0f, t0, stride);
-    push_range<int32_t, true>(df + bf * 3, faces, nf3, (int32_t)bv, t0, stride);
-  }
-  __threadfence_system();
-}
-
-// (3b) tell every destination that this rank's piece has landed; a destination waits for all
-// pieces and publishes the totals.
-__global__ void __launch_bounds__(32) exchange_done_kernel(ExPeers X, ExDest D, long long* total_out) {
-  ExCtrl* me = X.c[X.rank];
-  const int lane = threadIdx.x;
-  const uint32_t seq = me->seq_done + 1;
-  if (lane < X.world && D.v[lane]) st_release_sys(&X.c[lane]->done_flag[X.rank], seq);
-  bool ok = true;
-  if (D.v[X.rank] && lane < X.world) ok = wait_flag(&me->done_flag[lane], seq);
-  const bool all_ok = __all_sync(0xffffffffu, ok);
-  if (lane == 0) {
-    me->seq_done = seq;
-    if (!all_ok) me->err = 1;
-    if (total_out) { total_out[0] = me->total[0]; total_out[1] = me->total[1]; }
+    me->seq_done = dseq;
+    me->ticket = 0;
+    if (!all_ok || !s_ok) me->err = 1;
+    if (total_out) { total_out[0] = s_base[2]; total_out[1] = s_base[3]; }
   }
 }
 
@@ -241,10 +265,9 @@ extern "C" int vtaco_exchange_mesh(const vtaco_exchange* ex, const vtaco_mesh_pi
   D.vcap = m->vertex_capacity;
   D.fcap = m->face_capacity;
   cudaStream_t s = (cudaStream_t)stream;
-  exchange_counts_kernel<<<1, 32, 0, s>>>(X, reinterpret_cast<const long long*>(m->counts));
-  exchange_push_kernel<<<num_sms(), 256, 0, s>>>(X, D, reinterpret_cast<const long long*>(m->counts), m->vertices,
-                                                 m->faces);
-  exchange_done_kernel<<<1, 32, 0, s>>>(X, D, reinterpret_cast<long long*>(m->total_counts));
+  // all blocks spin on the count flags, so they must be co-resident: one block per SM at most
+  exchange_mesh_kernel<<<num_sms(), 256, 0, s>>>(X, D, reinterpret_cast<const long long*>(m->counts), m->vertices,
+                                                 m->faces, reinterpret_cast<long long*>(m->total_counts));
   VTACO_LAUNCH_CHECK();
   return VTACO_OK;
 }

@@ -43,6 +43,8 @@ constexpr int kMcSuper = 256;     // blocks per super-block of the two-level pre
 
 struct McParams {
   const float* grid;
+  const float* halo;              // rows >= x_local are read from here (row r -> halo + (r - x_local) * ny * nz), or NULL
+  int x_local;                    // rows of the sub-volume that live in `grid` (== nx without a separate halo)
   int nx, ny, nz, nzc;            // nzc = ceil(nz / kMcRun) runs per (x,y) row
   int nzc_shift, ny_shift;        // log2 when the extent is a power of two (run -> coordinates by shifts), else -1
   int x_emit;                     // rows [0, x_emit) emit vertices / faces (== nx: whole volume)
@@ -89,12 +91,18 @@ __device__ __forceinline__ void run_coords(const McParams& P, long long run, int
   k0 = kc * kMcRun;
 }
 
+// z-row (i,j) of the sub-volume: the slab's own rows, or the halo rows kept elsewhere (the next rank's grid)
+__device__ __forceinline__ const float* mc_row(const McParams& P, int i, int j) {
+  return i < P.x_local ? P.grid + ((long long)i * P.ny + j) * P.nz
+                       : P.halo + ((long long)(i - P.x_local) * P.ny + j) * P.nz;
+}
+
 // "above" bits of kMcRun+1 consecutive z samples of row (i,j), bit t <-> k0+t; rows or samples
 // outside the lattice replicate the last valid sample (their cells/edges are masked out later).
 __device__ __forceinline__ unsigned row_bits(const McParams& P, int i, int j, int k0, float level) {
   i = min(i, P.nx - 1);
   j = min(j, P.ny - 1);
-  const float* row = P.grid + ((long long)i * P.ny + j) * P.nz;
+  const float* row = mc_row(P, i, j);
   unsigned bits = 0;
   if ((P.nz & 7) == 0) {   // uniform over the grid: the last run of a row takes this path too (a per-lane
                            // test sent one lane of EVERY warp through the scalar path below: 750 instructions per thread)
@@ -369,10 +377,10 @@ __global__ void __launch_bounds__(kMcThreads) mc_emit_kernel(const __grid_consta
     // samples of the four z-rows at this point (rows / samples outside the lattice replicate the last valid one,
     // as in row_bits: their cells / edges carry no flags)
     const int i1 = min(i + 1, P.nx - 1), j1 = min(j + 1, P.ny - 1), kc = min(k, P.nz - 1);
-    const float* r00 = P.grid + ((long long)i * P.ny + j) * P.nz;
-    const float* r10 = P.grid + ((long long)i1 * P.ny + j) * P.nz;
-    const float* r01 = P.grid + ((long long)i * P.ny + j1) * P.nz;
-    const float* r11 = P.grid + ((long long)i1 * P.ny + j1) * P.nz;
+    const float* r00 = mc_row(P, i, j);
+    const float* r10 = mc_row(P, i1, j);
+    const float* r01 = mc_row(P, i, j1);
+    const float* r11 = mc_row(P, i1, j1);
     const float g00 = __ldg(r00 + kc), g10 = __ldg(r10 + kc), g01 = __ldg(r01 + kc), g11 = __ldg(r11 + kc);
     // the samples one step up in z: the next lane's, except for the run's last point
     float n00 = __shfl_down_sync(0xffffffffu, g00, 1, 8), n10 = __shfl_down_sync(0xffffffffu, g10, 1, 8);
@@ -510,7 +518,10 @@ extern "C" int vtaco_marching_cubes(const vtaco_mc_args* a, void* stream) {
     return VTACO_ERR_INVALID_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   McParams P = {};
+  if (a->halo_rows < 0 || a->halo_rows >= a->nx || (a->halo_rows > 0 && !a->halo_grid)) return VTACO_ERR_INVALID_ARG;
   P.grid = a->grid; P.nx = a->nx; P.ny = a->ny; P.nz = a->nz; P.npts = n;
+  P.halo = a->halo_rows > 0 ? a->halo_grid : nullptr;
+  P.x_local = a->nx - a->halo_rows;
   P.x_emit = a->x_emit > 0 ? a->x_emit : a->nx;
   P.x_origin = a->x_origin;
   P.level = a->level; P.level_keys = a->level_keys; P.level_ptr = a->level_ptr;

@@ -215,6 +215,16 @@ class MeshExchange(object):
             return True
         return False
 
+    def shared_grid(self, nx):
+        """(nx,nx,nx) lattice grid in symmetric memory and every rank's address of it (collective)."""
+        import torch.distributed._symmetric_memory as symm
+        grid = symm.empty((nx, nx, nx), dtype=torch.float32, device=self.device)
+        h = symm.rendezvous(grid, self.group)
+        ptrs = [int(p) + int(getattr(h, 'offset', 0)) for p in h.buffer_ptrs]
+        assert ptrs[self.rank] == grid.data_ptr(), 'symmetric buffer pointer mismatch'
+        self._grid_handle = h
+        return grid, ptrs
+
     def level(self, keys):
         from . import _abi
         import ctypes as C

@@ -46,7 +46,7 @@ class MarchingCubes(object):
             self._faces = torch.empty((int(fcap), 3), dtype=torch.int32, device=self.device)
 
     def __call__(self, volume, level=None, level_keys=None, voffset=0.0, vscale=1.0, sync=True,
-                 x_emit=None, x_origin=0, level_ptr=None):
+                 x_emit=None, x_origin=0, level_ptr=None, halo=None):
         """volume: (nx,ny,nz) float32 CUDA tensor (axis0 = x).  level: float, or None ->
         0.5*(min+max) (from `level_keys` if the decoder tracked them, else computed here);
         `level_ptr`: address of a device float holding the level (multi-GPU exchange).
@@ -54,19 +54,28 @@ class MarchingCubes(object):
         (valid until the next call) — or, with sync=False, the un-trimmed buffers and the
         device counter tensor (int64[4]: V, F, numbered vertices, -).
         Slab mode (`x_emit` rows owned, the rest of the volume are halo rows, `x_origin` = lattice
-        row of volume[0]): include/vtaco_b200.h, vtaco_marching_cubes."""
+        row of volume[0]): include/vtaco_b200.h, vtaco_marching_cubes.  `halo=(device address, rows)`:
+        the halo rows are not part of `volume` but are read in place from another (ny,nz)-row buffer —
+        the next rank's grid, peer-mapped (vtaco_mc_args.halo_grid)."""
         _abi.require_cuda(volume, 'volume')
         if volume.dim() != 3 or not volume.is_contiguous():
             raise ValueError('volume must be a contiguous (nx,ny,nz) tensor')
         L = _abi.lib()
         nx, ny, nz = volume.shape
-        n = nx * ny * nz
+        halo_ptr, halo_rows = (int(halo[0]), int(halo[1])) if halo is not None else (0, 0)
+        if halo_rows:
+            if level_ptr is None and level is None and level_keys is None:
+                raise ValueError('a separate halo needs an explicit level (the min/max scan covers `volume` only)')
+            nx += halo_rows
+        n = volume.numel()
         nbytes = L.vtaco_mc_scratch_bytes(nx, ny, nz)
         vcap = self._verts.size(0) if self._verts is not None else max(1024, 12 * max(nx * ny, ny * nz, nx * nz))
         fcap = self._faces.size(0) if self._faces is not None else 2 * vcap
         self._ensure(nbytes, vcap, fcap)
         a = _abi.McArgs()
         a.grid, a.nx, a.ny, a.nz = volume.data_ptr(), nx, ny, nz
+        if halo_rows:
+            a.halo_grid, a.halo_rows = halo_ptr, halo_rows
         st = _abi.stream_ptr(self.device)
         with torch.cuda.device(self.device):
             if level_ptr is not None:
