@@ -12,7 +12,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, 'vtaco_b200', 'lib', 'libvtaco_b200.so')
-KEYS = ['UTCHMMA', 'UTCBAR', 'LDTM', 'STTM', 'SYNCS', 'ELECT', 'FFMA2', 'FFMA', 'REDG', 'ATOMG', 'LDS', 'LDG', 'STG']
+KEYS = ['UTCHMMA', 'UTCBAR', 'LDTM', 'STTM', 'SYNCS', 'ELECT', 'UBLKCP', 'FFMA2', 'FADD2', 'FFMA', 'REDG', 'ATOMG', 'LDS', 'LDG', 'STG']
 
 
 def main():
