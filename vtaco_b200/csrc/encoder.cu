@@ -176,46 +176,103 @@ __device__ __forceinline__ void scatter_rows(const float* __restrict__ sX, int c
 //   FIRST : x = fc_pos(p)                                   pointnet.py:154,156
 //   else  : x = cat[net, pool_local(net)]                   pointnet.py:157-160
 // and the scatter of its output into the next pooling buffer.
+//
+// FOUR warps per group of 32 points: warp q computes output channels [8q, 8q+8) of every layer for the 32
+// points (lane == point), the inputs / hidden activations are shared through shared-memory columns.  The first
+// version gave a point to one thread: 5 120 dependent-ish FMAs per thread and, at the shipped T = 3 640, 29 CTAs of
+// one warp per scheduler — 40 us per block, latency-bound (ncu: issue slots 15 %, the rest waiting).  Per output
+// channel the accumulation order over k is unchanged, so the results are bit-identical to that version.
+constexpr int kEG = 32;          // points per group
+constexpr int kEGS = kEG + 1;    // shared column stride (conflict-free for lane == point and lane == channel)
+constexpr size_t kEncBlockSmem = (ENC_BLOCK_STRIDE + 256 + 96 * kEGS) * sizeof(float);
+
+__device__ __forceinline__ void axpy8(float (&acc)[8], const float* __restrict__ Wk, float x) {
+  const float4 w0 = reinterpret_cast<const float4*>(Wk)[0], w1 = reinterpret_cast<const float4*>(Wk)[1];
+  acc[0] = fmaf(w0.x, x, acc[0]); acc[1] = fmaf(w0.y, x, acc[1]); acc[2] = fmaf(w0.z, x, acc[2]); acc[3] = fmaf(w0.w, x, acc[3]);
+  acc[4] = fmaf(w1.x, x, acc[4]); acc[5] = fmaf(w1.y, x, acc[5]); acc[6] = fmaf(w1.z, x, acc[6]); acc[7] = fmaf(w1.w, x, acc[7]);
+}
+
+// scatter_rows for points [i0, i1) of a 32-point group whose columns start at sX with stride `cs`
+template <bool MEAN>
+__device__ __forceinline__ void scatter_rows_range(const float* __restrict__ sX, int cs, int i0, int i1, long long n0,
+                                                   long long nmax, int lane, int nkeys, const int (&myslot)[4],
+                                                   float* const (&dst)[4], float* __restrict__ row_out) {
+  int cur[4] = {-1, -1, -1, -1};
+  float val[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int i = i0; i < i1; ++i) {
+    const long long ni = n0 + i;
+    if (ni >= nmax) break;  // uniform
+    const float v = sX[lane * cs + i];
+    if (row_out) row_out[ni * 32 + lane] = v;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (k < nkeys && dst[k]) {
+        const int s = __shfl_sync(kFullMask, myslot[k], i);
+        if (s != cur[k]) {
+          if (cur[k] >= 0) {
+            if (MEAN) atomicAdd(dst[k] + (long long)cur[k] * 32 + lane, val[k]);
+            else atomic_max_float(dst[k] + (long long)cur[k] * 32 + lane, val[k]);
+          }
+          cur[k] = s;
+          val[k] = v;
+        } else {
+          val[k] = MEAN ? (val[k] + v) : fmaxf(val[k], v);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (k < nkeys && dst[k] && cur[k] >= 0) {
+      if (MEAN) atomicAdd(dst[k] + (long long)cur[k] * 32 + lane, val[k]);
+      else atomic_max_float(dst[k] + (long long)cur[k] * 32 + lane, val[k]);
+    }
+  }
+}
+
 template <bool FIRST>
-__global__ void __launch_bounds__(kET) enc_block_kernel(const __grid_constant__ EncParams P, int blk, int r_read,
-                                                        int r_write, int r_init, int net_in, int net_out) {
+__global__ void __launch_bounds__(128) enc_block_kernel(const __grid_constant__ EncParams P, int blk, int r_read,
+                                                        int r_write, int r_init, int net_in, int net_out,
+                                                        long long n_groups) {
   extern __shared__ __align__(16) float esm[];
   float* sW = esm;                          // block weights (5184) [+ fc_pos 256]
-  float* sX = sW + ENC_BLOCK_STRIDE + 256;  // [64][kES]
+  float* sX = sW + ENC_BLOCK_STRIDE + 256;  // [64][kEGS] inputs, later [32][kEGS] outputs
+  float* sH = sX + 64 * kEGS;               // [32][kEGS] hidden activations
   const float* Wg = P.W + ENC_OFF_BLOCKS + (long long)blk * ENC_BLOCK_STRIDE;
-  for (int i = threadIdx.x; i < ENC_BLOCK_STRIDE / 4; i += kET)
+  for (int i = threadIdx.x; i < ENC_BLOCK_STRIDE / 4; i += 128)
     reinterpret_cast<float4*>(sW)[i] = __ldg(reinterpret_cast<const float4*>(Wg) + i);
-  if (FIRST)
-    for (int i = threadIdx.x; i < 256 / 4; i += kET)
-      reinterpret_cast<float4*>(sW + ENC_BLOCK_STRIDE)[i] = __ldg(reinterpret_cast<const float4*>(P.W) + i);
-  if (FIRST) __syncthreads();   // fc_pos is read right away; otherwise the weight fill overlaps the input gather below
-
-  const int tid = threadIdx.x, lane = tid & 31, col0 = tid & ~31;
-  const long long nb0 = (long long)blockIdx.x * kET;
-  const long long n = nb0 + tid;
-  const bool valid = n < P.n;
-  int myslot[4] = {0, 0, 0, 0};
-  for (int k = 0; k < P.nkeys; ++k) myslot[k] = valid ? P.slot[k][n] : 0;
-
-  float* xcol = sX + tid;
   if (FIRST) {
-    const float* Wp = sW + ENC_BLOCK_STRIDE;
-    const float px = valid ? P.p[n * 3] : 0.f, py = valid ? P.p[n * 3 + 1] : 0.f, pz = valid ? P.p[n * 3 + 2] : 0.f;
+    for (int i = threadIdx.x; i < 256 / 4; i += 128)
+      reinterpret_cast<float4*>(sW + ENC_BLOCK_STRIDE)[i] = __ldg(reinterpret_cast<const float4*>(P.W) + i);
+    __syncthreads();   // fc_pos is read right away; otherwise the weight fill overlaps the first input gather
+  }
+  const int tid = threadIdx.x, lane = tid & 31, q = tid >> 5;
+  float* dst[4] = {nullptr, nullptr, nullptr, nullptr};
+  if (r_write >= 0)
+    for (int k = 0; k < P.nkeys; ++k) dst[k] = P.pool[r_write][k];
+
+  for (long long grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+    const long long n0 = grp * kEG;
+    const long long n = n0 + lane;
+    const bool valid = n < P.n;
+    int myslot[4] = {0, 0, 0, 0};
+    for (int k = 0; k < P.nkeys; ++k) myslot[k] = valid ? P.slot[k][n] : 0;
+
+    if (FIRST) {   // lane == point: channels [16q, 16q+16) of fc_pos(p)
+      const float* Wp = sW + ENC_BLOCK_STRIDE;
+      const float px = valid ? P.p[n * 3] : 0.f, py = valid ? P.p[n * 3 + 1] : 0.f, pz = valid ? P.p[n * 3 + 2] : 0.f;
 #pragma unroll 8
-    for (int j = 0; j < 64; ++j)
-      xcol[j * kES] = fmaf(Wp[128 + j], pz, fmaf(Wp[64 + j], py, fmaf(Wp[j], px, Wp[ENC_OFF_BPOS + j])));
-  } else {
-    const float* netin = P.net[net_in];
-    // 16 rows per batch: all global loads of a batch are in flight together (the row-at-a-time loop paid one
-    // L2 round trip per row and key; ncu at the shipped T = 3 640: with 8 rows per batch the four dependent
-    // round trips were still ~40 % of the kernel's warp samples, one warp per scheduler has nothing to hide them)
-    constexpr int kRows = 16;
-    for (int i0 = 0; i0 < 32; i0 += kRows) {
-      float a[kRows], s[kRows];
+      for (int jj = 0; jj < 16; ++jj) {
+        const int j = 16 * q + jj;
+        sX[j * kEGS + lane] = fmaf(Wp[128 + j], pz, fmaf(Wp[64 + j], py, fmaf(Wp[j], px, Wp[ENC_OFF_BPOS + j])));
+      }
+    } else {       // lane == channel: warp q assembles points 8q .. 8q+7, all their global loads in flight together
+      const float* netin = P.net[net_in];
+      float a[8], s[8];
 #pragma unroll
-      for (int u = 0; u < kRows; ++u) {
-        const int i = i0 + u;
-        const long long ni = nb0 + col0 + i;
+      for (int u = 0; u < 8; ++u) {
+        const int i = 8 * q + u;
+        const long long ni = n0 + i;
         const bool ok = ni < P.n;                       // warp-uniform
         a[u] = ok ? netin[ni * 32 + lane] : 0.f;
         s[u] = 0.f;  // c_out = 0; c_out += fea  (key order xz, xy, yz, grid)
@@ -230,81 +287,92 @@ __global__ void __launch_bounds__(kET) enc_block_kernel(const __grid_constant__ 
         }
       }
 #pragma unroll
-      for (int u = 0; u < kRows; ++u) {
-        const int i = i0 + u;
-        if (nb0 + col0 + i < P.n) {
-          sX[lane * kES + col0 + i] = a[u];
-          sX[(32 + lane) * kES + col0 + i] = s[u];
-        }
+      for (int u = 0; u < 8; ++u) {
+        const int i = 8 * q + u;
+        sX[lane * kEGS + i] = a[u];
+        sX[(32 + lane) * kEGS + i] = s[u];
       }
     }
-  }
-  if (!FIRST) __syncthreads();   // weights in shared memory (and the warp's input columns)
-  else __syncwarp();
+    __syncthreads();   // inputs of the group (and, the first time, the weights) are in shared memory
 
-  float h[32], o[32];
+    float h[8], o[8];
 #pragma unroll
-  for (int j = 0; j < 32; ++j) { h[j] = sW[ENC_B_B0 + j]; o[j] = sW[ENC_B_B1 + j]; }
-#pragma unroll 2
-  for (int k = 0; k < 64; ++k) {
-    const float x = xcol[k * kES];
-    axpy32(h, sW + ENC_B_W0 + k * 32, fmaxf(x, 0.f));  // fc_0(relu(x))
-    axpy32(o, sW + ENC_B_WS + k * 32, x);              // shortcut(x), no bias
-  }
-#pragma unroll
-  for (int j = 0; j < 32; ++j) xcol[j * kES] = fmaxf(h[j], 0.f);
+    for (int j = 0; j < 8; ++j) { h[j] = sW[ENC_B_B0 + 8 * q + j]; o[j] = sW[ENC_B_B1 + 8 * q + j]; }
 #pragma unroll 4
-  for (int k = 0; k < 32; ++k) axpy32(o, sW + ENC_B_W1 + k * 32, xcol[k * kES]);  // fc_1(relu(net))
+    for (int k = 0; k < 64; ++k) {
+      const float x = sX[k * kEGS + lane];
+      axpy8(h, sW + ENC_B_W0 + k * 32 + 8 * q, fmaxf(x, 0.f));  // fc_0(relu(x))
+      axpy8(o, sW + ENC_B_WS + k * 32 + 8 * q, x);              // shortcut(x), no bias
+    }
 #pragma unroll
-  for (int j = 0; j < 32; ++j) xcol[j * kES] = o[j];
-  __syncwarp();
+    for (int j = 0; j < 8; ++j) sH[(8 * q + j) * kEGS + lane] = fmaxf(h[j], 0.f);
+    __syncthreads();   // hidden activations complete; nobody reads the input columns any more
+#pragma unroll 4
+    for (int k = 0; k < 32; ++k) axpy8(o, sW + ENC_B_W1 + k * 32 + 8 * q, sH[k * kEGS + lane]);  // fc_1(relu(net))
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sX[(8 * q + j) * kEGS + lane] = o[j];
+    __syncthreads();
 
-  float* dst[4] = {nullptr, nullptr, nullptr, nullptr};
-  if (r_write >= 0)
-    for (int k = 0; k < P.nkeys; ++k) dst[k] = P.pool[r_write][k];
-  if (P.pool_mean) scatter_rows<true>(sX, col0, nb0 + col0, P.n, lane, P.nkeys, myslot, dst, P.net[net_out]);
-  else scatter_rows<false>(sX, col0, nb0 + col0, P.n, lane, P.nkeys, myslot, dst, P.net[net_out]);
+    // lane == channel again: warp q stores / scatters points 8q .. 8q+7
+    if (P.pool_mean) scatter_rows_range<true>(sX, kEGS, 8 * q, 8 * q + 8, n0, P.n, lane, P.nkeys, myslot, dst, P.net[net_out]);
+    else scatter_rows_range<false>(sX, kEGS, 8 * q, 8 * q + 8, n0, P.n, lane, P.nkeys, myslot, dst, P.net[net_out]);
 
-  if (r_init >= 0 && valid) {
-    const float init = P.pool_mean ? 0.0f : -CUDART_INF_F;
-    for (int k = 0; k < P.nkeys; ++k) fill_row(P.pool[r_init][k] + n * 32, init);
+    if (r_init >= 0 && valid) {   // re-initialise the buffer after next: two float4 of the point's row per warp
+      const float init = P.pool_mean ? 0.0f : -CUDART_INF_F;
+      const float4 f = make_float4(init, init, init, init);
+      for (int k = 0; k < P.nkeys; ++k) {
+        float4* row = reinterpret_cast<float4*>(P.pool[r_init][k] + n * 32);
+        row[2 * q] = f;
+        row[2 * q + 1] = f;
+      }
+    }
+    __syncthreads();   // the columns are reused by the next group
   }
 }
 
-// c = fc_c(net) (pointnet.py:162) and the atomicAdd half of scatter_mean (:93,108).
-__global__ void __launch_bounds__(kET) enc_final_kernel(const __grid_constant__ EncParams P, int net_in) {
+static unsigned enc_block_grid(long long n_groups) {
+  const long long cap = (long long)num_sms() * 6;
+  return (unsigned)(n_groups < cap ? n_groups : cap);
+}
+
+// c = fc_c(net) (pointnet.py:162) and the atomicAdd half of scatter_mean (:93,108).  Same shape as the block
+// kernel: four warps per group of 32 points, warp q computes channels [8q, 8q+8).
+constexpr size_t kEncFinalSmem = (ENC_FCC_FLOATS + 64 * kEGS) * sizeof(float);
+__global__ void __launch_bounds__(128) enc_final_kernel(const __grid_constant__ EncParams P, int net_in, long long n_groups) {
   extern __shared__ __align__(16) float esm[];
   float* sW = esm;                   // fc_c (1056)
-  float* sX = sW + ENC_FCC_FLOATS;   // [32][kES]
+  float* sX = sW + ENC_FCC_FLOATS;   // [32][kEGS] inputs
+  float* sO = sX + 32 * kEGS;        // [32][kEGS] outputs
   const float* Wg = P.W + ENC_OFF_BLOCKS + (long long)P.n_blocks * ENC_BLOCK_STRIDE;
-  for (int i = threadIdx.x; i < ENC_FCC_FLOATS / 4; i += kET)
+  for (int i = threadIdx.x; i < ENC_FCC_FLOATS / 4; i += 128)
     reinterpret_cast<float4*>(sW)[i] = __ldg(reinterpret_cast<const float4*>(Wg) + i);
-  __syncthreads();
-  const int tid = threadIdx.x, lane = tid & 31, col0 = tid & ~31;
-  const long long nb0 = (long long)blockIdx.x * kET;
-  const long long n = nb0 + tid;
-  const bool valid = n < P.n;
-  int myslot[4] = {0, 0, 0, 0};
-  for (int k = 0; k < P.nkeys; ++k) myslot[k] = valid ? P.slot[k][n] : 0;
-  const float* netin = P.net[net_in];
-#pragma unroll 8
-  for (int i = 0; i < 32; ++i) {
-    const long long ni = nb0 + col0 + i;
-    if (ni < P.n) sX[lane * kES + col0 + i] = netin[ni * 32 + lane];
-  }
-  __syncwarp();
-  float* xcol = sX + tid;
-  float c[32];
-#pragma unroll
-  for (int j = 0; j < 32; ++j) c[j] = sW[1024 + j];
-#pragma unroll 4
-  for (int k = 0; k < 32; ++k) axpy32(c, sW + k * 32, xcol[k * kES]);
-#pragma unroll
-  for (int j = 0; j < 32; ++j) xcol[j * kES] = c[j];
-  __syncwarp();
+  const int tid = threadIdx.x, lane = tid & 31, q = tid >> 5;
   float* dst[4] = {nullptr, nullptr, nullptr, nullptr};
   for (int k = 0; k < P.nkeys; ++k) dst[k] = P.sum[k];
-  scatter_rows<true>(sX, col0, nb0 + col0, P.n, lane, P.nkeys, myslot, dst, P.c_out);
+  const float* netin = P.net[net_in];
+  for (long long grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+    const long long n0 = grp * kEG;
+    const long long n = n0 + lane;
+    int myslot[4] = {0, 0, 0, 0};
+    for (int k = 0; k < P.nkeys; ++k) myslot[k] = n < P.n ? P.slot[k][n] : 0;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {      // lane == channel: warp q loads points 8q .. 8q+7
+      const int i = 8 * q + u;
+      sX[lane * kEGS + i] = (n0 + i < P.n) ? netin[(n0 + i) * 32 + lane] : 0.f;
+    }
+    __syncthreads();
+    float c[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) c[j] = sW[1024 + 8 * q + j];
+#pragma unroll 4
+    for (int k = 0; k < 32; ++k) axpy8(c, sW + k * 32 + 8 * q, sX[k * kEGS + lane]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sO[(8 * q + j) * kEGS + lane] = c[j];
+    __syncthreads();
+    scatter_rows_range<true>(sO, kEGS, 8 * q, 8 * q + 8, n0, P.n, lane, P.nkeys, myslot, dst, P.c_out);
+    // next group: sX is rewritten right away (its readers all passed the second barrier), sO only after the next
+    // group's first barrier, which every warp reaches after this scatter
+  }
 }
 
 // mean = sum / count, written once per occupied cell (the representative's thread) into the
@@ -470,28 +538,20 @@ extern "C" int vtaco_encoder_pointnet(const vtaco_encoder_args* a, void* stream)
   P.net[0] = c.take<float>(n * 32);
   P.net[1] = c.take<float>(n * 32);
 
-  const unsigned g256 = (unsigned)((n + 255) / 256), gE = (unsigned)((n + kET - 1) / kET);
+  const unsigned g256 = (unsigned)((n + 255) / 256);
   enc_index_kernel<<<g256, 256, 0, st>>>(P);
   enc_slot_kernel<<<g256, 256, 0, st>>>(P, 1);
-  const size_t smem_blk = (ENC_BLOCK_STRIDE + 256 + 64 * kES) * sizeof(float);
-  static std::atomic<bool> configured[64];
-  int dev = 0;
-  VTACO_CUDA_CHECK(cudaGetDevice(&dev));
-  if (!configured[dev & 63].load(std::memory_order_relaxed)) {
-    VTACO_CUDA_CHECK(cudaFuncSetAttribute(enc_block_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_blk));
-    VTACO_CUDA_CHECK(cudaFuncSetAttribute(enc_block_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_blk));
-    configured[dev & 63].store(true, std::memory_order_relaxed);
-  }
+  const long long n_groups = (n + kEG - 1) / kEG;
+  const unsigned gB = enc_block_grid(n_groups);
   const int nb = a->n_blocks;
   // kernel i reads pool[(i-1)%3], scatters into pool[i%3], initialises pool[(i+1)%3]
-  enc_block_kernel<true><<<gE, kET, smem_blk, st>>>(P, 0, -1, nb > 1 ? 0 : -1, nb > 2 ? 1 : -1, 0, 0);
+  enc_block_kernel<true><<<gB, 128, kEncBlockSmem, st>>>(P, 0, -1, nb > 1 ? 0 : -1, nb > 2 ? 1 : -1, 0, 0, n_groups);
   for (int i = 1; i < nb; ++i) {
     const bool last = (i == nb - 1);
-    enc_block_kernel<false><<<gE, kET, smem_blk, st>>>(P, i, (i - 1) % 3, last ? -1 : i % 3,
-                                                       (i + 1 < nb - 1) ? (i + 1) % 3 : -1, (i - 1) & 1, i & 1);
+    enc_block_kernel<false><<<gB, 128, kEncBlockSmem, st>>>(P, i, (i - 1) % 3, last ? -1 : i % 3,
+                                                            (i + 1 < nb - 1) ? (i + 1) % 3 : -1, (i - 1) & 1, i & 1, n_groups);
   }
-  const size_t smem_fin = (ENC_FCC_FLOATS + 32 * kES) * sizeof(float);
-  enc_final_kernel<<<gE, kET, smem_fin, st>>>(P, (nb - 1) & 1);
+  enc_final_kernel<<<gB, 128, kEncFinalSmem, st>>>(P, (nb - 1) & 1, n_groups);
   enc_finalize_kernel<<<g256, 256, 0, st>>>(P);
   VTACO_LAUNCH_CHECK();
   for (int k = 0; k < a->n_keys; ++k)

@@ -314,15 +314,14 @@ extern "C" int vtaco_encoder_backward(const vtaco_encoder_bwd_args* a, void* str
   }
   const unsigned g256 = (unsigned)((n + 255) / 256), gE = (unsigned)((n + kET - 1) / kET);
   const unsigned gRow = (unsigned)((n * 32 + 255) / 256);
-  const size_t smem_blk = (ENC_BLOCK_STRIDE + 256 + 64 * kES) * sizeof(float);
+  const long long n_groups = (n + kEG - 1) / kEG;
+  const unsigned gB = enc_block_grid(n_groups);
   const size_t smem_bwd = (ENC_BLOCK_STRIDE + 256 + 128 * kES) * sizeof(float);
   const size_t smem_fin = (ENC_FCC_FLOATS + 32 * kES) * sizeof(float);
   static std::atomic<bool> configured[64];
   int dev = 0;
   VTACO_CUDA_CHECK(cudaGetDevice(&dev));
   if (!configured[dev & 63].load(std::memory_order_relaxed)) {
-    VTACO_CUDA_CHECK(cudaFuncSetAttribute(enc_block_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_blk));
-    VTACO_CUDA_CHECK(cudaFuncSetAttribute(enc_block_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_blk));
     VTACO_CUDA_CHECK(cudaFuncSetAttribute(encb_block_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bwd));
     VTACO_CUDA_CHECK(cudaFuncSetAttribute(encb_block_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bwd));
     configured[dev & 63].store(true, std::memory_order_relaxed);
@@ -337,7 +336,7 @@ extern "C" int vtaco_encoder_backward(const vtaco_encoder_bwd_args* a, void* str
     P.pool[1][k] = nb > 2 ? L.pool[k][2] : nullptr;
   }
   P.net[0] = L.net[0];
-  enc_block_kernel<true><<<gE, kET, smem_blk, st>>>(P, 0, -1, nb > 1 ? 0 : -1, nb > 2 ? 1 : -1, 0, 0);
+  enc_block_kernel<true><<<gB, 128, kEncBlockSmem, st>>>(P, 0, -1, nb > 1 ? 0 : -1, nb > 2 ? 1 : -1, 0, 0, n_groups);
   for (int i = 1; i < nb; ++i) {
     const bool last = (i == nb - 1);
     for (int k = 0; k < nk; ++k) {
@@ -347,7 +346,7 @@ extern "C" int vtaco_encoder_backward(const vtaco_encoder_bwd_args* a, void* str
     }
     P.net[0] = L.net[i - 1];
     P.net[1] = L.net[i];
-    enc_block_kernel<false><<<gE, kET, smem_blk, st>>>(P, i, 0, last ? -1 : 1, (i + 2 < nb) ? 2 : -1, 0, 1);
+    enc_block_kernel<false><<<gB, 128, kEncBlockSmem, st>>>(P, i, 0, last ? -1 : 1, (i + 2 < nb) ? 2 : -1, 0, 1, n_groups);
   }
   VTACO_LAUNCH_CHECK();
 

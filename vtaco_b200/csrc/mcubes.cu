@@ -38,8 +38,6 @@ namespace vtaco {
 
 constexpr int kMcThreads = 256;   // threads per block
 constexpr int kMcRun = 8;         // consecutive z points per thread
-constexpr int kMcBlockPts = kMcThreads * kMcRun;
-constexpr int kMcSuper = 256;     // blocks per super-block of the two-level prefix
 
 struct McParams {
   const float* grid;
@@ -191,7 +189,6 @@ __global__ void __launch_bounds__(kMcThreads) mc_fused_kernel(const __grid_const
   __shared__ uint8_t s_tricount[256];
   __shared__ unsigned s_wexcl[kMcSub * kWarps];
   __shared__ unsigned s_rows[kMcBlockRuns];
-  __shared__ unsigned s_total;
   if (threadIdx.x == 0) s_bid = (int)atomicAdd(P.ctrl, 1u);      // ticket: all blocks before this one have started
   s_tricount[threadIdx.x] = (uint8_t)__ldg(kMcTriCount + threadIdx.x);
   __syncthreads();
@@ -263,7 +260,6 @@ __global__ void __launch_bounds__(kMcThreads) mc_fused_kernel(const __grid_const
     }
     s_wexcl[lane] = si - v;
     total = __shfl_sync(0xffffffffu, si, 31);
-    if (lane == 0) s_total = total;
   }
   // ---- decoupled look-back (warp 0): exclusive prefix of this block over all blocks before it ----
   if (threadIdx.x < 32) {

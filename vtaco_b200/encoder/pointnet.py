@@ -154,6 +154,7 @@ class LocalPoolPointnet(nn.Module):
                 'conv-occupancy hot path and is not built (SURVEY.md §2 row 13)')
         self.division = 'cuda'
         self._pack_cache = None
+        self._pack_params = None
         self._ws = None
 
     # ------------------------------------------------------------------ helpers
@@ -178,6 +179,7 @@ class LocalPoolPointnet(nn.Module):
         through `param.data` do not bump `_version` — call this after one when running under no_grad;
         with grad enabled every call re-packs, and `.to()` / `load_state_dict` invalidate on their own)."""
         self._pack_cache = None
+        self._pack_params = None
 
     def _apply(self, fn, *args, **kwargs):
         self.invalidate()
@@ -189,8 +191,10 @@ class LocalPoolPointnet(nn.Module):
 
     def _packed_weights(self):
         """K-major fp32 buffer (layout in include/vtaco_b200.h), one vtaco_pack_linear launch."""
-        params = [self.fc_pos.weight, self.fc_pos.bias, self.fc_c.weight, self.fc_c.bias] + \
-            [p for b in self.blocks for p in b.parameters()]
+        if self._pack_params is None:      # cached: walking the module tree costs more than the check it feeds
+            self._pack_params = tuple([self.fc_pos.weight, self.fc_pos.bias, self.fc_c.weight, self.fc_c.bias] +
+                                      [p for b in self.blocks for p in b.parameters()])
+        params = self._pack_params
         key = tuple((p.data_ptr(), p._version) for p in params)
         if self._pack_cache is not None and self._pack_cache[0] == key:
             return self._pack_cache[1]
@@ -222,8 +226,8 @@ class LocalPoolPointnet(nn.Module):
         _abi.require_cuda(p, 'p')
         if p.dim() != 3 or p.size(2) != 3:
             raise ValueError('p must have shape (B, T, 3)')
-        own = self._pointnet_params()
-        if _abi.wants_grad(p, *[t for _, t in own]):
+        own = self._pointnet_params() if torch.is_grad_enabled() else ()   # (walks the module tree: not under no_grad)
+        if own and _abi.wants_grad(p, *[t for _, t in own]):
             # no gradient w.r.t. the input cloud is produced (backward returns None for p), like the
             # decoder: the reference never reads it
             if return_code or return_index:

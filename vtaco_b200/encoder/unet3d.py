@@ -170,11 +170,13 @@ class UNet3D(nn.Module):
             return False
         if self.testing and self.final_activation is not None:
             return False
-        convs = [m for m in self.modules() if isinstance(m, nn.Conv3d)]
-        ok = all(c.in_channels % 16 == 0 and c.out_channels % 32 == 0 and c.in_channels <= 512 and
-                 c.kernel_size[0] in (1, 3) and c.kernel_size[0] == c.kernel_size[1] == c.kernel_size[2] for c in convs)
+        if getattr(self, '_fusable_static', None) is None:   # the module tree does not change after construction
+            convs = [m for m in self.modules() if isinstance(m, nn.Conv3d)]
+            ok = all(c.in_channels % 16 == 0 and c.out_channels % 32 == 0 and c.in_channels <= 512 and
+                     c.kernel_size[0] in (1, 3) and c.kernel_size[0] == c.kernel_size[1] == c.kernel_size[2] for c in convs)
+            self._fusable_static = (ok, sum(1 for e in self.encoders if e.pooling is not None))
+        ok, n_pool = self._fusable_static
         D, H, W = x.shape[2:]
-        n_pool = sum(1 for e in self.encoders if e.pooling is not None)
         return ok and all(d % (2 ** n_pool) == 0 for d in (D, H, W))
 
     def _packed(self, conv):
