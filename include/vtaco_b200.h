@@ -517,6 +517,8 @@ typedef struct vtaco_conv3d_args {
   int32_t relu;
   float* y;                /* [N][D][H][W][Cout] */
   double* out_stats;       /* optional [N][Cout][2], accumulated */
+  int32_t ksize_z;         /* extent of the filter along z: 0 = ksize (3-D convolution), 1 = a 2-D k x k convolution on
+                              every z-slice (packed weights then hold k*k taps: W[co][ci][dy][dx]) */
 } vtaco_conv3d_args;
 int vtaco_conv3d_cl(const vtaco_conv3d_args* args, void* stream);
 /* MaxPool3d(kernel 2, stride 2), channels-last; stats (optional, zeroed by the caller, N must be 1):
@@ -526,6 +528,14 @@ int vtaco_maxpool2_cl(const float* x, float* y, int32_t N, int32_t D, int32_t H,
 /* per-channel (sum, sumsq) of one channels-last sample x [S][C] accumulated into stats [C][2]
  * (zeroed by the caller); C % 4 == 0 and C/4 divides 256. */
 int vtaco_channel_stats_cl(const float* x, int64_t S, int32_t C, double* stats, void* stream);
+/* (7c) 2-D U-Net on the feature planes (reference src/encoder/unet.py:45-239): its 3x3 / 1x1 convolutions run on
+ * vtaco_conv3d_cl with D = 1 (a 2-D filter is the middle z-slice of a 3x3x3 one; bias + ReLU in the epilogue, no
+ * GroupNorm; the skip connection is the second input at the same resolution).  The two other layers:
+ * vtaco_maxpool2d_cl: MaxPool2d(2) on x [N][H][W][C] -> y [N][H/2][W/2][C] (H, W even, C % 4 == 0);
+ * vtaco_depth_to_space2_cl: x [N][H][W][4*C], channel (a*2+b)*C + c -> y [N][2H][2W][C] at (2i+a, 2j+b) — the
+ *   interleave of ConvTranspose2d(kernel 2, stride 2), whose arithmetic is a 1x1 convolution to 4*C channels. */
+int vtaco_maxpool2d_cl(const float* x, float* y, int32_t N, int32_t H, int32_t W, int32_t C, void* stream);
+int vtaco_depth_to_space2_cl(const float* x, float* y, int32_t N, int32_t H, int32_t W, int32_t C, void* stream);
 
 /* UNet3D decoder input in one pass (src/encoder/unet3d.py Decoder.forward):
  * out [N][C1+C2][Do][Ho][Wo] = cat(skip [N][C1][Do][Ho][Wo], nearest-upsample(x [N][C2][Di][Hi][Wi]), dim=1),

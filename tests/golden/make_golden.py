@@ -270,6 +270,7 @@ def main():
     make_emd(common)
     make_helpers(common)
     make_unet3d_shipped()
+    make_unet2d_shipped()
     for f in sorted(os.listdir(HERE)):
         if f.endswith('.npz'):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, 'KiB')
@@ -396,6 +397,19 @@ def make_unet3d_shipped():
     np.savez_compressed(os.path.join(HERE, 'unet3d_shipped.npz'), y=y, seed_w=np.int64(91), seed_x=np.array([92, 93]))
 
 
+def make_unet2d_shipped():
+    """G12: the reference's 2-D UNet with the SHIPPED kwargs (VTacO_YCB.yaml:41-44: depth 4, merge_mode concat,
+    start_filts 32; 32 -> 32 channels) on two 32 x 32 feature planes, fp32 on the CPU.  Parameters come from
+    `randomise(module, 95)` (a numpy stream), so the test re-creates them instead of storing 7.8 M weights."""
+    from src.encoder.unet import UNet
+    u = UNet(32, in_channels=32, depth=4, merge_mode='concat', start_filts=32)
+    randomise(u, 95)
+    x = rs_randn(96, 2, 32, 32, 32) * (np.random.RandomState(97).rand(2, 32, 32, 32) < 0.3)
+    with torch.no_grad():
+        y = u.eval()(torch.from_numpy(x.astype(np.float32))).numpy()
+    np.savez_compressed(os.path.join(HERE, 'unet2d_shipped.npz'), y=y, seed_w=np.int64(95), seed_x=np.array([96, 97]))
+
+
 def make_helpers(common):
     """G10: src/common.py R_from_PYR / norm_pc_1 and the fingertip transform of generation.py:177-188
     (the inline code there, evaluated with the reference's own helper functions)."""
@@ -428,6 +442,9 @@ if __name__ == '__main__':
     elif sys.argv[1:] == ['unet3d']:
         import_reference()
         make_unet3d_shipped()
+    elif sys.argv[1:] == ['unet2d']:
+        import_reference()
+        make_unet2d_shipped()
     elif sys.argv[1:] == ['chamfer']:
         make_chamfer(import_reference()[0])
     elif sys.argv[1:] == ['grads']:

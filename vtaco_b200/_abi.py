@@ -91,7 +91,8 @@ class Conv3dArgs(C.Structure):
                 ('C2', C.c_int32), ('D2', C.c_int32), ('H2', C.c_int32), ('W2', C.c_int32),
                 ('w_packed', C.c_void_p), ('bias', C.c_void_p), ('Cout', C.c_int32), ('ksize', C.c_int32),
                 ('in_stats', C.c_void_p), ('gamma', C.c_void_p), ('beta', C.c_void_p), ('groups', C.c_int32),
-                ('eps', C.c_double), ('relu', C.c_int32), ('y', C.c_void_p), ('out_stats', C.c_void_p)]
+                ('eps', C.c_double), ('relu', C.c_int32), ('y', C.c_void_p), ('out_stats', C.c_void_p),
+                ('ksize_z', C.c_int32)]
 
 
 class PackDesc(C.Structure):
@@ -184,6 +185,8 @@ _OPTIONAL = {
     'vtaco_maxpool2_cl': [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                           C.c_void_p],
     'vtaco_channel_stats_cl': [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p],
+    'vtaco_maxpool2d_cl': [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p],
+    'vtaco_depth_to_space2_cl': [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p],
     'vtaco_fingertip_ids': [C.c_void_p, C.c_int64, C.POINTER(C.c_double), C.POINTER(C.c_int32), C.c_int32, C.c_double,
                             C.c_void_p, C.c_void_p],
     'vtaco_tactile_point_map': [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_double,

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'lib', 'libvtaco_b200.so')
-SOURCES = ['core.cu', 'pack.cu', 'decoder.cu', 'decoder_tc.cu', 'decoder_tc4.cu', 'decoder_bwd.cu', 'encoder.cu', 'mcubes.cu', 'exchange.cu', 'tactile.cu', 'metrics.cu', 'emd.cu', 'conv3d.cu']
+SOURCES = ['core.cu', 'pack.cu', 'decoder.cu', 'decoder_tc.cu', 'decoder_tc4.cu', 'decoder_bwd.cu', 'encoder.cu', 'mcubes.cu', 'exchange.cu', 'tactile.cu', 'metrics.cu', 'emd.cu', 'conv3d.cu', 'plane_ops.cu']
 # debug / measurement kernels live in their own library (tools/ only), not in the product ABI
 BENCH_LIB = os.path.join(HERE, 'lib', 'libvtaco_microbench.so')
 BENCH_SOURCES = ['tc_microbench.cu']

@@ -31,7 +31,6 @@ constexpr int kCvKC = 16;                 // input channels per chunk (4 planes 
 constexpr int kCvTileY = 16, kCvTileX = 8;
 constexpr int kCvMaxCin = 512;
 constexpr int kCvLoaders = 512;            // warps 0..15 fill the bricks and run the epilogue; warp 16 only issues the MMAs
-constexpr int kCvItems = (3 * 18 * 10 * 4 + kCvLoaders - 1) / kCvLoaders;   // brick float4s per loader thread (3x3x3 halo brick)
 constexpr uint32_t kCvIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (4u << 17) | (8u << 24);  // F32 acc, TF32 x TF32, K-major, N=32, M=128
 
 struct ConvParams {
@@ -44,7 +43,7 @@ struct ConvParams {
   const float* beta;
   float* y;            // [N][D][H][W][Cout]
   double* out_stats;   // [N][Cout][2] or NULL
-  int N, D, H, W, C1, C2, D2, H2, W2, Cout, ksize, groups, relu;
+  int N, D, H, W, C1, C2, D2, H2, W2, Cout, ksize, groups, relu;   // (the filter's z extent is a template parameter)
   int tiles_x, tiles_y, n_tiles;
   double eps;
   long long* trace;    // debug (VTACO_CV_TRACE=1): clock64 stamps of thread 0 of block 0
@@ -88,17 +87,17 @@ __device__ __forceinline__ void cv_commit(uint32_t bar) {
 
 // shared memory: 2 brick buffers | 2 weight-chunk slots | GroupNorm tables | statistics | barriers
 struct CvSmem { int brick, w, scale, shift, stat, bar, tmem, total, plane_stride, brick_bytes, row_pitch, bvox, wslot; };
-__host__ __device__ inline CvSmem cv_layout(int ksize, int cin) {
+__host__ __device__ inline CvSmem cv_layout(int ksize, int kz, int cin) {
   CvSmem s;
-  const int h = ksize / 2;
-  const int bz = 1 + 2 * h, by = kCvTileY + 2 * h, bx = kCvTileX + 2 * h;
+  const int h = ksize / 2, hz = kz / 2;
+  const int bz = 1 + 2 * hz, by = kCvTileY + 2 * h, bx = kCvTileX + 2 * h;
   s.bvox = bz * by * bx;
   s.row_pitch = bx * 16;                                   // bytes between brick rows (= 8-row groups of the MMA)
   s.plane_stride = (s.bvox * 16 + 80 + 127) / 128 * 128 + 16;   // odd multiple of 16 B: spreads the planes over the banks
   s.brick_bytes = (4 * s.plane_stride + 127) / 128 * 128;
   s.brick = 0;
   s.w = 2 * s.brick_bytes;
-  const int taps = ksize * ksize * ksize;
+  const int taps = ksize * ksize * kz;
   s.wslot = taps * 2048;
   s.scale = s.w + 2 * s.wslot;
   s.shift = s.scale + cin * 4;
@@ -111,11 +110,13 @@ __host__ __device__ inline CvSmem cv_layout(int ksize, int cin) {
   return s;
 }
 
-template <int KSIZE>
+// KZ = extent of the filter along z: KSIZE (3-D convolution) or 1 (a 2-D convolution on every z-slice — the
+// feature planes of the 2-D U-Net are volumes of depth 1: a third of the taps and of the halo brick)
+template <int KSIZE, int KZ>
 __global__ void __launch_bounds__(kCvThreads, 1) conv3d_tc_kernel(const __grid_constant__ ConvParams P) {
   extern __shared__ __align__(128) unsigned char sm[];
   const int Cin = P.C1 + P.C2;
-  const CvSmem L = cv_layout(KSIZE, Cin);
+  const CvSmem L = cv_layout(KSIZE, KZ, Cin);
   float* sScale = reinterpret_cast<float*>(sm + L.scale);
   float* sShift = reinterpret_cast<float*>(sm + L.shift);
   float* sStat = reinterpret_cast<float*>(sm + L.stat);
@@ -123,9 +124,10 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv3d_tc_kernel(const __grid_c
   uint32_t* sTmem = reinterpret_cast<uint32_t*>(sm + L.tmem);
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-  constexpr int h = KSIZE / 2, taps = KSIZE * KSIZE * KSIZE;
-  constexpr int bx_ext = kCvTileX + 2 * h, by_ext = kCvTileY + 2 * h, bz_ext = 1 + 2 * h;
+  constexpr int h = KSIZE / 2, hz = KZ / 2, taps = KSIZE * KSIZE * KZ;
+  constexpr int bx_ext = kCvTileX + 2 * h, by_ext = kCvTileY + 2 * h, bz_ext = 1 + 2 * hz;
   constexpr int kBvox = bz_ext * by_ext * bx_ext;
+  constexpr int kCvItems = (kBvox * 4 + kCvLoaders - 1) / kCvLoaders;   // brick float4s per loader thread
   constexpr int kPlane = (kBvox * 16 + 80 + 127) / 128 * 128 + 16;      // == cv_layout().plane_stride
   constexpr int kRowPitch = bx_ext * 16;
   const int ntile = blockIdx.y, n = blockIdx.z;
@@ -290,7 +292,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv3d_tc_kernel(const __grid_c
       int voxA[kCvItems], voxB[kCvItems];
 #pragma unroll
       for (int u = 0; u < kCvItems; ++u) {
-        const int gz = z + (rel[u] & 0xff) - h, gy = y0 + ((rel[u] >> 8) & 0xff) - h, gx = x0 + ((rel[u] >> 16) & 0xff) - h;
+        const int gz = z + (rel[u] & 0xff) - hz, gy = y0 + ((rel[u] >> 8) & 0xff) - h, gx = x0 + ((rel[u] >> 16) & 0xff) - h;
         const bool inb = rel[u] >= 0 && gz >= 0 && gz < P.D && gy >= 0 && gy < P.H && gx >= 0 && gx < P.W;
         voxA[u] = inb ? (int)((((size_t)n * P.D + gz) * P.H + gy) * P.W + gx) : -1;
         voxB[u] = -1;
@@ -470,6 +472,8 @@ extern "C" int vtaco_conv3d_cl(const vtaco_conv3d_args* a, void* stream) {
   if (!a || !a->x || !a->w_packed || !a->y) return VTACO_ERR_INVALID_ARG;
   if (a->N < 1 || a->D < 1 || a->H < 1 || a->W < 1 || a->C1 < 1 || a->C2 < 0 || a->Cout < 1) return VTACO_ERR_INVALID_ARG;
   if (a->ksize != 1 && a->ksize != 3) return VTACO_ERR_UNSUPPORTED;
+  const int kz = a->ksize_z ? a->ksize_z : a->ksize;
+  if (kz != 1 && kz != a->ksize) return VTACO_ERR_UNSUPPORTED;
   const int Cin = a->C1 + a->C2;
   if (a->C1 % kCvKC || a->C2 % kCvKC || a->Cout % 32 || Cin > kCvMaxCin) return VTACO_ERR_UNSUPPORTED;
   if (a->C2 > 0 && (!a->x2 || a->D2 < 1 || a->H2 < 1 || a->W2 < 1)) return VTACO_ERR_INVALID_ARG;
@@ -484,14 +488,15 @@ extern "C" int vtaco_conv3d_cl(const vtaco_conv3d_args* a, void* stream) {
   const long long tiles = (long long)P.tiles_x * P.tiles_y * a->D;
   if (tiles > 0x7fffffffll || a->Cout / 32 > 65535 || a->N > 65535) return VTACO_ERR_UNSUPPORTED;
   P.n_tiles = (int)tiles;
-  const CvSmem L = cv_layout(a->ksize, Cin);
+  const CvSmem L = cv_layout(a->ksize, kz, Cin);
   if (L.total > 227 * 1024) return VTACO_ERR_UNSUPPORTED;
   static std::atomic<int> configured[64];
   int dev = 0;
   VTACO_CUDA_CHECK(cudaGetDevice(&dev));
   if (configured[dev & 63].load(std::memory_order_relaxed) == 0) {
-    VTACO_CUDA_CHECK(cudaFuncSetAttribute(conv3d_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    VTACO_CUDA_CHECK(cudaFuncSetAttribute(conv3d_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VTACO_CUDA_CHECK(cudaFuncSetAttribute(conv3d_tc_kernel<3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VTACO_CUDA_CHECK(cudaFuncSetAttribute(conv3d_tc_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VTACO_CUDA_CHECK(cudaFuncSetAttribute(conv3d_tc_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured[dev & 63].store(1, std::memory_order_relaxed);
   }
   // persistent CTAs: one per SM in total, split over the (out-channel tile, sample) pairs
@@ -504,8 +509,9 @@ extern "C" int vtaco_conv3d_cl(const vtaco_conv3d_args* a, void* stream) {
     VTACO_CUDA_CHECK(cudaMalloc(&P.trace, 2048 * sizeof(long long)));
     VTACO_CUDA_CHECK(cudaMemsetAsync(P.trace, 0, 2048 * sizeof(long long), (cudaStream_t)stream));
   }
-  if (a->ksize == 3) conv3d_tc_kernel<3><<<grid, kCvThreads, L.total, (cudaStream_t)stream>>>(P);
-  else conv3d_tc_kernel<1><<<grid, kCvThreads, L.total, (cudaStream_t)stream>>>(P);
+  if (a->ksize == 3 && kz == 3) conv3d_tc_kernel<3, 3><<<grid, kCvThreads, L.total, (cudaStream_t)stream>>>(P);
+  else if (a->ksize == 3) conv3d_tc_kernel<3, 1><<<grid, kCvThreads, L.total, (cudaStream_t)stream>>>(P);
+  else conv3d_tc_kernel<1, 1><<<grid, kCvThreads, L.total, (cudaStream_t)stream>>>(P);
   VTACO_LAUNCH_CHECK();
   if (P.trace) {   // debug: average cycles between consecutive stamps, per (from -> to) slot pair
     static long long hbuf[2048];
