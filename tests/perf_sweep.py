@@ -57,7 +57,7 @@ with torch.no_grad():
                 continue
             ms = timed(lambda: dec(p, feats), reps=3 if N >= 10 ** 8 else 5)
             res['decoder_flat'].append({'features': name, 'N': N, 'ms': ms, 'Gpts_per_s': N / ms / 1e6,
-                                        'kernel': 'tcgen05 3xTF32 (forward)'})
+                                        'kernel': 'tcgen05, four tiles per SM (variant 7; forward)'})
         if N == 10 ** 6:
             ci = torch.randn(1, N, 32, device=dev)
             ms = timed(lambda: dec.forward_img(p, grid1, ci))
@@ -65,7 +65,7 @@ with torch.no_grad():
                                         'kernel': 'SIMT FFMA2 (forward_img, dense c_img tensor)'})
             ms = timed(lambda: dec.forward_contact(p, grid1))
             res['decoder_flat'].append({'features': 'grid64', 'N': N, 'ms': ms, 'Gpts_per_s': N / ms / 1e6,
-                                        'kernel': 'tcgen05 3xTF32 (forward_contact)'})
+                                        'kernel': 'tcgen05, four tiles per SM (variant 7; forward_contact)'})
         del p
         torch.cuda.empty_cache()
 
