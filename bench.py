@@ -658,8 +658,9 @@ def run_ours(args, rank, local_rank, world):
                     'ms_per_step': float(e2e_t.item()) / args.steps * 1e3,
                     'path': e2e_mode + ': pinned cloud -> H2D -> LocalPoolPointnet+UNet3D -> decode -> marching '
                             'cubes -> mesh D2H (pinned)'},
-            # per step: 1 fused decoder + 3 marching-cubes kernels [+ 4 exchange kernels when N>1, mesh exchange]
-            'gpu_launches': args.steps * (4 + (4 if (world > 1 and args.exchange == 'mesh') else 0)),
+            # our kernels per step: fused decoder, marching-cubes classification + emit [+ level exchange and the
+            # mesh-exchange kernel when N>1, mesh exchange]; the look-back state memset is not a kernel
+            'gpu_launches': args.steps * (3 + (2 if (world > 1 and args.exchange == 'mesh') else 0)),
             'stage_ms': ({'decode_plus_exchange': float(np.mean(dec_ms)), 'marching_cubes':
                           float(np.mean(step_ms)) - float(np.mean(dec_ms))} if dec_ms is not None else
                          {'decoder_kernel_alone': k_ms, 'rest_of_step(exchange+marching_cubes)':
