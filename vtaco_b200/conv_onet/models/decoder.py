@@ -130,6 +130,13 @@ class LocalDecoder(nn.Module):
         self._cl_cache = {}
         self._params = None
 
+    def _named_param_tuples(self):
+        """(names, parameters) of the module, cached like `_param_tuple` (the training path hands them to autograd)."""
+        if self.__dict__.get('_named_params') is None:
+            names, params = zip(*self.named_parameters())
+            self.__dict__['_named_params'] = (tuple(names), tuple(params))
+        return self.__dict__['_named_params']
+
     def _param_tuple(self):
         """The module's parameters as a cached tuple: `self.parameters()` walks the module tree (37 modules,
         ~25 us) and the hot path needs the list three times per call — it was most of the 0.13 ms a flat call
@@ -159,6 +166,8 @@ class LocalDecoder(nn.Module):
         self._pack_tc_cache = None
         self._cl_cache = {}
         self._params = None
+        self.__dict__['_desc_cache'] = {}
+        self.__dict__['_named_params'] = None
 
     def _apply(self, fn, *args, **kwargs):
         self.invalidate()
@@ -196,7 +205,7 @@ class LocalDecoder(nn.Module):
         ent += [(self.fc_out.weight, o), (self.fc_out.bias, o + 64)]
         if hasattr(self, 'fc_out_contact'):
             ent += [(self.fc_out_contact.weight, o + 32), (self.fc_out_contact.bias, o + 65)]
-        _abi.pack_linear(ent, buf)
+        _abi.pack_linear(ent, buf, cache=self.__dict__.setdefault('_desc_cache', {}))
         self._pack_cache = (key, buf)
         self._pack_tc_cache = None
         return buf
@@ -309,7 +318,7 @@ class LocalDecoder(nn.Module):
             if tip_ids is not None:
                 raise NotImplementedError('vtaco_b200: tip_ids is an inference-only form; pass '
                                           'tactile.c_img_from_ids(ids, c_img) as c_img when training')
-            names, params = zip(*self.named_parameters())
+            names, params = self._named_param_tuples()
             return _DecodeFn.apply(self, bool(use_img), bool(contact), tuple(feats.keys()), names, p, c_img,
                                    *feats.values(), *params)
         out, out_c, _ = self._decode_impl(p, c_plane, use_img, c_img, contact, tip_ids)
@@ -439,15 +448,19 @@ class LocalDecoder(nn.Module):
         else:
             g['fc_p.weight'] = flat[0:96].view(32, 3)
             g['fc_p.bias'] = flat[_abi.DEC_OFF_BP:_abi.DEC_OFF_BP + 32]
-        for i in range(nb):
-            o = _abi.DEC_OFF_BLOCKS + i * _abi.DEC_BLOCK_STRIDE
-            if self.c_dim:
-                g['fc_c.%d.weight' % i] = flat[o:o + 1024].view(32, 32)
-                g['fc_c.%d.bias' % i] = flat[o + 1024:o + 1056]
-            g['blocks.%d.fc_0.weight' % i] = flat[o + 1056:o + 2080].view(32, 32)
-            g['blocks.%d.fc_0.bias' % i] = flat[o + 2080:o + 2112]
-            g['blocks.%d.fc_1.weight' % i] = flat[o + 2112:o + 3136].view(32, 32)
-            g['blocks.%d.fc_1.bias' % i] = flat[o + 3136:o + 3168]
+        # the blocks are nb consecutive records of (W_c 1024, b_c 32, W_0 1024, b_0 32, W_1 1024, b_1 32) floats:
+        # one view + one unbind per field instead of six slices per block
+        blk = flat[_abi.DEC_OFF_BLOCKS:_abi.DEC_OFF_BLOCKS + nb * _abi.DEC_BLOCK_STRIDE].view(nb, _abi.DEC_BLOCK_STRIDE)
+        fields = (('fc_c.%d.weight', 0, 1024, self.c_dim), ('fc_c.%d.bias', 1024, 32, self.c_dim),
+                  ('blocks.%d.fc_0.weight', 1056, 1024, True), ('blocks.%d.fc_0.bias', 2080, 32, True),
+                  ('blocks.%d.fc_1.weight', 2112, 1024, True), ('blocks.%d.fc_1.bias', 3136, 32, True))
+        for fmt, off, n, on in fields:
+            if not on:
+                continue
+            seg = blk[:, off:off + n]
+            rows = (seg.reshape(nb, 32, 32) if n == 1024 else seg).unbind(0)
+            for i, r in enumerate(rows):
+                g[fmt % i] = r
         o = _abi.DEC_OFF_BLOCKS + nb * _abi.DEC_BLOCK_STRIDE
         g['fc_out.weight'] = flat[o:o + 32].view(1, 32)
         g['fc_out.bias'] = flat[o + 64:o + 65]

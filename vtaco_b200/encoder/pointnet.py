@@ -180,6 +180,7 @@ class LocalPoolPointnet(nn.Module):
         with grad enabled every call re-packs, and `.to()` / `load_state_dict` invalidate on their own)."""
         self._pack_cache = None
         self._pack_params = None
+        self.__dict__['_desc_cache'] = {}
 
     def _apply(self, fn, *args, **kwargs):
         self.invalidate()
@@ -208,7 +209,8 @@ class LocalPoolPointnet(nn.Module):
         o = 256 + 5184 * nb
         ent += [(self.fc_c.weight, o), (self.fc_c.bias, o + 1024)]
         for j in range(0, len(ent), _abi.PACK_MAX_DESCS):
-            _abi.pack_linear(ent[j:j + _abi.PACK_MAX_DESCS], buf)
+            _abi.pack_linear(ent[j:j + _abi.PACK_MAX_DESCS], buf,
+                             cache=self.__dict__.setdefault('_desc_cache', {}).setdefault(j, {}))
         self._pack_cache = (key, buf)
         return buf
 
