@@ -28,7 +28,7 @@
 
 namespace vtaco {
 
-constexpr int kBT = 256;       // threads per CTA == queries per tile
+constexpr int kBT = 256;       // threads per CTA == queries per tile (352 threads — what registers and shared memory allow — measured slower: 400 vs 307 us at 65 536 queries)
 constexpr int kBS = kBT + 1;   // column stride (floats)
 constexpr int kMaxBlocks = 8;
 
@@ -387,10 +387,10 @@ extern "C" int vtaco_decoder_backward(const vtaco_decoder_bwd_args* a, void* str
   VTACO_CUDA_CHECK(cudaGetDevice(&dev));
   if (!attr_done[dev & 63]) {
     VTACO_CUDA_CHECK(cudaFuncSetAttribute(decoder_bwd_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)(200 * 1024)));
+                                          (int)(227 * 1024)));
     attr_done[dev & 63] = true;
   }
-  if (smem > 200 * 1024) return VTACO_ERR_UNSUPPORTED;
+  if (smem > 227 * 1024) return VTACO_ERR_UNSUPPORTED;
   const long long tiles = (Q + kBT - 1) / kBT;
   const int grid = (int)std::min<long long>(tiles, num_sms());
   decoder_bwd_query_kernel<<<grid, kBT, smem, stream>>>(P);
