@@ -135,3 +135,38 @@ def test_dense_matches_flat_and_golden(variant):
         for x0, x1 in ((0, 5), (5, 16), (16, 29), (29, 32)):
             dec.forward_dense(c, nx, x0=x0, x1=x1, out=out)
         assert torch.equal(out, dense)
+
+
+@pytest.mark.parametrize('variant', [7, 5])
+@pytest.mark.parametrize('n_blocks,leaky,mode', [(1, False, 'bilinear'), (3, True, 'bilinear'), (5, False, 'nearest')])
+def test_tcgen05_variants_odd_configurations_vs_fp32_kernel(variant, n_blocks, leaky, mode):
+    """network depths other than the shipped 5, LeakyReLU head, nearest sampling, grid + planes together, an odd
+    lattice (nx = 37: partial 2 x 2 x 32 bricks on every axis, odd slab boundaries) and a ragged flat batch:
+    the tensor-core kernels against the exact-fp32 SIMT kernel (variant 1, pinned to the oracle above)."""
+    from vtaco_b200.conv_onet.models import decoder_dict
+    torch.manual_seed(3)
+    dec = decoder_dict['simple_local'](dim=3, c_dim=32, hidden_size=32, n_blocks=n_blocks, leaky=leaky,
+                                       sample_mode=mode, with_contact=True).cuda().eval()
+    with torch.no_grad():
+        for b in dec.blocks:
+            b.fc_1.weight.normal_(0, 0.1)
+    R = 20
+    feats = {'grid': torch.randn(2, 32, R, R, R, device='cuda'), 'xz': torch.randn(2, 32, R, R, device='cuda'),
+             'yz': torch.randn(2, 32, R, R, device='cuda')}
+    p = (torch.rand(2, 1237, 3, device='cuda') - 0.5) * 1.2
+    c_img = torch.randn(2, 1237, 32, device='cuda')
+    outs = {}
+    with torch.no_grad():
+        for v in (1, variant):
+            dec.kernel_variant = v
+            o = dec.forward_img(p, feats, c_img)
+            oc_, occ = dec.forward_contact(p, feats)
+            one = {k: t[:1] for k, t in feats.items()}
+            d = dec.forward_dense({'grid': one['grid']}, 37)
+            part = torch.full((37, 37, 37), float('nan'), device='cuda')
+            for x0, x1 in ((0, 5), (5, 6), (6, 37)):
+                dec.forward_dense({'grid': one['grid']}, 37, x0=x0, x1=x1, out=part)
+            assert torch.equal(part, d)
+            outs[v] = (o, oc_, occ, d)
+    for a, b in zip(outs[variant], outs[1]):
+        assert close(a.cpu().numpy(), b.cpu().numpy()) < 1e-5
