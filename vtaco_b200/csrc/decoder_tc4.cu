@@ -150,9 +150,31 @@ __global__ void __launch_bounds__(kT4Threads, 1) decoder_tc4_kernel(const __grid
 
   const bool cimg = P.use_img && P.c_img;   // per-query tactile feature tensor (decoder.py:83-85)
   // ---- one-time setup: operand blocks + bias vectors (contiguous in wtc), small vectors, barriers, TMEM ----
+  // The 165 KB of operand blocks + bias vectors arrive by TMA bulk copies (cp.async.bulk ... mbarrier::complete_tx)
+  // issued by one thread; they land while the CTA allocates TMEM and gathers its first tile, and every thread waits
+  // for them once, just before the first MMA issue (the plain load / store loop stood in front of everything: a few
+  // microseconds per launch, 10 % of a training-shape call and 1 % of an 8-GPU slab).
   const int wtc_floats = (3 * nb + 1) * (kT4MatBytes / 4) + (2 * nb + 1) * 32;
-  for (int i = tid; i < wtc_floats / 4; i += kT4Threads)
-    reinterpret_cast<float4*>(sWtc)[i] = __ldg(reinterpret_cast<const float4*>(wtc) + i);
+  const uint32_t wbar = smem_u32(sBars + kT4Groups);
+  const bool w_tma = (reinterpret_cast<uintptr_t>(wtc) & 15) == 0;
+  if (w_tma) {
+    if (tid == 0) {
+      mbar_init(wbar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      const uint32_t total = (uint32_t)wtc_floats * 4u;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(wbar), "r"(total) : "memory");
+      for (uint32_t off = 0; off < total; off += 32768u) {
+        const uint32_t bytes = min(32768u, total - off);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         smem_u32(sWtc) + off),
+                     "l"(reinterpret_cast<const char*>(wtc) + off), "r"(bytes), "r"(wbar)
+                     : "memory");
+      }
+    }
+  } else {
+    for (int i = tid; i < wtc_floats / 4; i += kT4Threads)
+      reinterpret_cast<float4*>(sWtc)[i] = __ldg(reinterpret_cast<const float4*>(wtc) + i);
+  }
   // the fc_p operand blocks follow the bias vectors in wtc: [fc_p B1 | B2 | fc_p_img B1 | B2], 256 floats each
   for (int i = tid; i < 512; i += kT4Threads) sPw[i] = __ldg(wtc + wtc_floats + (P.use_img ? 512 : 0) + i);
   for (int i = tid; i < 128; i += kT4Threads) {
@@ -392,6 +414,7 @@ __global__ void __launch_bounds__(kT4Threads, 1) decoder_tc4_kernel(const __grid
         a[7] = 0u;
         tmem_st8(tX, a);
       }
+      if (w_tma && step == 0) mbar_wait(wbar, 0);   // the operand blocks have landed (first tile of the group only)
       tc_wait_st();
       tc_fence_before();
       group_sync();
@@ -583,6 +606,7 @@ __global__ void __launch_bounds__(kT4Threads, 1) decoder_tc4_kernel(const __grid
     atomicMin(P.minmax_key, sMM[2 * warp]);
     atomicMax(P.minmax_key + 1, sMM[2 * warp + 1]);
   }
+  if (w_tma && tid == 0) mbar_wait(wbar, 0);        // a group without tiles never waited: no bulk copy may outlive the CTA
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
