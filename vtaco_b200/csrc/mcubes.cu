@@ -189,12 +189,18 @@ __global__ void __launch_bounds__(kMcThreads) mc_fused_kernel(const __grid_const
   __shared__ uint8_t s_tricount[256];
   __shared__ unsigned s_wexcl[kMcSub * kWarps];
   __shared__ unsigned s_rows[kMcBlockRuns];
-  if (threadIdx.x == 0) s_bid = (int)atomicAdd(P.ctrl, 1u);      // ticket: all blocks before this one have started
   s_tricount[threadIdx.x] = (uint8_t)__ldg(kMcTriCount + threadIdx.x);
-  __syncthreads();
-  const int b = s_bid;
   const float level = mc_level(P);
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  // Resident CTAs draw 1 024-run blocks from a ticket counter until none is left (the grid is one wave: 2 048 blocks
+  // on 6 x 148 slots were 2.3 waves, the last one a third full).  A block's index is its ticket, so every block before
+  // it has been drawn by a CTA that is running: the look-back below cannot wait on work that has not started.
+  for (;;) {
+  __syncthreads();                                               // shared state of the previous block is no longer read
+  if (threadIdx.x == 0) s_bid = (int)atomicAdd(P.ctrl, 1u);
+  __syncthreads();
+  const int b = s_bid;
+  if (b >= P.nblocks) break;
   // ---- classify kMcSub runs per thread (run = block base + s * 256 + thread: coalesced, lattice order = (s, thread));
   //      no barrier between them, so the loads of all four runs are in flight together ----
   //      A run needs the "above" bits of rows (i,j), (i+1,j), (i,j+1), (i+1,j+1); the last two are the first two of
@@ -327,6 +333,7 @@ __global__ void __launch_bounds__(kMcThreads) mc_fused_kernel(const __grid_const
     const unsigned slot = atomicAdd(P.ctrl + 1, 1u);
     P.work[slot] = make_uint2((unsigned)run, (unsigned)tb);
   }
+  }   // next ticket
 }
 
 // id of the vertex on axis `a` owned by point (i,j,k): the run's base + the vertices of the points before it
@@ -545,7 +552,10 @@ extern "C" int vtaco_marching_cubes(const vtaco_mc_args* a, void* stream) {
   P.emit = (a->phase & 2) ? 1 : 0;
   if (!P.emit) P.vcap = 0;
   VTACO_CUDA_CHECK(cudaMemsetAsync(P.state, 0, 8ll * P.nblocks + 16, st));
-  mc_fused_kernel<<<P.nblocks, kMcThreads, 0, st>>>(P);
+  {
+    const int resident = num_sms() * 6;     // 40 registers, 4.5 KB of shared memory: 6 CTAs per SM
+    mc_fused_kernel<<<P.nblocks < resident ? P.nblocks : resident, kMcThreads, 0, st>>>(P);
+  }
   if (P.emit) {
     long long blocks = (long long)num_sms() * 8;   // 8 lanes per work item; the kernel strides over the list
     if (blocks > (P.nruns * 8 + kMcThreads - 1) / kMcThreads) blocks = (P.nruns * 8 + kMcThreads - 1) / kMcThreads;
