@@ -12,7 +12,8 @@
 //   * a 32x32 product is  hi*W_hi + hi*W_lo  (kind::tf32, 4 + 4 MMAs of K = 8)  +  lo*bf16(W)
 //     (kind::f16, 2 MMAs of K = 16): 10 MMAs instead of 12, error terms ~2^-19 relative
 //     (bf16 rounding of lo and of W under a 2^-10 factor; the dropped lo*W_lo is 2^-21);
-//   * biases are added on the CUDA cores (the ones-block of the 3-tile kernel costs 8 columns);
+//   * biases need no ones-block (8 columns in the 3-tile kernel): a thread writes the NEXT step's bias into its own
+//     accumulator columns right after reading them (one tcgen05.st.x16), and every MMA of a step accumulates;
 //   * columns per tile: C_hi 0 | C_lo 32 | X_hi 48 | X_lo 80 | D 96..127.
 // Everything else (two threads per query, separable dense gather, step structure, elected
 // issuer rotating over the warps of a group) is decoder_tc2_kernel's.
@@ -90,6 +91,20 @@ __device__ __forceinline__ void split_store_t4(uint32_t tblk, int hv, const floa
   }
   tmem_st16(tblk + 16 * hv, hi);
   tmem_st8(tblk + 32 + 8 * hv, lo);
+}
+
+// The bias of the NEXT accumulation step goes into the accumulator columns as soon as this thread has read them
+// (its own lane, its own 16 columns): the step's MMAs then all accumulate, and neither the bias add after the
+// tcgen05.ld nor its operand loads are needed — one tcgen05.st.x16 replaces eight packed adds.
+__device__ __forceinline__ void store_bias16(uint32_t taddr, const float* __restrict__ b) {
+  uint32_t v[16];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float4 bb = reinterpret_cast<const float4*>(b)[j];
+    v[4 * j] = __float_as_uint(bb.x); v[4 * j + 1] = __float_as_uint(bb.y);
+    v[4 * j + 2] = __float_as_uint(bb.z); v[4 * j + 3] = __float_as_uint(bb.w);
+  }
+  tmem_st16(taddr, v);
 }
 
 // Shared-memory descriptor of a B block `units` 16-byte units after the block described by `lo`:
@@ -465,6 +480,7 @@ __global__ void __launch_bounds__(kT4Threads, 1) decoder_tc4_kernel(const __grid
       tc_wait_ld();
 #pragma unroll
       for (int j = 0; j < 16; ++j) net[j] = __uint_as_float(r[j]);
+      if (nb > 0) store_bias16(tD + ch0, sBias + 1 * 32 + ch0);      // b0_0 for the first W0 step
     }
     if (cimg) {   // c_img occupies the X columns: the 3-wide layer runs on the CUDA cores
       const float4* w0 = reinterpret_cast<const float4*>(sSmall + ch0);
@@ -506,55 +522,49 @@ __global__ void __launch_bounds__(kT4Threads, 1) decoder_tc4_kernel(const __grid
       T4_STAMP(4);   // group barrier passed
       if (wq == (step & 7) && elect_one()) {     // D = relu(net)*W0_i
         tc_fence_after();
-        issue_product_t4(mD, mX, wlo0 + (uint32_t)(3 * i + 1) * kMatUnits, 0);
+        issue_product_t4(mD, mX, wlo0 + (uint32_t)(3 * i + 1) * kMatUnits, 1);   // D already holds b0_i
         tc_commit(bar);
         T4_STAMP(20);  // issuer only: MMAs + commit issued
       }
       ++step;
       T4_STAMP(5);
-      const float4* b0 = reinterpret_cast<const float4*>(sBias + (2 * i + 1) * 32 + ch0);
       mma_wait();
       T4_STAMP(6);   // MMAs complete
       tc_fence_after();
       tmem_ld16(tD + ch0, r);
       tc_wait_ld();
       T4_STAMP(7);   // accumulator in registers
-      {                                           // h = relu(D + b0_i), packed adds
+      {                                           // h = relu(D)   (D = b0_i + relu(net) W0_i)
         float y[16];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 bb = b0[j];
-          const float2 s0 = __fadd2_rn(make_float2(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1])), make_float2(bb.x, bb.y));
-          const float2 s1 = __fadd2_rn(make_float2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), make_float2(bb.z, bb.w));
-          const float2 v0 = relu2(s0), v1 = relu2(s1);
-          y[4 * j] = v0.x; y[4 * j + 1] = v0.y; y[4 * j + 2] = v1.x; y[4 * j + 3] = v1.y;
+        for (int j = 0; j < 8; ++j) {
+          const float2 v = relu2(make_float2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1])));
+          y[2 * j] = v.x; y[2 * j + 1] = v.y;
         }
         split_store_t4(tX, hv, y);
       }
+      store_bias16(tD + ch0, sBias + (2 * i + 2) * 32 + ch0);       // b1_i + bc_{i+1} for the W1 step
       tc_wait_st();
       tc_fence_before();
       group_sync();
       if (wq == (step & 7) && elect_one()) {     // D = relu(h)*W1_i [+ C*Wc_{i+1}]
         tc_fence_after();
-        issue_product_t4(mD, mX, wlo0 + (uint32_t)(3 * i + 2) * kMatUnits, 0);
+        issue_product_t4(mD, mX, wlo0 + (uint32_t)(3 * i + 2) * kMatUnits, 1);   // D already holds b1_i + bc_{i+1}
         if (P.has_c && i + 1 < nb) issue_product_t4(mD, mC, wlo0 + (uint32_t)(3 * i + 3) * kMatUnits, 1);
         tc_commit(bar);
       }
       ++step;
-      const float4* b1 = reinterpret_cast<const float4*>(sBias + (2 * i + 2) * 32 + ch0);
       mma_wait();
       tc_fence_after();
       tmem_ld16(tD + ch0, r);
       tc_wait_ld();
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {               // net += D + (b1_i + bc_{i+1}), packed adds
-        const float4 bb = b1[j];
-        const float2 s0 = __fadd2_rn(make_float2(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1])), make_float2(bb.x, bb.y));
-        const float2 s1 = __fadd2_rn(make_float2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), make_float2(bb.z, bb.w));
-        const float2 n0 = __fadd2_rn(make_float2(net[4 * j], net[4 * j + 1]), s0);
-        const float2 n1 = __fadd2_rn(make_float2(net[4 * j + 2], net[4 * j + 3]), s1);
-        net[4 * j] = n0.x; net[4 * j + 1] = n0.y; net[4 * j + 2] = n1.x; net[4 * j + 3] = n1.y;
+      for (int j = 0; j < 8; ++j) {               // net += D   (D = b1_i + bc_{i+1} + relu(h) W1_i + c Wc_{i+1}), packed adds
+        const float2 n0 = __fadd2_rn(make_float2(net[2 * j], net[2 * j + 1]),
+                                     make_float2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1])));
+        net[2 * j] = n0.x; net[2 * j + 1] = n0.y;
       }
+      if (i + 1 < nb) store_bias16(tD + ch0, sBias + (2 * i + 3) * 32 + ch0);   // b0_{i+1} for the next W0 step
     }
 
     T4_STAMP(19);    // blocks done
