@@ -136,7 +136,9 @@ __device__ __forceinline__ void issue_product_t4(uint32_t d, uint32_t a_hi, uint
       trace[trace_n++] = ((long long)(slot) << 56) | (clock64() & 0x00ffffffffffffffll); \
   } while (0)
 
-template <bool DENSE, bool TRACE>
+// NB > 0: the network depth as a compile-time constant (the shipped 5): the block loop is unrolled and the operand
+// descriptors of every step are base + immediate
+template <bool DENSE, bool TRACE, int NB>
 __global__ void __launch_bounds__(kT4Threads, 1) decoder_tc4_kernel(const __grid_constant__ DecParams P,
                                                                     const float* __restrict__ wtc,
                                                                     long long* __restrict__ trace) {
@@ -160,7 +162,7 @@ __global__ void __launch_bounds__(kT4Threads, 1) decoder_tc4_kernel(const __grid
   const int g = warp >> 3, wq = warp & 7;   // group (tile slot), warp within the group
   const int lq = wq & 3, hv = wq >> 2;      // TMEM lane quarter (== warp % 4), channel half
   const int tq = lq * 32 + lane;            // query within the tile == TMEM lane
-  const int nb = P.n_blocks;
+  const int nb = NB > 0 ? NB : P.n_blocks;
   const int nx = P.nx;
 
   const bool cimg = P.use_img && P.c_img;   // per-query tactile feature tensor (decoder.py:83-85)
@@ -503,7 +505,8 @@ __global__ void __launch_bounds__(kT4Threads, 1) decoder_tc4_kernel(const __grid
 
     // ---------------- residual blocks: 2 accumulation steps each ----------------
     uint32_t r[16];
-    for (int i = 0; i < nb; ++i) {
+#pragma unroll
+    for (int i = 0; i < (NB > 0 ? NB : nb); ++i) {
       T4_STAMP(1);   // ALU phase starts (accumulator already read)
       {
         float y[16];
@@ -643,12 +646,14 @@ int launch_decoder_tc4(DecParams P, bool dense, const float* wtc, cudaStream_t s
   if (L.total > 227 * 1024) return VTACO_ERR_UNSUPPORTED;
   using Kernel = void (*)(DecParams, const float*, long long*);
   static const bool want_trace = getenv("VTACO_TC_TRACE") != nullptr;
-  const Kernel k = want_trace ? (dense ? (Kernel)decoder_tc4_kernel<true, true> : (Kernel)decoder_tc4_kernel<false, true>)
-                              : (dense ? (Kernel)decoder_tc4_kernel<true, false> : (Kernel)decoder_tc4_kernel<false, false>);
-  static std::atomic<size_t> configured[4][64];   // idempotent opt-in cache, safe across host threads
+  const bool nb5 = P.n_blocks == 5;
+  const Kernel k = want_trace ? (dense ? (Kernel)decoder_tc4_kernel<true, true, 0> : (Kernel)decoder_tc4_kernel<false, true, 0>)
+                   : nb5 ? (dense ? (Kernel)decoder_tc4_kernel<true, false, 5> : (Kernel)decoder_tc4_kernel<false, false, 5>)
+                         : (dense ? (Kernel)decoder_tc4_kernel<true, false, 0> : (Kernel)decoder_tc4_kernel<false, false, 0>);
+  static std::atomic<size_t> configured[8][64];   // idempotent opt-in cache, safe across host threads
   int dev = 0;
   VTACO_CUDA_CHECK(cudaGetDevice(&dev));
-  const int ki = (dense ? 1 : 0) + (want_trace ? 2 : 0);
+  const int ki = (dense ? 1 : 0) + (want_trace ? 2 : 0) + ((nb5 && !want_trace) ? 4 : 0);
   if (configured[ki][dev & 63].load(std::memory_order_relaxed) < (size_t)L.total) {
     VTACO_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
     configured[ki][dev & 63].store(L.total, std::memory_order_relaxed);
