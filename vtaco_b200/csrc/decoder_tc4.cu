@@ -14,9 +14,14 @@
 //     (bf16 rounding of lo and of W under a 2^-10 factor; the dropped lo*W_lo is 2^-21);
 //   * biases need no ones-block (8 columns in the 3-tile kernel): a thread writes the NEXT step's bias into its own
 //     accumulator columns right after reading them (one tcgen05.st.x16), and every MMA of a step accumulates;
-//   * columns per tile: C_hi 0 | C_lo 32 | X_hi 48 | X_lo 80 | D 96..127.
-// Everything else (two threads per query, separable dense gather, step structure, elected
-// issuer rotating over the warps of a group) is decoder_tc2_kernel's.
+//   * columns per tile: C_hi 0 | C_lo 32 | X_hi 48 | X_lo 80 | D 96..127;
+//   * the 3-wide input layer is two K = 8 MMAs as well (A = (p, 1, p_lo, 0) in the X columns of step 0);
+//   * the 165 KB of operand blocks arrive by TMA bulk copies that overlap TMEM allocation and the first gather;
+//   * with 8 warps per scheduler, time follows the instruction count: packed FADD2 / FFMA2 arithmetic,
+//     2*relu(x) = x + |x| (half-scaled fc_0 / fc_1), 16-wide tcgen05.st, descriptors as base + immediate, the
+//     network depth 5 as a compile-time constant, one polling warp per tile (DESIGN.md 4.1 has the measurements).
+// Two threads per query, the separable dense gather, the step structure and the elected issuer rotating over
+// the warps of a group are decoder_tc2_kernel's.
 #include "decoder_tc_common.cuh"
 #include <cstdio>
 #include <cstdlib>
@@ -60,25 +65,9 @@ __device__ __forceinline__ float2 relu2(float2 x) {   // FADD2 with an |.| opera
   return __fadd2_rn(x, make_float2(fabsf(x.x), fabsf(x.y)));
 }
 
-// Eight channels [16*hv + 8*h, +8) of x (already activated) -> operand columns of the block at `tblk`:
-// hi (tf32 container: x with the 13 low mantissa bits cleared) at tblk + 16*hv + 8*h, lo = bf16(x - hi),
-// two per column, at tblk + 32 + 8*hv + 4*h.  x - hi is formed as fma(hi, -1, x) on register pairs
-// (FFMA2: one instruction per two channels).
-__device__ __forceinline__ void split_store8(uint32_t tblk, int hv, int h, const float (&x)[8]) {
-  uint32_t hi[8], lo[4];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) hi[j] = trunc_tf32(x[j]);
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    const float2 d = __ffma2_rn(make_float2(__uint_as_float(hi[2 * c]), __uint_as_float(hi[2 * c + 1])),
-                                make_float2(-1.0f, -1.0f), make_float2(x[2 * c], x[2 * c + 1]));
-    lo[c] = pack_bf16(d.x, d.y);
-  }
-  tmem_st8(tblk + 16 * hv + 8 * h, hi);
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%4], {%0,%1,%2,%3};" ::"r"(lo[0]), "r"(lo[1]), "r"(lo[2]),
-               "r"(lo[3]), "r"(tblk + 32 + 8 * hv + 4 * h)
-               : "memory");
-}
+// Channels [16*hv, 16*hv + 16) of x (already activated) -> operand columns of the block at `tblk`: hi (tf32
+// container: x with the 13 low mantissa bits cleared) at tblk + 16*hv, lo = bf16(x - hi), two per column, at
+// tblk + 32 + 8*hv.  x - hi is formed as fma(hi, -1, x) on register pairs (FFMA2: one instruction per two channels).
 __device__ __forceinline__ void split_store_t4(uint32_t tblk, int hv, const float (&x)[16]) {
   uint32_t hi[16], lo[8];
 #pragma unroll
