@@ -1,7 +1,11 @@
-"""Multi-GPU plumbing of the dense extraction: x-slab partition of the lattice, all-gather
-of the logit slabs and min/max exchange for the iso-level (torch.distributed; NCCL over
-NVLink on the GPU box, gloo in the CPU tests).  SURVEY.md §8e.  The reference is
-single-GPU (train.py:29) — there is nothing to mirror here."""
+"""Multi-GPU plumbing of the dense extraction: x-slab partition of the lattice and the
+exchanges that follow a sharded decode —
+  * `MeshExchange` (default): per-slab marching cubes, iso-level agreement and gather of the mesh pieces by
+    device-side signalling over symmetric memory (csrc/exchange.cu);
+  * `FusedExchange`, `RootExchange`: the round-1 logit exchanges (decoder epilogue stores / bulk peer copies);
+  * `all_gather_slabs`, `all_reduce_minmax`: plain torch.distributed collectives (NCCL over NVLink on the GPU
+    box, gloo in the CPU tests).
+The reference is single-GPU (train.py:29) — there is nothing to mirror here."""
 import torch
 import torch.distributed as dist
 
