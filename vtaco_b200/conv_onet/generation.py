@@ -294,10 +294,14 @@ class Generator3D(object):
         return self.mc(grid, level=level, level_keys=keys, sync=sync)
 
     def sharded_mesh(self, c, tips=None, c_img_all=None, group=None):
-        """exchange='mesh' ("gather of mesh pieces"): every rank decodes its x-slab plus two
-        halo rows into its LOCAL grid, the ranks agree on the iso-level (16 B each), every rank runs
-        marching cubes on its slab and the pieces are concatenated into the destination rank(s) —
-        vertex / face order and ids identical to the single-GPU mesh.  No host synchronisation;
+        """exchange='mesh' ("gather of mesh pieces"): every rank decodes its x-slab into its
+        grid (symmetric memory), the ranks agree on the iso-level (16 B each), every rank runs marching
+        cubes on its slab — the two halo rows it needs are read in place from the next rank's grid
+        (`halo_from_peer`; False: decoded locally as well) — and the pieces are concatenated into the
+        destination rank(s): vertex / face order and ids identical to the single-GPU mesh.  Hazards: the
+        level rendezvous orders every rank's decode before any peer read; the count rendezvous inside
+        `ex.push` keeps a rank from starting its next decode while a neighbour still reads its rows.
+        No host synchronisation;
         returns (vertex buffer, face buffer, int64[2] totals) of vdist.MeshExchange (valid on the
         destination ranks)."""
         nx = self.resolution0 * 4
