@@ -50,6 +50,24 @@ def test_shipped_yaml_kwargs_accepted():
         encoder_dict['pointnet_local_pool'](c_dim=32, hidden_dim=32, out_mano=True, out_dim=51)
 
 
+def test_invalidate_reaches_every_packed_weight_cache():
+    """the packed-operand caches are keyed on (data_ptr, _version), which `param.data`
+    updates do not change — `invalidate()` is the documented way out and has to reach the UNets' caches too."""
+    from vtaco_b200.encoder import encoder_dict
+    e = encoder_dict['pointnet_local_pool'](dim=3, c_dim=32, padding=0.1, hidden_dim=32, plane_type=['grid', 'xz'],
+                                            grid_resolution=16, plane_resolution=16, unet=True,
+                                            unet_kwargs=dict(depth=2, start_filts=32), unet3d=True,
+                                            unet3d_kwargs=dict(num_levels=2, f_maps=32, in_channels=32, out_channels=32))
+    e.unet.__dict__['_wcache'] = {'stale': 1}
+    e.unet3d._wcache = {'stale': 1}
+    e._pack_cache = ('stale', None)
+    e.invalidate()
+    assert e.unet.__dict__['_wcache'] == {} and e.unet3d._wcache == {} and e._pack_cache is None
+    e.unet3d._wcache = {'stale': 1}
+    e.load_state_dict(e.state_dict())          # load_state_dict / .to() invalidate on their own
+    assert e.unet3d._wcache == {}
+
+
 def test_fc1_zero_init_like_reference():
     from vtaco_b200.layers import ResnetBlockFC
     b = ResnetBlockFC(64, 32)

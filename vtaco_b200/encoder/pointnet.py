@@ -181,6 +181,10 @@ class LocalPoolPointnet(nn.Module):
         self._pack_cache = None
         self._pack_params = None
         self.__dict__['_desc_cache'] = {}
+        for name in ('unet', 'unet3d'):      # their packed convolution weights follow the same keying
+            m = getattr(self, name, None)
+            if m is not None and hasattr(m, 'invalidate'):
+                m.invalidate()
 
     def _apply(self, fn, *args, **kwargs):
         self.invalidate()

@@ -103,6 +103,11 @@ class UNet(nn.Module):
         H, W = x.shape[2:]
         return H % (2 ** (self.depth - 1)) == 0 and W % (2 ** (self.depth - 1)) == 0
 
+    def invalidate(self):
+        """Drop the packed-weight cache (keyed on (data_ptr, _version) of each weight / bias: an update made through
+        `param.data` does not bump `_version` — call this after one; LocalPoolPointnet.invalidate() does)."""
+        self.__dict__['_wcache'] = {}
+
     def _packed(self, key, conv, kind):
         """operand buffers of a layer, cached per parameter version: (packed weights, bias)."""
         ver = (conv.weight.data_ptr(), conv.weight._version, conv.bias.data_ptr(), conv.bias._version)

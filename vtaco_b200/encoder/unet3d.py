@@ -179,6 +179,12 @@ class UNet3D(nn.Module):
         D, H, W = x.shape[2:]
         return ok and all(d % (2 ** n_pool) == 0 for d in (D, H, W))
 
+    def invalidate(self):
+        """Drop the packed-weight cache (keyed on (data_ptr, _version) of each weight: an update made through
+        `param.data` does not bump `_version` — call this after one; LocalPoolPointnet.invalidate() does)."""
+        self._wcache = {}
+        self._fusable_static = None
+
     def _packed(self, conv):
         key = (id(conv), conv.weight.data_ptr(), conv.weight._version)
         hit = self._wcache.get(id(conv))
