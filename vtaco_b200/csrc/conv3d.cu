@@ -487,6 +487,9 @@ extern "C" int vtaco_conv3d_cl(const vtaco_conv3d_args* a, void* stream) {
   P.tiles_y = (a->H + kCvTileY - 1) / kCvTileY;
   const long long tiles = (long long)P.tiles_x * P.tiles_y * a->D;
   if (tiles > 0x7fffffffll || a->Cout / 32 > 65535 || a->N > 65535) return VTACO_ERR_UNSUPPORTED;
+  // the kernel keeps voxel indices (n, z, y, x flattened) of both inputs in 32-bit integers
+  if ((long long)a->N * a->D * a->H * a->W > 0x7fffffffll) return VTACO_ERR_UNSUPPORTED;
+  if (a->C2 > 0 && (long long)a->N * a->D2 * a->H2 * a->W2 > 0x7fffffffll) return VTACO_ERR_UNSUPPORTED;
   P.n_tiles = (int)tiles;
   const CvSmem L = cv_layout(a->ksize, kz, Cin);
   if (L.total > 227 * 1024) return VTACO_ERR_UNSUPPORTED;
