@@ -613,7 +613,8 @@ def run_ours(args, rank, local_rank, world):
             passes = (2.0 + tf32_peak / bf16_now) if four else 2.0 if mixed else 3.0
             alg_tflops = achieved / 1e12
             ceiling = tf32_peak / passes
-            # executed tensor work (bias K-blocks and K padding included), reported separately, NOT the fraction:
+            # executed tensor work (every MMA issued: split products, bias K-blocks / K padding of the older variants),
+            # reported separately, NOT the fraction:
             tf32_mmas = 8 * (3 * nb_) + 2 if four else (4 if mixed else 12) * (3 * nb_) + (2 * nb_ + 1)
             bf16_mmas = 2 * (3 * nb_) if four else 4 * (3 * nb_) if mixed else 0
             tf32_fpq = tf32_mmas * 128 * 32 * 8 * 2 / 128.0
@@ -640,7 +641,10 @@ def run_ours(args, rank, local_rank, world):
                                            % os.path.basename(prof),
                             frac_if_counted_as_3_tf32_passes=alg_tflops / (tf32_peak / 3.0),
                             note='frac = algorithmic FLOPs (30 976 per query) x passes / kernel time / measured TF32 peak; '
-                                 'executed_* also counts the bias K-blocks and K padding the kernel issues')
+                                 + ('executed_* counts every MMA the kernel issues: three products per 32x32 matrix '
+                                    '(hi*W_hi, hi*W_lo, lo*bf16(W)) and the two K = 8 blocks of the input layer'
+                                    if four else
+                                    'executed_* also counts the bias K-blocks and K padding the kernel issues'))
         else:
             roofline = dict(common, bound='fp32', kernel='decoder_kernel<dense> (SIMT)', achieved=achieved / 1e12,
                             peak=fp32_peak / 1e12, unit='TFLOP/s', frac=achieved / fp32_peak,
